@@ -1,0 +1,142 @@
+/*
+ * simplenerf_b200 -- C ABI of the B200-native SimpleNeRF volumetric-rendering hot path.
+ *
+ * The reference (NagabhushanSN95/SimpleNeRF) is pure PyTorch and has no FFI; the "interface each
+ * entry point replaces" is therefore the Python function of src/models/SimpleNeRF01.py cited
+ * beside it.  The host-side mirror of that interface (same class contract as the reference's
+ * models.SimpleNeRF01.SimpleNeRF) is simplenerf_b200/models/FusedSimpleNeRF01.py, which binds
+ * these symbols through ctypes.
+ *
+ * Conventions
+ *   - every function returns an int status (SNERF_OK == 0); nothing throws across the ABI;
+ *     snerf_last_error() returns a thread-local message for the last non-zero status;
+ *   - all pointers are DEVICE pointers (unless named host_*), 16-byte aligned, row-major, fp32;
+ *   - the caller allocates every buffer including workspaces; the library never allocates device
+ *     memory and never synchronises: kernels are enqueued on `stream` (a cudaStream_t);
+ *   - "nullable" pointers switch the corresponding optional input/output off.
+ */
+#ifndef SIMPLENERF_B200_H
+#define SIMPLENERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNERF_OK 0
+#define SNERF_ERR_INVALID 1    /* bad argument (message says which)            */
+#define SNERF_ERR_CUDA 2       /* a CUDA runtime call / launch failed            */
+#define SNERF_ERR_UNSUPPORTED 3 /* shape outside what the kernels are built for  */
+
+#define SNERF_ABI_VERSION 1
+
+/* Shape of one reference `MLP` (ctor src/models/SimpleNeRF01.py:561-609). */
+typedef struct snerf_mlp_desc {
+    int32_t depth;        /* points_net_depth (8)                                              */
+    int32_t width;        /* points_net_width (256)                                            */
+    int32_t skip_layer;   /* skip concat happens after this trunk layer (4), :580              */
+    int32_t pts_degree;   /* points_positional_encoding_degree (10)                            */
+    int32_t trunk_degree; /* PE bands fed to the sigma trunk: 10, or 3 for points-augmentation
+                             (points_sigma_positional_encoding_degree, :576-578)               */
+    int32_t view_degree;  /* views_positional_encoding_degree (4); 0 when use_view_dirs=False  */
+    int32_t view_width;   /* views_net_width (128); 0 when there is no view branch             */
+    int32_t head_out;     /* pts_output_linear rows: 1 (sigma) or 4 (sigma+rgb, views-aug)     */
+} snerf_mlp_desc;
+
+/* Order of the fp32 parameter pointers handed to the MLP entry points (torch.nn.Linear layout:
+ * weight [out,in] row-major, bias [out]).  Entries of absent layers are NULL.                  */
+enum {
+    SNERF_P_TRUNK_W0 = 0, /* pts_linears.i.weight at 2*i, .bias at 2*i+1, i < 8               */
+    SNERF_P_HEAD_W = 16,  /* pts_output_linear                                                 */
+    SNERF_P_HEAD_B = 17,
+    SNERF_P_FEAT_W = 18,  /* feature_linear                                                    */
+    SNERF_P_FEAT_B = 19,
+    SNERF_P_VIEW_W = 20,  /* views_linears.0                                                   */
+    SNERF_P_VIEW_B = 21,
+    SNERF_P_RGB_W = 22,   /* views_output_linear                                               */
+    SNERF_P_RGB_B = 23,
+    SNERF_P_COUNT = 24
+};
+
+/* flags */
+#define SNERF_FLAG_NDC 1u          /* z is NDC depth; use rays_d_ndc for delta, convert depth (:437-441, :456-460) */
+#define SNERF_FLAG_WHITE_BKGD 2u   /* rgb += 1 - acc (:462-463)                                  */
+#define SNERF_FLAG_LINDISP 4u      /* sample linearly in disparity (:288-289)                    */
+#define SNERF_FLAG_SAVE_FOR_BWD 8u /* MLP forward keeps activations in the workspace             */
+#define SNERF_FLAG_PRECISE 16u     /* fp32 CUDA-core MLP instead of the bf16 tcgen05 MLP         */
+
+int snerf_abi_version(void);
+const char* snerf_last_error(void);
+/* 1 if the library was built with the tcgen05 (sm_100a) MLP kernels. */
+int snerf_has_tensor_path(void);
+
+/* ---- a3: stratified coarse sampling (get_z_vals_coarse, :272-302) --------------------------
+ * t_vals [n_samples] = torch.linspace(0,1,n_samples) (computed by the host exactly as the
+ * reference does); near/far [n_rays]; t_rand [n_rays,n_samples] nullable (NULL = no perturb).  */
+int snerf_sample_coarse(const float* near, const float* far, const float* t_vals, const float* t_rand,
+                        float* z_out, int n_rays, int n_samples, uint32_t flags, void* stream);
+
+/* ---- a11+a12: hierarchical resampling (get_z_vals_fine :304-315, sample_pdf :328-361) ------
+ * z_coarse, weights_coarse [n_rays,s_coarse]; u [n_rays or 1, n_new] with row stride u_stride
+ * (0 = one row broadcast: the deterministic linspace).  z_fine [n_rays, s_coarse+n_new] sorted.
+ * Optional debug outputs (nullable): samples [n_rays,n_new] (unsorted, in u order),
+ * cdf [n_rays,s_coarse-1], below/above int32 [n_rays,n_new].                                   */
+int snerf_sample_fine(const float* z_coarse, const float* weights_coarse, const float* u, int u_stride,
+                      float* z_fine, float* samples_dbg, float* cdf_dbg, int32_t* below_dbg, int32_t* above_dbg,
+                      int n_rays, int s_coarse, int n_new, void* stream);
+
+/* ---- a9+a10: alpha compositing (volume_rendering :430-483, convert_depth_from_ndc :485-502) -
+ * sigma, z [n_rays,S]; rgb [n_rays,S,3]; rays_* [n_rays,3] (rays_d_ndc only with FLAG_NDC).
+ * Per-ray outputs [n_rays] / [n_rays,3]; depth_ndc / depth_var_ndc only with FLAG_NDC.
+ * Per-sample outputs alpha / visibility / weights [n_rays,S] are nullable.                     */
+int snerf_composite_forward(const float* sigma, const float* rgb, const float* z, const float* rays_o,
+                            const float* rays_d, const float* rays_d_ndc, float* rgb_map, float* acc,
+                            float* depth, float* depth_var, float* depth_ndc, float* depth_var_ndc,
+                            float* alpha, float* visibility, float* weights, int n_rays, int n_samples,
+                            uint32_t flags, void* stream);
+
+/* Backward of the above.  Incoming gradients (all nullable): d_rgb_map [n,3], d_acc, d_depth,
+ * d_depth_var, d_depth_ndc, d_depth_var_ndc [n], d_alpha / d_visibility / d_weights [n,S].
+ * Outputs: d_sigma [n,S], d_rgb [n,S,3].                                                       */
+int snerf_composite_backward(const float* sigma, const float* rgb, const float* z, const float* rays_o,
+                             const float* rays_d, const float* rays_d_ndc, const float* d_rgb_map,
+                             const float* d_acc, const float* d_depth, const float* d_depth_var,
+                             const float* d_depth_ndc, const float* d_depth_var_ndc, const float* d_alpha,
+                             const float* d_visibility, const float* d_weights, float* d_sigma, float* d_rgb,
+                             int n_rays, int n_samples, uint32_t flags, void* stream);
+
+/* ---- a4-a8: point generation + positional encoding + MLP (run_network :363-428, MLP :560-715)
+ * pts = rays_o + rays_d * z is never materialised.  view_dirs [n_rays,3] (nullable when the MLP
+ * has no view branch).  sigma_noise [n_rays*S] nullable (already multiplied by raw_noise_std).
+ * host_params: HOST array of SNERF_P_COUNT device pointers.  packed: device image made by
+ * snerf_pack_weights (bf16 tensor path; ignored with FLAG_PRECISE).
+ * Outputs sigma [n_rays*S], rgb [n_rays*S,3].                                                  */
+size_t snerf_mlp_workspace_bytes(const snerf_mlp_desc* desc, int n_rays, int n_samples, uint32_t flags);
+size_t snerf_packed_weights_bytes(const snerf_mlp_desc* desc);
+int snerf_pack_weights(const snerf_mlp_desc* desc, const float* const* host_params, void* packed, void* stream);
+
+int snerf_mlp_forward(const snerf_mlp_desc* desc, const float* const* host_params, const void* packed,
+                      const float* rays_o, const float* rays_d, const float* view_dirs, const float* z,
+                      const float* sigma_noise, float* sigma, float* rgb, void* workspace, size_t workspace_bytes,
+                      int n_rays, int n_samples, uint32_t flags, void* stream);
+
+/* Backward: consumes the workspace left by a forward run with FLAG_SAVE_FOR_BWD (same desc,
+ * shapes and flags).  d_sigma [P], d_rgb [P,3] are gradients w.r.t. the forward outputs.
+ * host_grads: HOST array of SNERF_P_COUNT device pointers, same shapes as the parameters;
+ * gradients are ACCUMULATED (+=) into them (caller zeroes).  No gradient flows to rays / z.   */
+int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const* host_params, const void* packed,
+                       const float* rays_o, const float* rays_d, const float* view_dirs, const float* z,
+                       const float* sigma, const float* rgb, const float* d_sigma, const float* d_rgb,
+                       float* const* host_grads, void* workspace, size_t workspace_bytes, int n_rays,
+                       int n_samples, uint32_t flags, void* stream);
+
+/* Self-test of the tcgen05 GEMM building blocks against a CUDA-core GEMM (used by tests).
+ * Returns SNERF_OK and writes the max abs error of each mode to host_max_err[4].               */
+int snerf_tensor_selftest(float* host_max_err, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMPLENERF_B200_H */

@@ -1,0 +1,61 @@
+"""ctypes binding of include/simplenerf_b200.h.  There is no fallback: if the shared library is
+missing or a call fails, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, 'libsimplenerf_b200.so')
+
+P_COUNT = 24
+P_HEAD_W, P_HEAD_B, P_FEAT_W, P_FEAT_B, P_VIEW_W, P_VIEW_B, P_RGB_W, P_RGB_B = 16, 17, 18, 19, 20, 21, 22, 23
+FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP, FLAG_SAVE_FOR_BWD, FLAG_PRECISE = 1, 2, 4, 8, 16
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('depth', 'width', 'skip_layer', 'pts_degree', 'trunk_degree', 'view_degree',
+                                         'view_width', 'head_out')]
+
+
+_fp = C.c_void_p   # device pointers travel as integers
+_SIGNATURES = {
+    'snerf_abi_version': (C.c_int, []),
+    'snerf_last_error': (C.c_char_p, []),
+    'snerf_has_tensor_path': (C.c_int, []),
+    'snerf_sample_coarse': (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_uint32, _fp]),
+    'snerf_sample_fine': (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'snerf_composite_forward': (C.c_int, [_fp] * 15 + [C.c_int, C.c_int, C.c_uint32, _fp]),
+    'snerf_composite_backward': (C.c_int, [_fp] * 17 + [C.c_int, C.c_int, C.c_uint32, _fp]),
+    'snerf_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(MlpDesc), C.c_int, C.c_int, C.c_uint32]),
+    'snerf_packed_weights_bytes': (C.c_size_t, [C.POINTER(MlpDesc)]),
+    'snerf_pack_weights': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp), _fp, _fp]),
+    'snerf_mlp_forward': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                    C.c_size_t, C.c_int, C.c_int, C.c_uint32, _fp]),
+    'snerf_mlp_backward': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                     C.POINTER(_fp), _fp, C.c_size_t, C.c_int, C.c_int, C.c_uint32, _fp]),
+    'snerf_tensor_selftest': (C.c_int, [C.POINTER(C.c_float), _fp]),
+}
+EXPORTS = tuple(_SIGNATURES)
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: build it with `python -m simplenerf_b200.build` '
+                               '(there is no CPU or PyTorch fallback for this path)')
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.snerf_abi_version() != 1:
+            raise RuntimeError('libsimplenerf_b200.so: ABI version mismatch')
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise RuntimeError(f'{what} failed (status {status}): {load().snerf_last_error().decode()}')

@@ -1,0 +1,163 @@
+"""Tensor-level wrappers over the C ABI (include/simplenerf_b200.h).
+
+torch is plumbing here: it owns device memory and the current CUDA stream; all arithmetic happens
+in the kernels of libsimplenerf_b200.so.  Every wrapper raises if a tensor is not a contiguous
+fp32 CUDA tensor -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import FLAG_LINDISP, FLAG_NDC, FLAG_PRECISE, FLAG_SAVE_FOR_BWD, FLAG_WHITE_BKGD, MlpDesc, P_COUNT  # noqa: F401
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('simplenerf_b200 kernels need CUDA tensors (no CPU fallback exists)')
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError(f'expected a contiguous {dtype} tensor, got {t.dtype}, contiguous={t.is_contiguous()}')
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+def sample_coarse(near: torch.Tensor, far: torch.Tensor, t_vals: torch.Tensor, t_rand: Optional[torch.Tensor],
+                  lindisp: bool = False) -> torch.Tensor:
+    """get_z_vals_coarse (reference :272-302).  near/far [N,1] or [N]; t_vals [S]; t_rand [N,S] or None."""
+    n, s = near.shape[0], t_vals.shape[0]
+    near, far, t_vals = _f32(near).reshape(-1), _f32(far).reshape(-1), _f32(t_vals)
+    if t_rand is not None:
+        t_rand = _f32(t_rand)
+        assert tuple(t_rand.shape) == (n, s)
+    z = torch.empty((n, s), device=near.device, dtype=torch.float32)
+    _lib.check(_lib.load().snerf_sample_coarse(_ptr(near), _ptr(far), _ptr(t_vals), _ptr(t_rand), _ptr(z), n, s,
+                                               FLAG_LINDISP if lindisp else 0, _stream()), 'snerf_sample_coarse')
+    return z
+
+
+def sample_fine(z_coarse: torch.Tensor, weights_coarse: torch.Tensor, u: torch.Tensor, debug: bool = False):
+    """get_z_vals_fine + sample_pdf (reference :304-361).  u: [N,n_new] random draws, or [n_new] = the
+    deterministic linspace row shared by all rays."""
+    n, sc = z_coarse.shape
+    z_coarse, weights_coarse, u = _f32(z_coarse), _f32(weights_coarse), _f32(u)
+    n_new = u.shape[-1]
+    u_stride = 0 if u.dim() == 1 else n_new
+    if u.dim() == 2:
+        assert u.shape[0] == n
+    dev = z_coarse.device
+    z_fine = torch.empty((n, sc + n_new), device=dev, dtype=torch.float32)
+    dbg = {}
+    if debug:
+        dbg = dict(samples=torch.empty((n, n_new), device=dev), cdf=torch.empty((n, sc - 1), device=dev),
+                   below=torch.empty((n, n_new), device=dev, dtype=torch.int32),
+                   above=torch.empty((n, n_new), device=dev, dtype=torch.int32))
+    _lib.check(_lib.load().snerf_sample_fine(
+        _ptr(z_coarse), _ptr(weights_coarse), _ptr(u), u_stride, _ptr(z_fine), _ptr(dbg.get('samples')),
+        _ptr(dbg.get('cdf')), _ptr(dbg.get('below'), torch.int32), _ptr(dbg.get('above'), torch.int32), n, sc, n_new,
+        _stream()), 'snerf_sample_fine')
+    return (z_fine, dbg) if debug else z_fine
+
+
+# --------------------------------------------------------------------------------------------
+PER_RAY = ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc')
+PER_SAMPLE = ('alpha', 'visibility', 'weights')
+
+
+def composite_forward(sigma, rgb, z, rays_o, rays_d, rays_d_ndc, ndc: bool, white_bkgd: bool = False,
+                      per_sample: Sequence[str] = PER_SAMPLE) -> Dict[str, torch.Tensor]:
+    """volume_rendering (reference :430-483).  sigma, z [N,S]; rgb [N,S,3]."""
+    n, s = z.shape
+    dev = z.device
+    out = {'rgb': torch.empty((n, 3), device=dev), 'acc': torch.empty(n, device=dev),
+           'depth': torch.empty(n, device=dev), 'depth_var': torch.empty(n, device=dev)}
+    if ndc:
+        out['depth_ndc'] = torch.empty(n, device=dev)
+        out['depth_var_ndc'] = torch.empty(n, device=dev)
+    for k in per_sample:
+        out[k] = torch.empty((n, s), device=dev)
+    flags = (FLAG_NDC if ndc else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0)
+    _lib.check(_lib.load().snerf_composite_forward(
+        _ptr(sigma), _ptr(rgb), _ptr(z), _ptr(rays_o), _ptr(rays_d), _ptr(rays_d_ndc) if ndc else None,
+        _ptr(out['rgb']), _ptr(out['acc']), _ptr(out['depth']), _ptr(out['depth_var']), _ptr(out.get('depth_ndc')),
+        _ptr(out.get('depth_var_ndc')), _ptr(out.get('alpha')), _ptr(out.get('visibility')), _ptr(out.get('weights')),
+        n, s, flags, _stream()), 'snerf_composite_forward')
+    return out
+
+
+def composite_backward(sigma, rgb, z, rays_o, rays_d, rays_d_ndc, ndc: bool, white_bkgd: bool,
+                       grads: Dict[str, Optional[torch.Tensor]]):
+    """grads: optional incoming gradients keyed like composite_forward's outputs."""
+    n, s = z.shape
+    d_sigma = torch.empty((n, s), device=z.device)
+    d_rgb = torch.empty((n, s, 3), device=z.device)
+    g = {k: (None if v is None else _f32(v)) for k, v in grads.items()}
+    flags = (FLAG_NDC if ndc else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0)
+    _lib.check(_lib.load().snerf_composite_backward(
+        _ptr(sigma), _ptr(rgb), _ptr(z), _ptr(rays_o), _ptr(rays_d), _ptr(rays_d_ndc) if ndc else None,
+        _ptr(g.get('rgb')), _ptr(g.get('acc')), _ptr(g.get('depth')), _ptr(g.get('depth_var')), _ptr(g.get('depth_ndc')),
+        _ptr(g.get('depth_var_ndc')), _ptr(g.get('alpha')), _ptr(g.get('visibility')), _ptr(g.get('weights')),
+        _ptr(d_sigma), _ptr(d_rgb), n, s, flags, _stream()), 'snerf_composite_backward')
+    return d_sigma, d_rgb
+
+
+# --------------------------------------------------------------------------------------------
+def pointer_table(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (C.c_void_p * P_COUNT)()
+    for i, t in enumerate(tensors):
+        arr[i] = _ptr(t)
+    return arr
+
+
+def mlp_workspace_bytes(desc: MlpDesc, n_rays: int, n_samples: int, flags: int) -> int:
+    b = _lib.load().snerf_mlp_workspace_bytes(C.byref(desc), n_rays, n_samples, flags)
+    if b == 0:
+        raise RuntimeError(f'snerf_mlp_workspace_bytes: {_lib.load().snerf_last_error().decode()}')
+    return b
+
+
+def packed_weights_bytes(desc: MlpDesc) -> int:
+    return _lib.load().snerf_packed_weights_bytes(C.byref(desc))
+
+
+def pack_weights(desc: MlpDesc, params: Sequence[Optional[torch.Tensor]], packed: torch.Tensor) -> None:
+    _lib.check(_lib.load().snerf_pack_weights(C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _stream()),
+               'snerf_pack_weights')
+
+
+def mlp_forward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, noise, workspace, flags: int):
+    n, s = z.shape
+    sigma = torch.empty((n, s), device=z.device)
+    rgb = torch.empty((n, s, 3), device=z.device)
+    _lib.check(_lib.load().snerf_mlp_forward(
+        C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
+        _ptr(z), _ptr(noise), _ptr(sigma), _ptr(rgb), _ptr(workspace, torch.uint8), workspace.numel(), n, s, flags,
+        _stream()), 'snerf_mlp_forward')
+    return sigma, rgb
+
+
+def mlp_backward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, sigma, rgb, d_sigma, d_rgb,
+                 grads: List[Optional[torch.Tensor]], workspace, flags: int) -> None:
+    n, s = z.shape
+    _lib.check(_lib.load().snerf_mlp_backward(
+        C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
+        _ptr(z), _ptr(sigma), _ptr(rgb), _ptr(d_sigma), _ptr(d_rgb), pointer_table(grads), _ptr(workspace, torch.uint8),
+        workspace.numel(), n, s, flags, _stream()), 'snerf_mlp_backward')
+
+
+def tensor_selftest() -> List[float]:
+    errs = (C.c_float * 4)()
+    _lib.check(_lib.load().snerf_tensor_selftest(errs, _stream()), 'snerf_tensor_selftest')
+    return list(errs)

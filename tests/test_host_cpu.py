@@ -1,0 +1,88 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/simplenerf_b200.h declares, argument
+validation never reaches a kernel, and the host-side mirror of the reference interface behaves like it."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from simplenerf_b200 import _lib, build, synthetic
+from simplenerf_b200.models import get_model
+from simplenerf_b200.models.FusedSimpleNeRF01 import FusedSimpleNeRF, MlpBlock
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    header = open(os.path.join(ROOT, 'include', 'simplenerf_b200.h')).read()
+    declared = set(re.findall(r'\b(snerf_[a-z_]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.snerf_abi_version() == 1
+
+
+def test_argument_validation_without_gpu(lib):
+    assert lib.snerf_sample_coarse(None, None, None, None, None, 4, 64, 0, None) == 1
+    assert b'null' in lib.snerf_last_error()
+    assert lib.snerf_sample_fine(None, None, None, 0, None, None, None, None, None, 4, 64, 128, None) == 1
+    assert lib.snerf_composite_forward(*([None] * 15), 4, 64, 0, None) == 1
+    desc = _lib.MlpDesc(depth=8, width=128, skip_layer=4, pts_degree=10, trunk_degree=10, view_degree=4, view_width=128,
+                        head_out=1)
+    assert lib.snerf_mlp_workspace_bytes(ctypes.byref(desc), 16, 64, 0) == 0     # unsupported width
+    assert b'width' in lib.snerf_last_error()
+    good = MlpBlock(synthetic.make_configs()['model']['coarse_mlp']).desc
+    assert lib.snerf_mlp_workspace_bytes(ctypes.byref(good), 16, 64, _lib.FLAG_PRECISE | _lib.FLAG_SAVE_FOR_BWD) > 0
+    assert lib.snerf_mlp_forward(ctypes.byref(good), None, None, None, None, None, None, None, None, None, None, 0, 1, 1, 0,
+                                 None) == 1
+
+
+def test_model_factory_contract():
+    configs = synthetic.make_configs('simplenerf')
+    assert isinstance(get_model(configs, None), FusedSimpleNeRF)
+    with pytest.raises(RuntimeError, match='Unknown model'):
+        get_model(dict(configs, model=dict(configs['model'], name='Nope01')), None)
+
+
+def test_state_dict_layout_matches_survey():
+    model = get_model(synthetic.make_configs('simplenerf'), None)
+    sd = model.state_dict()
+    assert sum(v.numel() for v in sd.values()) == 2265488
+    assert tuple(sd['coarse_model.pts_linears.0.weight'].shape) == (256, 63)
+    assert tuple(sd['coarse_model.pts_linears.5.weight'].shape) == (256, 319)
+    assert tuple(sd['pts_aug_coarse_model.pts_linears.0.weight'].shape) == (256, 21)
+    assert tuple(sd['pts_aug_coarse_model.pts_linears.5.weight'].shape) == (256, 277)
+    assert tuple(sd['pts_aug_coarse_model.views_linears.0.weight'].shape) == (128, 325)
+    assert tuple(sd['views_aug_coarse_model.pts_output_linear.weight'].shape) == (4, 256)
+    assert 'views_aug_coarse_model.feature_linear.weight' not in sd
+    vanilla = get_model(synthetic.make_configs('vanilla'), None)
+    assert set(k.split('.')[0] for k in vanilla.state_dict()) == {'coarse_model', 'fine_model'}
+
+
+def test_cpu_batch_is_refused_loudly():
+    model = get_model(synthetic.make_configs('vanilla'), None)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        model(synthetic.make_ray_batch('llff', 4, 0))
+
+
+def test_unbuilt_features_raise():
+    cfg = synthetic.make_configs('vanilla')
+    cfg['model']['coarse_mlp']['predict_visibility'] = True
+    with pytest.raises(NotImplementedError):
+        get_model(cfg, None)
+
+
+def test_synthetic_rays_match_reference_geometry():
+    b = synthetic.make_ray_batch('llff', 64, 3)
+    assert torch.allclose(b['view_dirs'].norm(dim=-1), torch.ones(64), atol=1e-6)
+    # NDC origins sit on the near plane z = -1 (o2 = 1 + 2 near / oz with oz = -near)
+    assert torch.allclose(b['rays_o_ndc'][:, 2], -torch.ones(64), atol=1e-5)
+    f = synthetic.make_ray_batch('llff', 1008 * 2, 0, frame=True)
+    assert f['rays_o'].shape == (2016, 3)
