@@ -83,6 +83,8 @@ extern "C" int snerf_mlp_forward(const snerf_mlp_desc* desc, const float* const*
     if (rc != SNERF_OK) return rc;
     rc = check_params(*desc, (const void* const*)host_params, "snerf_mlp_forward");
     if (rc != SNERF_OK) return rc;
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_mlp_forward: bad sizes");
+    if (n_rays == 0) return SNERF_OK;
     SNERF_REQUIRE(rays_o && rays_d && z && sigma && rgb && workspace, "snerf_mlp_forward: null pointer");
     SNERF_REQUIRE(desc->view_degree == 0 || view_dirs != nullptr, "snerf_mlp_forward: view_dirs required by this MLP");
     SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_mlp_forward: bad sizes");
@@ -106,6 +108,8 @@ extern "C" int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const
     if (rc != SNERF_OK) return rc;
     rc = check_params(*desc, (const void* const*)host_grads, "snerf_mlp_backward(grads)");
     if (rc != SNERF_OK) return rc;
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_mlp_backward: bad sizes");
+    if (n_rays == 0) return SNERF_OK;
     SNERF_REQUIRE(sigma && rgb && d_sigma && d_rgb && workspace, "snerf_mlp_backward: null pointer");
     SNERF_REQUIRE(flags & SNERF_FLAG_SAVE_FOR_BWD, "snerf_mlp_backward: forward must have run with SNERF_FLAG_SAVE_FOR_BWD");
     SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_mlp_backward: bad sizes");

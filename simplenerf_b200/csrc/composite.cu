@@ -267,6 +267,8 @@ extern "C" int snerf_composite_forward(const float* sigma, const float* rgb, con
                                        float* alpha, float* visibility, float* weights, int n_rays, int n_samples,
                                        uint32_t flags, void* stream) {
     const bool ndc = (flags & SNERF_FLAG_NDC) != 0;
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_composite_forward: bad sizes");
+    if (n_rays == 0) return SNERF_OK;
     SNERF_REQUIRE(sigma && rgb && z && rays_d, "snerf_composite_forward: null input");
     SNERF_REQUIRE(rgb_map && acc && depth && depth_var, "snerf_composite_forward: null per-ray output");
     SNERF_REQUIRE(!ndc || (rays_o && rays_d_ndc && depth_ndc && depth_var_ndc),
@@ -287,6 +289,8 @@ extern "C" int snerf_composite_backward(const float* sigma, const float* rgb, co
                                         const float* d_visibility, const float* d_weights, float* d_sigma,
                                         float* d_rgb, int n_rays, int n_samples, uint32_t flags, void* stream) {
     const bool ndc = (flags & SNERF_FLAG_NDC) != 0;
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_composite_backward: bad sizes");
+    if (n_rays == 0) return SNERF_OK;
     SNERF_REQUIRE(sigma && rgb && z && rays_d && d_sigma && d_rgb, "snerf_composite_backward: null pointer");
     SNERF_REQUIRE(!ndc || (rays_o && rays_d_ndc), "snerf_composite_backward: NDC mode needs rays_o and rays_d_ndc");
     SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_composite_backward: bad sizes");

@@ -161,9 +161,9 @@ using namespace snerf;
 
 extern "C" int snerf_sample_coarse(const float* near, const float* far, const float* t_vals, const float* t_rand,
                                    float* z_out, int n_rays, int n_samples, uint32_t flags, void* stream) {
-    SNERF_REQUIRE(near && far && t_vals && z_out, "snerf_sample_coarse: null pointer");
     SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_sample_coarse: bad sizes (%d rays, %d samples)", n_rays, n_samples);
-    if (n_rays == 0) return SNERF_OK;
+    if (n_rays == 0) return SNERF_OK;   // empty batch: nothing to launch (pointers may be null)
+    SNERF_REQUIRE(near && far && t_vals && z_out, "snerf_sample_coarse: null pointer");
     const long long total = (long long)n_rays * n_samples;
     const int blocks = (int)((total + 255) / 256);
     sample_coarse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, t_vals, t_rand, z_out, n_rays, n_samples,
@@ -175,9 +175,10 @@ extern "C" int snerf_sample_coarse(const float* near, const float* far, const fl
 extern "C" int snerf_sample_fine(const float* z_coarse, const float* weights_coarse, const float* u, int u_stride,
                                  float* z_fine, float* samples_dbg, float* cdf_dbg, int32_t* below_dbg,
                                  int32_t* above_dbg, int n_rays, int s_coarse, int n_new, void* stream) {
-    SNERF_REQUIRE(z_coarse && weights_coarse && u && z_fine, "snerf_sample_fine: null pointer");
     SNERF_REQUIRE(n_rays >= 0 && s_coarse >= 3 && n_new >= 1, "snerf_sample_fine: bad sizes (%d rays, %d coarse, %d new)",
                   n_rays, s_coarse, n_new);
+    if (n_rays == 0) return SNERF_OK;
+    SNERF_REQUIRE(z_coarse && weights_coarse && u && z_fine, "snerf_sample_fine: null pointer");
     SNERF_REQUIRE(u_stride == 0 || u_stride >= n_new, "snerf_sample_fine: u_stride %d < n_new %d", u_stride, n_new);
     if (s_coarse + n_new > 1024) return fail(SNERF_ERR_UNSUPPORTED, "snerf_sample_fine: %d + %d samples > 1024", s_coarse, n_new);
     if (n_rays == 0) return SNERF_OK;
