@@ -1,11 +1,662 @@
-// placeholder until the tcgen05 path lands
+// bf16 tcgen05 MLP (the throughput path): positional encoding + 8x256 trunk + heads as ONE persistent,
+// warp-specialised kernel per MLP evaluation.
+//
+// Reference behaviour: src/models/SimpleNeRF01.py  run_network :363-392, PositionalEncoder :525-557,
+// MLP.forward :626-654, get_view_independent_outputs :656-685, get_view_dependent_outputs :687-715.
+//
+// Forward kernel (one CTA per SM, 128-point tiles, 352 threads):
+//   warp 0     weight loader   packed bf16 weight chunks [N x 64] stream L2 -> smem ring by bulk async copy (TMA)
+//   warp 1     MMA issuer      tcgen05.mma M=128, N=256|128, K=16; accumulators ping-pong in TMEM (2 x 256 cols)
+//   warps 2-5  epilogue        TMEM -> regs -> bias/ReLU -> bf16 -> swizzled smem panel (the next layer's A operand);
+//                              sigma / rgb heads in fp32 on CUDA cores from the un-rounded activations
+//   warps 6-9  encoder         rays + depth -> point -> positional encoding -> bf16 panel E of the NEXT tile
+//   warp 10    stash writer    (training) bulk-copies every activation panel to HBM for the backward pass
+// The epilogue hands activations to the MMA issuer panel by panel (64 columns), so layer l+1's MMAs start while
+// layer l's epilogue is still running; activations never leave the SM in eval mode.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace snerf {
-size_t tc_workspace_bytes(const MlpDims&, const snerf_mlp_desc&, int, int, uint32_t) { return 0; }
-size_t tc_packed_bytes(const snerf_mlp_desc&) { return 256; }
-int tc_pack(const snerf_mlp_desc&, const float* const*, void*, cudaStream_t) { return fail(SNERF_ERR_UNSUPPORTED, "tensor path not built"); }
-int tc_forward(const snerf_mlp_desc&, const float* const*, const void*, const float*, const float*, const float*, const float*, const float*, float*, float*, void*, size_t, int, int, uint32_t, cudaStream_t) { return fail(SNERF_ERR_UNSUPPORTED, "tensor path not built"); }
-int tc_backward(const snerf_mlp_desc&, const float* const*, const void*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, float* const*, void*, size_t, int, int, uint32_t, cudaStream_t) { return fail(SNERF_ERR_UNSUPPORTED, "tensor path not built"); }
-int tc_selftest(float*, cudaStream_t) { return fail(SNERF_ERR_UNSUPPORTED, "tensor path not built"); }
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------
+// plan: GEMM steps, packed-weight layout
+// ------------------------------------------------------------------------------------------------
+constexpr int kStages = 3;
+constexpr int kStageBytes = 32768;
+constexpr int kMaxSteps = 10;
+constexpr int kMaxChunks = 5;
+constexpr int kPanelE = 4;   // panel id of the encoding buffer
+constexpr int kPanelP = 5;   // (backward) first panel of the prologue buffer
+
+enum EpiKind : uint8_t { EPI_RELU = 0, EPI_RELU_HEAD1, EPI_RELU_HEAD4, EPI_LINEAR, EPI_VIEW };
+
+struct TcStep {
+    uint32_t w_off;               // byte offset of the first weight chunk in the packed image
+    uint16_t n_rows;              // N of the MMA (256 or 128)
+    uint8_t n_chunks;
+    uint8_t kind;
+    uint8_t panel[kMaxChunks];    // A panel per chunk
+    uint8_t ksteps[kMaxChunks];   // 16-wide K steps per chunk
+    uint8_t bias_row;             // row of the smem bias table
+    uint8_t slot;                 // stash slot of the panels this step writes
+    uint8_t last_e_use;           // this step is the last reader of panel E within a tile
+    uint8_t pad;
+};
+
+struct PackChunk {
+    const float* src;
+    int32_t ld;
+    int16_t n_rows, k_lo, k_hi, col0, row0, transposed;
+    uint32_t dst_off;
+};
+constexpr int kMaxPack = 96;
+
+struct TcPlan {
+    int n_fwd, n_bwd;
+    TcStep fwd[kMaxSteps], bwd[kMaxSteps];
+    int n_pack;
+    PackChunk pack[kMaxPack];
+    uint32_t packed_bytes;
+    uint32_t tile_stash_bytes;    // activation (and dY) stash bytes per 128-point tile
+};
+
+static void add_chunk(TcPlan& pl, TcStep& st, int panel, int ksteps, const float* src, int ld, int n_rows, int k_lo, int k_hi,
+                      int col0, int row0, bool transposed) {
+    PackChunk& c = pl.pack[pl.n_pack++];
+    c.src = src; c.ld = ld; c.n_rows = (int16_t)n_rows; c.k_lo = (int16_t)k_lo; c.k_hi = (int16_t)k_hi;
+    c.col0 = (int16_t)col0; c.row0 = (int16_t)row0; c.transposed = transposed ? 1 : 0;
+    c.dst_off = pl.packed_bytes;
+    if (st.n_chunks == 0) st.w_off = pl.packed_bytes;
+    st.panel[st.n_chunks] = (uint8_t)panel;
+    st.ksteps[st.n_chunks] = (uint8_t)ksteps;
+    st.n_chunks++;
+    pl.packed_bytes += (uint32_t)n_rows * kRowBytes;
 }
-extern "C" int snerf_has_tensor_path(void) { return 0; }
+
+// prm may be null (layout only)
+static TcPlan build_plan(const snerf_mlp_desc& d, const float* const* prm) {
+    const MlpDims m(d);
+    TcPlan pl{};
+    auto P = [&](int i) -> const float* { return prm ? prm[i] : nullptr; };
+    // ---- forward steps ----
+    for (int l = 0; l < m.depth; ++l) {
+        TcStep& st = pl.fwd[pl.n_fwd++];
+        st.n_rows = 256;
+        st.kind = EPI_RELU;
+        st.bias_row = (uint8_t)l;
+        st.slot = (uint8_t)l;
+        const int fan_in = m.trunk_fan_in(l);
+        if (l == 0) {
+            add_chunk(pl, st, kPanelE, ceil_div(m.trunk_in, 16), P(0), fan_in, 256, 0, m.trunk_in, 0, 0, false);
+        } else {
+            int col = 0;
+            if (l - 1 == m.skip_layer) {
+                add_chunk(pl, st, kPanelE, ceil_div(m.trunk_in, 16), P(2 * l), fan_in, 256, 0, m.trunk_in, 0, 0, false);
+                col = m.trunk_in;
+            }
+            for (int j = 0; j < 4; ++j) add_chunk(pl, st, j, 4, P(2 * l), fan_in, 256, 0, 64, col + 64 * j, 0, false);
+        }
+    }
+    pl.fwd[m.depth - 1].kind = m.has_view ? EPI_RELU_HEAD1 : EPI_RELU_HEAD4;
+    pl.fwd[m.skip_layer + 1].last_e_use = 1;
+    if (m.has_view) {
+        TcStep& ft = pl.fwd[pl.n_fwd++];
+        ft.n_rows = 256; ft.kind = EPI_LINEAR; ft.bias_row = 8; ft.slot = 8;
+        for (int j = 0; j < 4; ++j) add_chunk(pl, ft, j, 4, P(SNERF_P_FEAT_W), m.width, 256, 0, 64, 64 * j, 0, false);
+        TcStep& vw = pl.fwd[pl.n_fwd++];
+        vw.n_rows = 128; vw.kind = EPI_VIEW; vw.slot = 9;
+        for (int j = 0; j < 4; ++j) add_chunk(pl, vw, j, 4, P(SNERF_P_VIEW_W), m.view_in, 128, 0, 64, 64 * j, 0, false);
+        if (m.enc_hi > 0) {   // points-augmentation: encoding bands trunk_degree.. feed the view layer (:633)
+            add_chunk(pl, vw, kPanelE, 4, P(SNERF_P_VIEW_W), m.view_in, 128, m.trunk_in, m.enc, m.width, 0, false);
+            pl.fwd[m.skip_layer + 1].last_e_use = 0;
+            vw.last_e_use = 1;
+        }
+    }
+    pl.tile_stash_bytes = (uint32_t)(m.has_view ? 9 * 65536 + 32768 : 8 * 65536);
+    return pl;
+}
+
+size_t tc_packed_bytes(const snerf_mlp_desc& d) { return align_up(build_plan(d, nullptr).packed_bytes, 1024); }
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 torch.nn.Linear weights -> bf16 swizzled [N x 64] chunks
+// ------------------------------------------------------------------------------------------------
+struct PackParams {
+    int n;
+    PackChunk c[kMaxPack];
+};
+
+__global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ PackParams pp, uint8_t* __restrict__ packed) {
+    const PackChunk& c = pp.c[blockIdx.y];
+    const int total = c.n_rows * 8;   // one thread per 16-byte chunk (8 bf16)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i >> 3, ch = i & 7;
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            float f[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int kk = ch * 8 + h * 2 + e;
+                float v = 0.f;
+                if (kk >= c.k_lo && kk < c.k_hi) {
+                    v = c.transposed ? c.src[(size_t)(c.row0 + kk - c.k_lo) * c.ld + c.col0 + n]
+                                     : c.src[(size_t)(c.row0 + n) * c.ld + c.col0 + (kk - c.k_lo)];
+                }
+                f[e] = v;
+            }
+            w[h] = pack_bf16(f[0], f[1]);
+        }
+        *reinterpret_cast<uint4*>(packed + c.dst_off + swz_offset(n, ch)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+int tc_pack(const snerf_mlp_desc& d, const float* const* prm, void* packed, cudaStream_t st) {
+    const TcPlan pl = build_plan(d, prm);
+    PackParams pp;
+    pp.n = pl.n_pack;
+    for (int i = 0; i < pl.n_pack; ++i) pp.c[i] = pl.pack[i];
+    tc_pack_kernel<<<dim3(2, pl.n_pack), 256, 0, st>>>(pp, (uint8_t*)packed);
+    SNERF_LAUNCH_OK("tc_pack_kernel");
+    return SNERF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// positional encoding helpers
+// ------------------------------------------------------------------------------------------------
+// enc[0..63]: x(3), then per band sin(3), cos(3); enc[63] = 0 (pad).  :537-551
+__device__ __forceinline__ void encode_point(const float x[3], int degree, float* enc) {
+    enc[0] = x[0]; enc[1] = x[1]; enc[2] = x[2];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        if (k < degree) {
+            const float freq = (float)(1 << k);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float sn, cs;
+                sincosf(x[c] * freq, &sn, &cs);
+                enc[3 + 6 * k + c] = sn;
+                enc[6 + 6 * k + c] = cs;
+            }
+        }
+    }
+}
+
+// per-ray part of the view layer: vb[ray][o] = b_view[o] + sum_c W_view[o][col0 + c] * PE(view_dir)[c]   (:640, :695)
+__global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restrict__ view_dirs, const float* __restrict__ w_view,
+                                                           const float* __restrict__ b_view, float* __restrict__ vb, int n_rays,
+                                                           int view_degree, int view_in, int col0, int venc) {
+    const int ray = blockIdx.x;
+    __shared__ float ve[32];
+    if (threadIdx.x == 0) {
+        float v[3] = {view_dirs[ray * 3], view_dirs[ray * 3 + 1], view_dirs[ray * 3 + 2]};
+        float e[64];
+        encode_point(v, view_degree, e);
+        for (int c = 0; c < venc; ++c) ve[c] = e[c];
+    }
+    __syncthreads();
+    const int o = threadIdx.x;
+    float acc = b_view[o];
+    for (int c = 0; c < venc; ++c) acc = fmaf(w_view[(size_t)o * view_in + col0 + c], ve[c], acc);
+    vb[(size_t)ray * 128 + o] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kFwdThreads = 352;
+constexpr uint32_t kOffH = 0;
+constexpr uint32_t kOffE = 65536;
+constexpr uint32_t kOffRing = kOffE + 2 * kPanelBytes;                 // 98304
+constexpr uint32_t kOffConst = kOffRing + kStages * kStageBytes;        // 196608
+constexpr uint32_t kConstBias = 0;                                      // [9][256] fp32
+constexpr uint32_t kConstHeadW = 9 * 256 * 4;                           // [4][256] fp32
+constexpr uint32_t kConstRgbW = kConstHeadW + 4 * 256 * 4;              // [3][128] fp32
+constexpr uint32_t kConstMisc = kConstRgbW + 3 * 128 * 4;               // head bias[4], rgb bias[4]
+constexpr uint32_t kConstBytes = kConstMisc + 64;
+constexpr uint32_t kOffBars = kOffConst + 16384;
+constexpr uint32_t kFwdSmem = kOffBars + 512 + 1024;                    // + alignment slack
+
+struct FwdParams {
+    const uint8_t* packed;
+    const float* bias[9];          // trunk 0..7, feature
+    const float *w_head, *b_head, *w_rgb, *b_rgb;
+    const float* view_bias;        // [n_rays,128]
+    const float *rays_o, *rays_d, *z, *noise;
+    float *sigma, *rgb;
+    uint8_t* stash;                // null in eval
+    long long n_points;
+    int n_samples, n_tiles, n_steps, pts_degree, head_out;
+    uint32_t tile_stash_bytes;
+    TcStep steps[kMaxSteps];
+};
+
+struct FwdBars {
+    uint64_t w_full[kStages], w_empty[kStages], acc_full[2], panel_ready[4], panel_stored[4], enc_ready[2], enc_free[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid_constant__ FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    FwdBars* bars = (FwdBars*)(smem + kOffBars);
+    float* s_bias = (float*)(smem + kOffConst + kConstBias);
+    float* s_whead = (float*)(smem + kOffConst + kConstHeadW);
+    float* s_wrgb = (float*)(smem + kOffConst + kConstRgbW);
+    float* s_misc = (float*)(smem + kOffConst + kConstMisc);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const bool save = p.stash != nullptr;
+
+    // ---- setup ----
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->enc_ready[i], 128); mbar_init(&bars->enc_free[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->panel_ready[i], 128); mbar_init(&bars->panel_stored[i], 1); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+    for (int i = threadIdx.x; i < 9 * 256; i += kFwdThreads) {
+        const float* b = p.bias[i >> 8];
+        s_bias[i] = b ? b[i & 255] : 0.f;
+    }
+    for (int i = threadIdx.x; i < p.head_out * 256; i += kFwdThreads) s_whead[i] = p.w_head[i];
+    if (p.w_rgb) for (int i = threadIdx.x; i < 3 * 128; i += kFwdThreads) s_wrgb[i] = p.w_rgb[i];
+    if (threadIdx.x < 4) s_misc[threadIdx.x] = threadIdx.x < p.head_out ? p.b_head[threadIdx.x] : 0.f;
+    if (threadIdx.x >= 4 && threadIdx.x < 7) s_misc[threadIdx.x] = p.b_rgb ? p.b_rgb[threadIdx.x - 4] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0) {
+        // ======================= weight loader =======================
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int ti = 0; ti < my_tiles; ++ti)
+                for (int s = 0; s < p.n_steps; ++s) {
+                    const TcStep& st = p.steps[s];
+                    const uint32_t bytes = (uint32_t)st.n_rows * kRowBytes;
+                    for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
+                        const uint32_t stage = cnt % kStages, round = cnt / kStages;
+                        if (round > 0) mbar_wait(&bars->w_empty[stage], (round - 1) & 1);
+                        mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
+                        bulk_g2s(smem + kOffRing + stage * kStageBytes, p.packed + st.w_off + (uint32_t)c * bytes, bytes,
+                                 &bars->w_full[stage]);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            uint32_t cnt = 0, it = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int ebuf = ti & 1;
+                bool enc_waited = false;
+                for (int s = 0; s < p.n_steps; ++s, ++it) {
+                    const TcStep& st = p.steps[s];
+                    const uint32_t d_tmem = tmem + (it & 1) * 256;
+                    const uint32_t idesc = umma_idesc(128, st.n_rows, false, false);
+                    uint32_t waited = 0;
+                    for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
+                        const int pn = st.panel[c];
+                        uint32_t a_addr;
+                        if (pn == kPanelE) {
+                            if (!enc_waited) { mbar_wait(&bars->enc_ready[ebuf], (ti >> 1) & 1); enc_waited = true; }
+                            a_addr = smem_u32(smem + kOffE + ebuf * kPanelBytes);
+                        } else {
+                            if (it > 0 && !(waited & (1u << pn))) { mbar_wait(&bars->panel_ready[pn], (it - 1) & 1); waited |= 1u << pn; }
+                            a_addr = smem_u32(smem + kOffH + pn * kPanelBytes);
+                        }
+                        const uint32_t stage = cnt % kStages;
+                        mbar_wait(&bars->w_full[stage], (cnt / kStages) & 1);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(smem + kOffRing + stage * kStageBytes);
+                        for (int k = 0; k < st.ksteps[c]; ++k)
+                            umma(d_tmem, umma_desc_kmajor(a_addr, k), umma_desc_kmajor(b_addr, k), idesc, (c | k) != 0);
+                        umma_commit(&bars->w_empty[stage]);
+                    }
+                    umma_commit(&bars->acc_full[it & 1]);
+                    if (st.last_e_use) umma_commit(&bars->enc_free[ebuf]);
+                    // every epilogue of step it-1 has finished before step it+1 may reuse its accumulator
+                    if (it > 0 && !(waited & 8u)) mbar_wait(&bars->panel_ready[3], (it - 1) & 1);
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ======================= epilogue =======================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t it = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int tile = blockIdx.x + ti * gridDim.x;
+            const long long pt = (long long)tile * kTileRows + row;
+            const bool valid = pt < p.n_points;
+            const int ray = valid ? (int)(pt / p.n_samples) : 0;
+            for (int s = 0; s < p.n_steps; ++s, ++it) {
+                const TcStep& st = p.steps[s];
+                const int kind = st.kind;
+                mbar_wait(&bars->acc_full[it & 1], (it >> 1) & 1);
+                tc_fence_after();
+                const int n_pan = st.n_rows / 64;
+                const bool writes_h = (kind != EPI_VIEW) || save;
+                float head[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) head[h] = s_misc[(kind == EPI_VIEW ? 4 : 0) + h];
+                for (int j = 0; j < 4; ++j) {
+                    if (j < n_pan) {
+                        float v[64];
+                        {
+                            float t[32];
+                            tmem_ld32(lane_addr + (it & 1) * 256 + j * 64, t);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = t[i];
+                            tmem_ld32(lane_addr + (it & 1) * 256 + j * 64 + 32, t);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[32 + i] = t[i];
+                        }
+                        if (kind == EPI_VIEW) {
+                            const float4* vb = reinterpret_cast<const float4*>(p.view_bias + (size_t)ray * 128 + j * 64);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float4 b = __ldg(vb + i);
+                                v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
+                                v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
+                                v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
+                                v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
+                            }
+#pragma unroll
+                            for (int h = 0; h < 3; ++h) {
+                                const float4* w = reinterpret_cast<const float4*>(s_wrgb + h * 128 + j * 64);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const float4 ww = w[i];
+                                    head[h] = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, head[h]))));
+                                }
+                            }
+                        } else {
+                            const float4* bb = reinterpret_cast<const float4*>(s_bias + st.bias_row * 256 + j * 64);
+                            const bool relu = kind != EPI_LINEAR;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float4 b = bb[i];
+                                v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                            }
+                            if (relu) {
+#pragma unroll
+                                for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+                            }
+                            if (kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4) {
+                                const int nh = kind == EPI_RELU_HEAD1 ? 1 : 4;
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    if (h < nh) {
+                                        const float4* w = reinterpret_cast<const float4*>(s_whead + h * 256 + j * 64);
+                                        float a = head[h];
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) {
+                                            const float4 ww = w[i];
+                                            a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
+                                        }
+                                        head[h] = a;
+                                    }
+                                }
+                            }
+                        }
+                        if (writes_h) {
+                            if (save && it > 0) mbar_wait(&bars->panel_stored[j], (it - 1) & 1);
+                            uint8_t* dst = smem + kOffH + j * kPanelBytes;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const uint4 u = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                                                           pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+                                *reinterpret_cast<uint4*>(dst + swz_offset(row, c)) = u;
+                            }
+                            fence_async_smem();
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&bars->panel_ready[j]);
+                }
+                if (valid) {
+                    if (kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4) {
+                        const float nz = p.noise ? p.noise[pt] : 0.f;
+                        p.sigma[pt] = fmaxf(head[0] + nz, 0.f);                                        // :668-672
+                        if (kind == EPI_RELU_HEAD4) {
+#pragma unroll
+                            for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
+                        }
+                    } else if (kind == EPI_VIEW) {
+#pragma unroll
+                        for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h]);             // :704-707
+                    }
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ======================= encoder =======================
+        const int row = (warp - 6) * 32 + lane;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int tile = blockIdx.x + ti * gridDim.x;
+            const int ebuf = ti & 1;
+            const long long pt = (long long)tile * kTileRows + row;
+            float x[3] = {0.f, 0.f, 0.f};
+            if (pt < p.n_points) {
+                const int ray = (int)(pt / p.n_samples);
+                const float zz = p.z[pt];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) x[c] = fmaf(p.rays_d[ray * 3 + c], zz, p.rays_o[ray * 3 + c]);   // :140/:142
+            }
+            float enc[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) enc[i] = 0.f;
+            encode_point(x, p.pts_degree, enc);
+            if (ti >= 2) mbar_wait(&bars->enc_free[ebuf], ((ti >> 1) - 1) & 1);
+            uint8_t* dst = smem + kOffE + ebuf * kPanelBytes;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 u = make_uint4(pack_bf16(enc[8 * c], enc[8 * c + 1]), pack_bf16(enc[8 * c + 2], enc[8 * c + 3]),
+                                           pack_bf16(enc[8 * c + 4], enc[8 * c + 5]), pack_bf16(enc[8 * c + 6], enc[8 * c + 7]));
+                *reinterpret_cast<uint4*>(dst + swz_offset(row, c)) = u;
+            }
+            fence_async_smem();
+            mbar_arrive(&bars->enc_ready[ebuf]);
+        }
+    } else {
+        // ======================= stash writer (training) =======================
+        if (save && lane == 0) {
+            uint32_t it = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int tile = blockIdx.x + ti * gridDim.x;
+                uint8_t* base = p.stash + (size_t)tile * p.tile_stash_bytes;
+                for (int s = 0; s < p.n_steps; ++s, ++it) {
+                    const TcStep& st = p.steps[s];
+                    const int n_pan = st.n_rows / 64;
+                    for (int j = 0; j < 4; ++j) {
+                        mbar_wait(&bars->panel_ready[j], it & 1);
+                        if (j < n_pan) {
+                            bulk_s2g(base + (size_t)st.slot * 65536 + j * kPanelBytes, smem + kOffH + j * kPanelBytes, kPanelBytes);
+                            bulk_commit();
+                        }
+                    }
+                    bulk_wait_read<0>();
+                    for (int j = 0; j < 4; ++j) mbar_arrive(&bars->panel_stored[j]);
+                }
+            }
+            bulk_wait_all<0>();
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace + drivers
+// ------------------------------------------------------------------------------------------------
+struct TcWorkspace {
+    size_t view_bias, act, dy, total;
+    int n_tiles;
+};
+
+static TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n_rays, int n_samples, uint32_t flags) {
+    TcWorkspace w{};
+    const long long P = (long long)n_rays * n_samples;
+    w.n_tiles = (int)((P + kTileRows - 1) / kTileRows);
+    size_t off = 0;
+    w.view_bias = off;
+    off += align_up(m.has_view ? (size_t)n_rays * 128 * sizeof(float) : 0, 1024);
+    if (flags & SNERF_FLAG_SAVE_FOR_BWD) {
+        w.act = off;
+        off += (size_t)w.n_tiles * pl.tile_stash_bytes;
+        w.dy = off;
+        off += (size_t)w.n_tiles * pl.tile_stash_bytes;
+    }
+    w.total = off + 1024;
+    return w;
+}
+
+size_t tc_workspace_bytes(const MlpDims& m, const snerf_mlp_desc& d, int n_rays, int n_samples, uint32_t flags) {
+    return tc_ws_layout(m, build_plan(d, nullptr), n_rays, n_samples, flags).total;
+}
+
+static int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o, const float* rays_d,
+               const float* view_dirs, const float* z, const float* noise, float* sigma, float* rgb, void* ws, size_t ws_bytes,
+               int n_rays, int n_samples, uint32_t flags, cudaStream_t st) {
+    const MlpDims m(d);
+    const TcPlan pl = build_plan(d, prm);
+    const TcWorkspace w = tc_ws_layout(m, pl, n_rays, n_samples, flags);
+    SNERF_REQUIRE(ws_bytes >= w.total, "mlp_forward: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    SNERF_REQUIRE(((uintptr_t)packed & 15) == 0 && ((uintptr_t)ws & 15) == 0, "mlp_forward: packed/workspace must be 16-byte aligned");
+    uint8_t* wsb = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    if (m.has_view) {
+        tc_view_bias_kernel<<<n_rays, 128, 0, st>>>(view_dirs, prm[SNERF_P_VIEW_W], prm[SNERF_P_VIEW_B], (float*)(wsb + w.view_bias),
+                                                    n_rays, d.view_degree, m.view_in, m.width + m.enc_hi, m.venc);
+        SNERF_LAUNCH_OK("tc_view_bias_kernel");
+    }
+    FwdParams p{};
+    p.packed = (const uint8_t*)packed;
+    for (int l = 0; l < 8; ++l) p.bias[l] = prm[2 * l + 1];
+    p.bias[8] = m.has_view ? prm[SNERF_P_FEAT_B] : nullptr;
+    p.w_head = prm[SNERF_P_HEAD_W]; p.b_head = prm[SNERF_P_HEAD_B];
+    p.w_rgb = m.has_view ? prm[SNERF_P_RGB_W] : nullptr; p.b_rgb = m.has_view ? prm[SNERF_P_RGB_B] : nullptr;
+    p.view_bias = (const float*)(wsb + w.view_bias);
+    p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.noise = noise; p.sigma = sigma; p.rgb = rgb;
+    p.stash = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.act : nullptr;
+    p.n_points = (long long)n_rays * n_samples;
+    p.n_samples = n_samples; p.n_tiles = w.n_tiles; p.n_steps = pl.n_fwd; p.pts_degree = d.pts_degree; p.head_out = m.head_out;
+    p.tile_stash_bytes = pl.tile_stash_bytes;
+    for (int s = 0; s < pl.n_fwd; ++s) p.steps[s] = pl.fwd[s];
+    static bool attr = false;
+    if (!attr) {
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        attr = true;
+    }
+    const int grid = w.n_tiles < num_sms() ? w.n_tiles : num_sms();
+    tc_forward_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(p);
+    SNERF_LAUNCH_OK("tc_forward_kernel");
+    return SNERF_OK;
+}
+
+int tc_backward(const snerf_mlp_desc&, const float* const*, const void*, const float*, const float*, const float*, const float*,
+                const float*, const float*, const float*, const float*, float* const*, void*, size_t, int, int, uint32_t,
+                cudaStream_t) {
+    return fail(SNERF_ERR_UNSUPPORTED, "tensor-path backward not built yet");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Descriptor probe: runs a host-specified list of tcgen05.mma instructions on host-provided operand
+// images and returns the accumulator (tools/tc_probe.py).
+// ------------------------------------------------------------------------------------------------
+struct ProbeOp { uint32_t a_off, b_off, d_col, accumulate; };
+
+__global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict__ a_img, uint32_t a_bytes,
+                                                       const uint8_t* __restrict__ b_img, uint32_t b_bytes,
+                                                       float* __restrict__ d_out, const ProbeOp* __restrict__ ops, int n_ops,
+                                                       uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
+                                                       uint32_t idesc, uint64_t desc_bits, int n_cols) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_load, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + 65536;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_load, 1);
+        mbar_init(&bar_mma, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&bar_load, a_bytes + b_bytes);
+        bulk_g2s(sa, a_img, a_bytes, &bar_load);
+        bulk_g2s(sb, b_img, b_bytes, &bar_load);
+        mbar_wait(&bar_load, 0);
+        tc_fence_after();
+        for (int i = 0; i < n_ops; ++i) {
+            const ProbeOp op = ops[i];
+            const uint32_t aa = smem_u32(sa) + op.a_off, ba = smem_u32(sb) + op.b_off;
+            const uint64_t ad = (uint64_t)((aa >> 4) & 0x3FFFu) | ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) |
+                                ((uint64_t)((a_sbo >> 4) & 0x3FFFu) << 32) | desc_bits;
+            const uint64_t bd = (uint64_t)((ba >> 4) & 0x3FFFu) | ((uint64_t)((b_lbo >> 4) & 0x3FFFu) << 16) |
+                                ((uint64_t)((b_sbo >> 4) & 0x3FFFu) << 32) | desc_bits;
+            umma(tmem_base + op.d_col, ad, bd, idesc, op.accumulate != 0);
+        }
+        umma_commit(&bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    for (int c = 0; c < n_cols; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
+        float* row = d_out + (size_t)(warp * 32 + lane) * n_cols + c;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) row[i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+int tc_selftest(float* host_max_err, cudaStream_t) {
+    for (int i = 0; i < 4; ++i) host_max_err[i] = -1.f;
+    return fail(SNERF_ERR_UNSUPPORTED, "use tools/tc_probe.py");
+}
+
+}  // namespace snerf
+
+using namespace snerf;
+extern "C" int snerf_has_tensor_path(void) { return 1; }
+
+// debug entry (not part of the public ABI): all pointers are device pointers
+extern "C" int snerfdbg_probe(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, float* d_out,
+                              const void* ops, int n_ops, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
+                              uint32_t idesc, uint64_t desc_bits, int n_cols, void* stream) {
+    SNERF_REQUIRE(a_bytes <= 65536 && b_bytes <= 131072 && n_cols % 32 == 0 && n_cols <= 512, "probe: bad sizes");
+    SNERF_CUDA_OK(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 131072));
+    tc_probe_kernel<<<1, 128, 65536 + 131072, (cudaStream_t)stream>>>((const uint8_t*)a_img, a_bytes, (const uint8_t*)b_img,
+                                                                    b_bytes, d_out, (const ProbeOp*)ops, n_ops, a_lbo, a_sbo,
+                                                                    b_lbo, b_sbo, idesc, desc_bits, n_cols);
+    SNERF_LAUNCH_OK("tc_probe_kernel");
+    return SNERF_OK;
+}
