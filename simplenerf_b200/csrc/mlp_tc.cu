@@ -15,107 +15,10 @@
 // layer l's epilogue is still running; activations never leave the SM in eval mode.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_plan.cuh"
 
 namespace snerf {
 using namespace tc;
-
-// ------------------------------------------------------------------------------------------------
-// plan: GEMM steps, packed-weight layout
-// ------------------------------------------------------------------------------------------------
-constexpr int kStages = 3;
-constexpr int kStageBytes = 32768;
-constexpr int kMaxSteps = 10;
-constexpr int kMaxChunks = 5;
-constexpr int kPanelE = 4;   // panel id of the encoding buffer
-constexpr int kPanelP = 5;   // (backward) first panel of the prologue buffer
-
-enum EpiKind : uint8_t { EPI_RELU = 0, EPI_RELU_HEAD1, EPI_RELU_HEAD4, EPI_LINEAR, EPI_VIEW };
-
-struct TcStep {
-    uint32_t w_off;               // byte offset of the first weight chunk in the packed image
-    uint16_t n_rows;              // N of the MMA (256 or 128)
-    uint8_t n_chunks;
-    uint8_t kind;
-    uint8_t panel[kMaxChunks];    // A panel per chunk
-    uint8_t ksteps[kMaxChunks];   // 16-wide K steps per chunk
-    uint8_t bias_row;             // row of the smem bias table
-    uint8_t slot;                 // stash slot of the panels this step writes
-    uint8_t last_e_use;           // this step is the last reader of panel E within a tile
-    uint8_t pad;
-};
-
-struct PackChunk {
-    const float* src;
-    int32_t ld;
-    int16_t n_rows, k_lo, k_hi, col0, row0, transposed;
-    uint32_t dst_off;
-};
-constexpr int kMaxPack = 96;
-
-struct TcPlan {
-    int n_fwd, n_bwd;
-    TcStep fwd[kMaxSteps], bwd[kMaxSteps];
-    int n_pack;
-    PackChunk pack[kMaxPack];
-    uint32_t packed_bytes;
-    uint32_t tile_stash_bytes;    // activation (and dY) stash bytes per 128-point tile
-};
-
-static void add_chunk(TcPlan& pl, TcStep& st, int panel, int ksteps, const float* src, int ld, int n_rows, int k_lo, int k_hi,
-                      int col0, int row0, bool transposed) {
-    PackChunk& c = pl.pack[pl.n_pack++];
-    c.src = src; c.ld = ld; c.n_rows = (int16_t)n_rows; c.k_lo = (int16_t)k_lo; c.k_hi = (int16_t)k_hi;
-    c.col0 = (int16_t)col0; c.row0 = (int16_t)row0; c.transposed = transposed ? 1 : 0;
-    c.dst_off = pl.packed_bytes;
-    if (st.n_chunks == 0) st.w_off = pl.packed_bytes;
-    st.panel[st.n_chunks] = (uint8_t)panel;
-    st.ksteps[st.n_chunks] = (uint8_t)ksteps;
-    st.n_chunks++;
-    pl.packed_bytes += (uint32_t)n_rows * kRowBytes;
-}
-
-// prm may be null (layout only)
-static TcPlan build_plan(const snerf_mlp_desc& d, const float* const* prm) {
-    const MlpDims m(d);
-    TcPlan pl{};
-    auto P = [&](int i) -> const float* { return prm ? prm[i] : nullptr; };
-    // ---- forward steps ----
-    for (int l = 0; l < m.depth; ++l) {
-        TcStep& st = pl.fwd[pl.n_fwd++];
-        st.n_rows = 256;
-        st.kind = EPI_RELU;
-        st.bias_row = (uint8_t)l;
-        st.slot = (uint8_t)l;
-        const int fan_in = m.trunk_fan_in(l);
-        if (l == 0) {
-            add_chunk(pl, st, kPanelE, ceil_div(m.trunk_in, 16), P(0), fan_in, 256, 0, m.trunk_in, 0, 0, false);
-        } else {
-            int col = 0;
-            if (l - 1 == m.skip_layer) {
-                add_chunk(pl, st, kPanelE, ceil_div(m.trunk_in, 16), P(2 * l), fan_in, 256, 0, m.trunk_in, 0, 0, false);
-                col = m.trunk_in;
-            }
-            for (int j = 0; j < 4; ++j) add_chunk(pl, st, j, 4, P(2 * l), fan_in, 256, 0, 64, col + 64 * j, 0, false);
-        }
-    }
-    pl.fwd[m.depth - 1].kind = m.has_view ? EPI_RELU_HEAD1 : EPI_RELU_HEAD4;
-    pl.fwd[m.skip_layer + 1].last_e_use = 1;
-    if (m.has_view) {
-        TcStep& ft = pl.fwd[pl.n_fwd++];
-        ft.n_rows = 256; ft.kind = EPI_LINEAR; ft.bias_row = 8; ft.slot = 8;
-        for (int j = 0; j < 4; ++j) add_chunk(pl, ft, j, 4, P(SNERF_P_FEAT_W), m.width, 256, 0, 64, 64 * j, 0, false);
-        TcStep& vw = pl.fwd[pl.n_fwd++];
-        vw.n_rows = 128; vw.kind = EPI_VIEW; vw.slot = 9;
-        for (int j = 0; j < 4; ++j) add_chunk(pl, vw, j, 4, P(SNERF_P_VIEW_W), m.view_in, 128, 0, 64, 64 * j, 0, false);
-        if (m.enc_hi > 0) {   // points-augmentation: encoding bands trunk_degree.. feed the view layer (:633)
-            add_chunk(pl, vw, kPanelE, 4, P(SNERF_P_VIEW_W), m.view_in, 128, m.trunk_in, m.enc, m.width, 0, false);
-            pl.fwd[m.skip_layer + 1].last_e_use = 0;
-            vw.last_e_use = 1;
-        }
-    }
-    pl.tile_stash_bytes = (uint32_t)(m.has_view ? 9 * 65536 + 32768 : 8 * 65536);
-    return pl;
-}
 
 size_t tc_packed_bytes(const snerf_mlp_desc& d) { return align_up(build_plan(d, nullptr).packed_bytes, 1024); }
 
@@ -162,27 +65,6 @@ int tc_pack(const snerf_mlp_desc& d, const float* const* prm, void* packed, cuda
     return SNERF_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// positional encoding helpers
-// ------------------------------------------------------------------------------------------------
-// enc[0..63]: x(3), then per band sin(3), cos(3); enc[63] = 0 (pad).  :537-551
-__device__ __forceinline__ void encode_point(const float x[3], int degree, float* enc) {
-    enc[0] = x[0]; enc[1] = x[1]; enc[2] = x[2];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-        if (k < degree) {
-            const float freq = (float)(1 << k);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float sn, cs;
-                sincosf(x[c] * freq, &sn, &cs);
-                enc[3 + 6 * k + c] = sn;
-                enc[6 + 6 * k + c] = cs;
-            }
-        }
-    }
-}
-
 // per-ray part of the view layer: vb[ray][o] = b_view[o] + sum_c W_view[o][col0 + c] * PE(view_dir)[c]   (:640, :695)
 __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restrict__ view_dirs, const float* __restrict__ w_view,
                                                            const float* __restrict__ b_view, float* __restrict__ vb, int n_rays,
@@ -214,7 +96,6 @@ constexpr uint32_t kConstBias = 0;                                      // [9][2
 constexpr uint32_t kConstHeadW = 9 * 256 * 4;                           // [4][256] fp32
 constexpr uint32_t kConstRgbW = kConstHeadW + 4 * 256 * 4;              // [3][128] fp32
 constexpr uint32_t kConstMisc = kConstRgbW + 3 * 128 * 4;               // head bias[4], rgb bias[4]
-constexpr uint32_t kConstBytes = kConstMisc + 64;
 constexpr uint32_t kOffBars = kOffConst + 16384;
 constexpr uint32_t kFwdSmem = kOffBars + 512 + 1024;                    // + alignment slack
 
@@ -499,40 +380,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
 // ------------------------------------------------------------------------------------------------
 // workspace + drivers
 // ------------------------------------------------------------------------------------------------
-struct TcWorkspace {
-    size_t view_bias, act, dy, total;
-    int n_tiles;
-};
-
-static TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n_rays, int n_samples, uint32_t flags) {
-    TcWorkspace w{};
-    const long long P = (long long)n_rays * n_samples;
-    w.n_tiles = (int)((P + kTileRows - 1) / kTileRows);
-    size_t off = 0;
-    w.view_bias = off;
-    off += align_up(m.has_view ? (size_t)n_rays * 128 * sizeof(float) : 0, 1024);
-    if (flags & SNERF_FLAG_SAVE_FOR_BWD) {
-        w.act = off;
-        off += (size_t)w.n_tiles * pl.tile_stash_bytes;
-        w.dy = off;
-        off += (size_t)w.n_tiles * pl.tile_stash_bytes;
-    }
-    w.total = off + 1024;
-    return w;
-}
-
 size_t tc_workspace_bytes(const MlpDims& m, const snerf_mlp_desc& d, int n_rays, int n_samples, uint32_t flags) {
     return tc_ws_layout(m, build_plan(d, nullptr), n_rays, n_samples, flags).total;
-}
-
-static int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return sms;
 }
 
 int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o, const float* rays_d,
@@ -571,12 +420,6 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     tc_forward_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(p);
     SNERF_LAUNCH_OK("tc_forward_kernel");
     return SNERF_OK;
-}
-
-int tc_backward(const snerf_mlp_desc&, const float* const*, const void*, const float*, const float*, const float*, const float*,
-                const float*, const float*, const float*, const float*, float* const*, void*, size_t, int, int, uint32_t,
-                cudaStream_t) {
-    return fail(SNERF_ERR_UNSUPPORTED, "tensor-path backward not built yet");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,184 @@
+// Plan shared by the tensor-path kernels: the sequence of GEMM steps of one MLP (forward chain and
+// dgrad chain), the layout of the packed bf16 weight image, the activation / gradient stash and the workspace.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace snerf {
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------
+// plan: GEMM steps, packed-weight layout
+// ------------------------------------------------------------------------------------------------
+constexpr int kStages = 3;
+constexpr int kStageBytes = 32768;
+constexpr int kMaxSteps = 10;
+constexpr int kMaxChunks = 5;
+constexpr int kPanelE = 4;   // panel id of the encoding buffer
+constexpr int kPanelP = 5;   // (backward) first panel of the prologue buffer
+
+enum EpiKind : uint8_t { EPI_RELU = 0, EPI_RELU_HEAD1, EPI_RELU_HEAD4, EPI_LINEAR, EPI_VIEW, BWD_LINEAR, BWD_MASK };
+
+struct TcStep {
+    uint32_t w_off;               // byte offset of the first weight chunk in the packed image
+    uint16_t n_rows;              // N of the MMA (256 or 128)
+    uint8_t n_chunks;
+    uint8_t kind;
+    uint8_t panel[kMaxChunks];    // A panel per chunk
+    uint8_t ksteps[kMaxChunks];   // 16-wide K steps per chunk
+    uint8_t bias_row;             // row of the smem bias table
+    uint8_t slot;                 // stash slot of the panels this step writes
+    uint8_t last_e_use;           // this step is the last reader of the aux panels (E / P) within a tile
+    uint8_t mask_slot;            // (backward) activation-stash slot whose sign masks this step's output
+};
+
+struct PackChunk {
+    const float* src;
+    int32_t ld;
+    int16_t n_rows, k_lo, k_hi, col0, row0, transposed;
+    uint32_t dst_off;
+};
+constexpr int kMaxPack = 96;
+
+struct TcPlan {
+    int n_fwd, n_bwd;
+    TcStep fwd[kMaxSteps], bwd[kMaxSteps];
+    int n_pack;
+    PackChunk pack[kMaxPack];
+    uint32_t packed_bytes;
+    uint32_t tile_stash_bytes;    // activation (and dY) stash bytes per 128-point tile
+};
+
+static inline void add_chunk(TcPlan& pl, TcStep& st, int panel, int ksteps, const float* src, int ld, int n_rows, int k_lo, int k_hi,
+                      int col0, int row0, bool transposed) {
+    PackChunk& c = pl.pack[pl.n_pack++];
+    c.src = src; c.ld = ld; c.n_rows = (int16_t)n_rows; c.k_lo = (int16_t)k_lo; c.k_hi = (int16_t)k_hi;
+    c.col0 = (int16_t)col0; c.row0 = (int16_t)row0; c.transposed = transposed ? 1 : 0;
+    c.dst_off = pl.packed_bytes;
+    if (st.n_chunks == 0) st.w_off = pl.packed_bytes;
+    st.panel[st.n_chunks] = (uint8_t)panel;
+    st.ksteps[st.n_chunks] = (uint8_t)ksteps;
+    st.n_chunks++;
+    pl.packed_bytes += (uint32_t)n_rows * kRowBytes;
+}
+
+// prm may be null (layout only)
+static inline TcPlan build_plan(const snerf_mlp_desc& d, const float* const* prm) {
+    const MlpDims m(d);
+    TcPlan pl{};
+    auto P = [&](int i) -> const float* { return prm ? prm[i] : nullptr; };
+    // ---- forward steps ----
+    for (int l = 0; l < m.depth; ++l) {
+        TcStep& st = pl.fwd[pl.n_fwd++];
+        st.n_rows = 256;
+        st.kind = EPI_RELU;
+        st.bias_row = (uint8_t)l;
+        st.slot = (uint8_t)l;
+        const int fan_in = m.trunk_fan_in(l);
+        if (l == 0) {
+            add_chunk(pl, st, kPanelE, ceil_div(m.trunk_in, 16), P(0), fan_in, 256, 0, m.trunk_in, 0, 0, false);
+        } else {
+            int col = 0;
+            if (l - 1 == m.skip_layer) {
+                add_chunk(pl, st, kPanelE, ceil_div(m.trunk_in, 16), P(2 * l), fan_in, 256, 0, m.trunk_in, 0, 0, false);
+                col = m.trunk_in;
+            }
+            for (int j = 0; j < 4; ++j) add_chunk(pl, st, j, 4, P(2 * l), fan_in, 256, 0, 64, col + 64 * j, 0, false);
+        }
+    }
+    pl.fwd[m.depth - 1].kind = m.has_view ? EPI_RELU_HEAD1 : EPI_RELU_HEAD4;
+    pl.fwd[m.skip_layer + 1].last_e_use = 1;
+    if (m.has_view) {
+        TcStep& ft = pl.fwd[pl.n_fwd++];
+        ft.n_rows = 256; ft.kind = EPI_LINEAR; ft.bias_row = 8; ft.slot = 8;
+        for (int j = 0; j < 4; ++j) add_chunk(pl, ft, j, 4, P(SNERF_P_FEAT_W), m.width, 256, 0, 64, 64 * j, 0, false);
+        TcStep& vw = pl.fwd[pl.n_fwd++];
+        vw.n_rows = 128; vw.kind = EPI_VIEW; vw.slot = 9;
+        for (int j = 0; j < 4; ++j) add_chunk(pl, vw, j, 4, P(SNERF_P_VIEW_W), m.view_in, 128, 0, 64, 64 * j, 0, false);
+        if (m.enc_hi > 0) {   // points-augmentation: encoding bands trunk_degree.. feed the view layer (:633)
+            add_chunk(pl, vw, kPanelE, 4, P(SNERF_P_VIEW_W), m.view_in, 128, m.trunk_in, m.enc, m.width, 0, false);
+            pl.fwd[m.skip_layer + 1].last_e_use = 0;
+            vw.last_e_use = 1;
+        }
+    }
+    pl.tile_stash_bytes = (uint32_t)(m.has_view ? 9 * 65536 + 32768 : 8 * 65536);
+
+    // ---- backward (dgrad) steps: B operand = W^T chunks [256 in-features x 64 out-features] ----
+    // dY_l = gradient w.r.t. the pre-activation of trunk layer l; stash slot l.  Slot 8 = d feature, 9 = d hv.
+    if (m.has_view) {
+        TcStep& vg = pl.bwd[pl.n_bwd++];    // d feature = dY_v W_view[:, :256]   (feature has no activation)
+        vg.n_rows = 256; vg.kind = BWD_LINEAR; vg.slot = 8;
+        for (int c = 0; c < 2; ++c) add_chunk(pl, vg, kPanelP + c, 4, P(SNERF_P_VIEW_W), m.view_in, 256, 0, 64, 0, 64 * c, true);
+    }
+    {
+        TcStep& fg = pl.bwd[pl.n_bwd++];    // d h8 = d feature W_feat + d head_pre W_head, masked by h8 > 0
+        fg.n_rows = 256; fg.kind = BWD_MASK; fg.mask_slot = 7; fg.slot = 7; fg.last_e_use = 1;
+        if (m.has_view)
+            for (int c = 0; c < 4; ++c) add_chunk(pl, fg, c, 4, P(SNERF_P_FEAT_W), m.width, 256, 0, 64, 0, 64 * c, true);
+        add_chunk(pl, fg, kPanelP + 2, 1, P(SNERF_P_HEAD_W), m.width, 256, 0, m.head_out, 0, 0, true);
+    }
+    for (int l = m.depth - 1; l >= 1; --l) {   // d h_l = dY_l W_l[:, hidden part], masked by h_l > 0
+        TcStep& st = pl.bwd[pl.n_bwd++];
+        st.n_rows = 256; st.kind = BWD_MASK; st.mask_slot = (uint8_t)(l - 1); st.slot = (uint8_t)(l - 1);
+        const int hcol0 = (l - 1 == m.skip_layer) ? m.trunk_in : 0;
+        for (int c = 0; c < 4; ++c) add_chunk(pl, st, c, 4, P(2 * l), m.trunk_fan_in(l), 256, 0, 64, hcol0, 64 * c, true);
+    }
+    return pl;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// positional encoding helpers
+// ------------------------------------------------------------------------------------------------
+// enc[0..63]: x(3), then per band sin(3), cos(3); enc[63] = 0 (pad).  :537-551
+__device__ __forceinline__ void encode_point(const float x[3], int degree, float* enc) {
+    enc[0] = x[0]; enc[1] = x[1]; enc[2] = x[2];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        if (k < degree) {
+            const float freq = (float)(1 << k);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float sn, cs;
+                sincosf(x[c] * freq, &sn, &cs);
+                enc[3 + 6 * k + c] = sn;
+                enc[6 + 6 * k + c] = cs;
+            }
+        }
+    }
+}
+
+struct TcWorkspace {
+    size_t view_bias, act, dy, total;
+    int n_tiles;
+};
+
+static inline TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n_rays, int n_samples, uint32_t flags) {
+    TcWorkspace w{};
+    const long long P = (long long)n_rays * n_samples;
+    w.n_tiles = (int)((P + kTileRows - 1) / kTileRows);
+    size_t off = 0;
+    w.view_bias = off;
+    off += align_up(m.has_view ? (size_t)n_rays * 128 * sizeof(float) : 0, 1024);
+    if (flags & SNERF_FLAG_SAVE_FOR_BWD) {
+        w.act = off;
+        off += (size_t)w.n_tiles * pl.tile_stash_bytes;
+        w.dy = off;
+        off += (size_t)w.n_tiles * pl.tile_stash_bytes;
+    }
+    w.total = off + 1024;
+    return w;
+}
+
+static inline int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+
+}  // namespace snerf
