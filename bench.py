@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the SimpleNeRF volumetric-rendering hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config C2 of BASELINE.json): LLFF-shaped SimpleNeRF training step -- 1008x756 camera, 3 views,
+4096 rays per GPU, 64 coarse + 128 extra fine samples (192-point fine pass), coarse + fine + points-augmented
++ views-augmented MLPs, forward + backward (+ Adam update), random-init weights, synthetic rays.
+A "step" is one pass of the hot path over one 4096-ray batch per GPU (weak scaling: the reference's
+RealEstate config C4 is 32768 rays over 8 GPUs = 4096 per GPU); under torchrun the MLP gradients are
+all-reduced over NCCL every step.  Metric: train rays/s over all GPUs.
+
+Our arm   : the drop-in model (simplenerf_b200.models.FusedSimpleNeRF01, bf16 tcgen05 path) -- `value` with
+            the batch resident in HBM, `e2e` with the batch in pinned host memory copied every step and the
+            loss read back.
+Reference : `--impl reference` times the reference algorithm's CPU restatement (oracle/, "port": the
+            reference is pure Python/torch and /root/reference does not exist on the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 4096
+TRAIN_FLOP_PER_RAY = 2 * 648_585_216          # fwd+bwd MACs per ray (4 MLPs) x 2
+RENDER_FLOP_PER_RAY = 2 * 256 * 593_408       # vanilla coarse+fine eval
+STREAMS = (('rgb_coarse', 'depth_coarse'), ('rgb_fine', 'depth_fine'),
+           ('points_augmentation_rgb_coarse', 'points_augmentation_depth_coarse'),
+           ('views_augmentation_rgb_coarse', 'views_augmentation_depth_coarse'))
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(tflops=d.get('bf16_tflops_sustained', d['bf16_tflops']), tflops_burst=d['bf16_tflops'],
+                    hbm=d['hbm_gbs'], source='measured (MEASURED_PEAKS.json, sustained bf16)')
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons during the timed region (NVML; falls back to nvidia-smi)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
+               0x80: 'hw_power_brake_slowdown', 0x2: 'applications_clocks_setting'}
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as exc:   # noqa: BLE001
+            self.reasons.add(f'sampler_error:{type(exc).__name__}')
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+def make_state(model, seed=0):
+    """Deterministic random-init weights (an opaque field) for any module with the reference's names."""
+    from simplenerf_b200 import synthetic
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    return synthetic.densify_state(synthetic.deterministic_state(shapes, seed))
+
+
+def training_loss(out, target, tdepth):
+    return sum(((out[a] - target) ** 2).mean() + 0.1 * ((out[b] - tdepth) ** 2).mean() for a, b in STREAMS)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_training_pass(n_rays: int, sub_batch: int, threads: int):
+    """One training pass of the oracle over n_rays (grad accumulation in sub-batches like Trainer01.py:82-101)."""
+    import torch
+    from oracle import nerf_oracle as orc
+    from simplenerf_b200 import synthetic
+    torch.set_num_threads(threads)
+    configs = synthetic.make_configs('simplenerf')
+    model = orc.NerfOracle(configs)
+    model.load_state_dict(make_state(model))
+    model.train()
+    batch = synthetic.make_ray_batch('llff', n_rays, 1021)
+    g = torch.Generator().manual_seed(3)
+    target, tdepth = torch.rand((n_rays, 3), generator=g), 1 + 4 * torch.rand((n_rays,), generator=g)
+
+    def run():
+        t0 = time.perf_counter()
+        for i in range(0, n_rays, sub_batch):
+            sub = {k: (v[i:i + sub_batch] if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+            out = model(sub)
+            training_loss(out, target[i:i + sub_batch], tdepth[i:i + sub_batch]).backward()
+        return time.perf_counter() - t0
+    return run
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    sample = 512
+    run = cpu_training_pass(sample, sample, threads)
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    total = sum(times)
+    value = sample * args.steps / total
+    line = {
+        'impl': 'reference', 'metric': 'train rays/s (64+128 samples, fwd+bwd)', 'value': value, 'unit': 'rays/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.gpus),
+        'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': f'{sample} rays of the same workload per step (fwd+bwd, 4 MLPs), oracle/nerf_oracle.py on the host'},
+        'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int):
+    return {'workload': 'C2: LLFF-shaped SimpleNeRF training step, 3 views 1008x756, 4096 rays/GPU, 64 coarse + 192 fine '
+                        'points/ray, coarse+fine+points-aug+views-aug MLPs, fwd+bwd+Adam',
+            'rays_per_gpu': RAYS_PER_GPU, 'global_rays': RAYS_PER_GPU * n_gpus, 'parallelism': f'ray-sharded dp{n_gpus}',
+            'l2': 'per-step working set (bf16 activation + gradient stash, ~15 GB) exceeds the 126 MB L2'}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from simplenerf_b200 import _lib, ops, synthetic
+    from simplenerf_b200.models import get_model
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    if not _lib.load().snerf_has_tensor_path():
+        raise RuntimeError('libsimplenerf_b200.so was built without the tensor path')
+
+    configs = synthetic.make_configs('simplenerf')
+    model = get_model(configs, None)
+    model.load_state_dict(make_state(model))
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, betas=(0.9, 0.999), fused=True)
+    params = [p for p in model.parameters()]
+    n = RAYS_PER_GPU
+    host = synthetic.make_ray_batch('llff', n, 1021 + rank)
+    g = torch.Generator().manual_seed(3 + rank)
+    host['target_rgb'] = torch.rand((n, 3), generator=g)
+    host['target_depth'] = 1 + 4 * torch.rand((n,), generator=g)
+    host = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+    resident = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values() if isinstance(v, torch.Tensor))
+
+    def step(batch):
+        opt.zero_grad(set_to_none=True)
+        out = model(batch)
+        loss = training_loss(out, batch['target_rgb'], batch['target_depth'])
+        loss.backward()
+        if world > 1:   # ray-sharded data parallel: sum of shard gradients / world == gradient of the global mean loss
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        opt.step()
+        return loss
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+
+    # ---- value: inputs resident in HBM; MLP kernels timed with CUDA events inside the timed region ----
+    events = {'mlp_forward': [], 'mlp_backward': []}
+
+    class Timer:
+        def __init__(self, name):
+            self.name = name
+
+        def __enter__(self):
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+        def __exit__(self, *exc):
+            self.e1.record()
+            events[self.name].append((self.e0, self.e1))
+            return False
+
+    ops.TIMER['hook'] = Timer
+    launches0 = ops.LAUNCHES['count']
+    with ClockSampler(local) as clocks:
+        ms_total = timed(lambda: step(resident), args.steps)
+    launches = ops.LAUNCHES['count'] - launches0
+    ops.TIMER['hook'] = None
+    mlp_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in events.items()}
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step * 1e-3)
+
+    # ---- e2e: batch in pinned host memory, copied every step; loss read back ----
+    def e2e_step():
+        batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+        return float(step(batch))     # device -> host read of the loss
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e_value = world * n / (ms_e2e * 1e-3)
+
+    # ---- secondary metric: ms per 1008x756 frame (vanilla coarse+fine eval, tile-sharded rows, no collective) ----
+    render = None
+    if not args.no_render:
+        vcfg = synthetic.make_configs('vanilla')
+        vmodel = get_model(vcfg, None)
+        vmodel.load_state_dict(make_state(vmodel))
+        vmodel = vmodel.to(dev).eval()
+        h, w = synthetic.CAMERAS['llff']['resolution']
+        rows = (h + world - 1) // world
+        r0, r1 = rank * rows, min(h, (rank + 1) * rows)
+        frame = synthetic.make_ray_batch('llff', (r1 - r0) * w, 0, frame=True, start=r0 * w)
+        frame = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in frame.items()}
+        with torch.no_grad():
+            vmodel(frame)
+            ms_frame = timed(lambda: vmodel(frame), 2) / 2
+        render = {'ms_per_frame': ms_frame, 'rays_per_s': h * w / (ms_frame * 1e-3), 'resolution': [h, w],
+                  'tensor_frac_of_peak': h * w * RENDER_FLOP_PER_RAY / (ms_frame * 1e-3) / (peaks()['tflops'] * 1e12 * world),
+                  'sharding': f'{world} row bands, no collective'}
+
+    # ---- cpu baseline (rank 0, N=1 only): the oracle on the host cores, one full C2 step ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        run = cpu_training_pass(4096 if not args.quick_cpu else 256, 2048, threads)
+        t = run()
+        cpu = {'value': (4096 if not args.quick_cpu else 256) / t, 'unit': 'rays/s', 'cores': threads, 'kind': 'port',
+               'sample': 'one full 4096-ray step as 2 sub-batches of 2048 (Trainer01 sub_batch_size), fwd+bwd, no warm-up' if not args.quick_cpu
+               else '256 rays fwd+bwd'}
+
+    if rank == 0:
+        pk = peaks()
+        mlp_total = mlp_ms['mlp_forward'] + mlp_ms['mlp_backward']
+        achieved = n * TRAIN_FLOP_PER_RAY / (mlp_total * 1e-3) / 1e12
+        line = {
+            'metric': 'train rays/s (64+128 samples, fwd+bwd)', 'value': value, 'unit': 'rays/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': workload_config(world),
+            'e2e': {'value': e2e_value, 'unit': 'rays/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d_bytes,
+                    'd2h_bytes_per_step': 4},
+            'gpu_launches': launches,
+            'clocks': clocks.summary(),
+            'roofline': {'bound': 'tensor', 'kernel': 'tc_forward_kernel + tc_dgrad_kernel + tc_wgrad_kernel (all 4 MLPs)',
+                         'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
+                         'traffic': None, 'peak_source': pk['source'],
+                         'ms_per_step': {'mlp_forward': mlp_ms['mlp_forward'], 'mlp_backward': mlp_ms['mlp_backward'],
+                                         'other': ms_step - mlp_total},
+                         'frac_forward': n * 2 * 220_348_416 / (mlp_ms['mlp_forward'] * 1e-3) / 1e12 / pk['tflops'],
+                         'frac_backward': n * 2 * 428_236_800 / (mlp_ms['mlp_backward'] * 1e-3) / 1e12 / pk['tflops'],
+                         'step_frac_of_peak': n * TRAIN_FLOP_PER_RAY / (ms_step * 1e-3) / 1e12 / pk['tflops']},
+            'cpu_baseline': cpu,
+            'render': render,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-render', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--quick-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,56 @@
+"""Torch restatement of the ROUNDING POINTS of the bf16 tensor path (test infrastructure only).
+
+Same algorithm as ``oracle.nerf_oracle.mlp_forward`` (reference src/models/SimpleNeRF01.py:626-715) with
+bf16 rounding applied exactly where the tcgen05 kernels round: the encoded points, every hidden activation
+and the feature vector that feed a tensor-core GEMM, and the weights of those GEMMs.  Heads (sigma, rgb) and
+the view-direction part of the view layer stay fp32, as in the kernels.  Rounding is straight-through in the
+backward pass, so autograd yields the gradient the kernels are expected to produce (it
+isolates kernel bugs from the unavoidable ReLU-mask flips of a bf16 forward)."""
+import torch
+import torch.nn.functional as F
+
+from . import nerf_oracle as orc
+
+
+class _RoundBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+bf = _RoundBf16.apply
+
+
+def mlp_forward_bf16(spec, params, pts, view_dirs, sigma_noise=None):
+    enc = orc.positional_encoding(pts, spec.pts_degree)
+    e_bf = bf(enc)
+    x = e_bf[:, :spec.trunk_in]
+    h32 = None
+    for i in range(spec.depth):
+        h32 = F.relu(F.linear(x, bf(params[f'pts_linears.{i}.weight']), params[f'pts_linears.{i}.bias']))
+        x = bf(h32)
+        if i in spec.skips:
+            x = torch.cat([e_bf[:, :spec.trunk_in], x], -1)
+    head = F.linear(h32, params['pts_output_linear.weight'], params['pts_output_linear.bias'])
+    sigma = head[..., 0:1]
+    if sigma_noise is not None:
+        sigma = sigma + sigma_noise
+    out = {'sigma': F.relu(sigma)}
+    if not spec.view_dep_rgb:
+        out['rgb'] = out['rgb_view_independent'] = torch.sigmoid(head[..., 1:4])
+        return out
+    feat = bf(F.linear(x, bf(params['feature_linear.weight']), params['feature_linear.bias']))
+    wv = params['views_linears.0.weight']
+    n_hi = spec.pts_enc_dim - spec.trunk_in
+    venc = orc.positional_encoding(view_dirs, spec.view_degree)
+    pre = F.linear(feat, bf(wv[:, :spec.width])) + F.linear(venc, wv[:, spec.width + n_hi:], params['views_linears.0.bias'])
+    if n_hi:
+        pre = pre + F.linear(e_bf[:, spec.trunk_in:], bf(wv[:, spec.width:spec.width + n_hi]))
+    hv = F.relu(pre)
+    out['rgb'] = out['rgb_view_dependent'] = torch.sigmoid(
+        F.linear(hv, params['views_output_linear.weight'], params['views_output_linear.bias']))
+    return out

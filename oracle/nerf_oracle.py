@@ -337,6 +337,7 @@ class NerfOracle(torch.nn.Module):
                 holder.views_output_linear = torch.nn.Linear(spec.view_width, spec.view_head_out)
             setattr(self, slot, holder)
         self.randoms: Optional[Randoms] = None
+        self.mlp_impl: Callable = mlp_forward   # tests may swap in oracle.bf16_emulation.mlp_forward_bf16
 
     # -- helpers ----------------------------------------------------------------------------
     def _params(self, slot: str) -> Dict[str, torch.Tensor]:
@@ -358,7 +359,7 @@ class NerfOracle(torch.nn.Module):
         pieces: Dict[str, List[torch.Tensor]] = {}
         params = self._params(slot)
         for i in range(0, flat.shape[0], chunk):                          # :404
-            part = mlp_forward(spec, params, flat[i:i + chunk], None if vd is None else vd[i:i + chunk],
+            part = self.mlp_impl(spec, params, flat[i:i + chunk], None if vd is None else vd[i:i + chunk],
                                None if noise is None else noise[i:i + chunk])
             for k, v in part.items():
                 pieces.setdefault(k, []).append(v)
@@ -431,13 +432,6 @@ class NerfOracle(torch.nn.Module):
 
 
 def deterministic_state(shapes: Dict[str, tuple], seed: int) -> Dict[str, torch.Tensor]:
-    """Host-independent stand-in for nn.Linear's default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
-    drawn from numpy's PCG64 (stable across torch builds), in sorted-name order."""
-    import numpy as np
-    rng = np.random.Generator(np.random.PCG64(seed))
-    state = {}
-    for name in sorted(shapes):
-        shape = shapes[name]
-        bound = 1.0 / np.sqrt(shape[-1] if name.endswith('weight') else shapes[name[:-4] + 'weight'][-1])
-        state[name] = torch.from_numpy(rng.uniform(-bound, bound, size=shape).astype(np.float32))
-    return state
+    """Host-independent stand-in for nn.Linear's default init (shared with the synthetic-input module)."""
+    from simplenerf_b200.synthetic import deterministic_state as _det
+    return _det(shapes, seed)

@@ -25,6 +25,25 @@ def _ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
     return t.data_ptr()
 
 
+# kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
+LAUNCHES = {'count': 0}
+# optional hook: a callable (name) -> context manager, used by bench.py to time the MLP kernels with CUDA events
+TIMER = {'hook': None}
+
+
+class _NoTimer:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _timed(name: str):
+    hook = TIMER['hook']
+    return hook(name) if hook is not None else _NoTimer()
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -43,6 +62,7 @@ def sample_coarse(near: torch.Tensor, far: torch.Tensor, t_vals: torch.Tensor, t
         t_rand = _f32(t_rand)
         assert tuple(t_rand.shape) == (n, s)
     z = torch.empty((n, s), device=near.device, dtype=torch.float32)
+    LAUNCHES['count'] += 1
     _lib.check(_lib.load().snerf_sample_coarse(_ptr(near), _ptr(far), _ptr(t_vals), _ptr(t_rand), _ptr(z), n, s,
                                                FLAG_LINDISP if lindisp else 0, _stream()), 'snerf_sample_coarse')
     return z
@@ -64,6 +84,7 @@ def sample_fine(z_coarse: torch.Tensor, weights_coarse: torch.Tensor, u: torch.T
         dbg = dict(samples=torch.empty((n, n_new), device=dev), cdf=torch.empty((n, sc - 1), device=dev),
                    below=torch.empty((n, n_new), device=dev, dtype=torch.int32),
                    above=torch.empty((n, n_new), device=dev, dtype=torch.int32))
+    LAUNCHES['count'] += 1
     _lib.check(_lib.load().snerf_sample_fine(
         _ptr(z_coarse), _ptr(weights_coarse), _ptr(u), u_stride, _ptr(z_fine), _ptr(dbg.get('samples')),
         _ptr(dbg.get('cdf')), _ptr(dbg.get('below'), torch.int32), _ptr(dbg.get('above'), torch.int32), n, sc, n_new,
@@ -89,6 +110,7 @@ def composite_forward(sigma, rgb, z, rays_o, rays_d, rays_d_ndc, ndc: bool, whit
     for k in per_sample:
         out[k] = torch.empty((n, s), device=dev)
     flags = (FLAG_NDC if ndc else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0)
+    LAUNCHES['count'] += 1
     _lib.check(_lib.load().snerf_composite_forward(
         _ptr(sigma), _ptr(rgb), _ptr(z), _ptr(rays_o), _ptr(rays_d), _ptr(rays_d_ndc) if ndc else None,
         _ptr(out['rgb']), _ptr(out['acc']), _ptr(out['depth']), _ptr(out['depth_var']), _ptr(out.get('depth_ndc')),
@@ -105,6 +127,7 @@ def composite_backward(sigma, rgb, z, rays_o, rays_d, rays_d_ndc, ndc: bool, whi
     d_rgb = torch.empty((n, s, 3), device=z.device)
     g = {k: (None if v is None else _f32(v)) for k, v in grads.items()}
     flags = (FLAG_NDC if ndc else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0)
+    LAUNCHES['count'] += 1
     _lib.check(_lib.load().snerf_composite_backward(
         _ptr(sigma), _ptr(rgb), _ptr(z), _ptr(rays_o), _ptr(rays_d), _ptr(rays_d_ndc) if ndc else None,
         _ptr(g.get('rgb')), _ptr(g.get('acc')), _ptr(g.get('depth')), _ptr(g.get('depth_var')), _ptr(g.get('depth_ndc')),
@@ -133,6 +156,7 @@ def packed_weights_bytes(desc: MlpDesc) -> int:
 
 
 def pack_weights(desc: MlpDesc, params: Sequence[Optional[torch.Tensor]], packed: torch.Tensor) -> None:
+    LAUNCHES['count'] += 1
     _lib.check(_lib.load().snerf_pack_weights(C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _stream()),
                'snerf_pack_weights')
 
@@ -141,20 +165,25 @@ def mlp_forward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, noi
     n, s = z.shape
     sigma = torch.empty((n, s), device=z.device)
     rgb = torch.empty((n, s, 3), device=z.device)
-    _lib.check(_lib.load().snerf_mlp_forward(
-        C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
-        _ptr(z), _ptr(noise), _ptr(sigma), _ptr(rgb), _ptr(workspace, torch.uint8), workspace.numel(), n, s, flags,
-        _stream()), 'snerf_mlp_forward')
+    # tensor path: view-bias kernel (view-dependent MLPs) + the fused chain kernel; precise path: ~14 launches
+    LAUNCHES['count'] += (14 if flags & FLAG_PRECISE else (2 if desc.view_width else 1))
+    with _timed('mlp_forward'):
+        _lib.check(_lib.load().snerf_mlp_forward(
+            C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
+            _ptr(z), _ptr(noise), _ptr(sigma), _ptr(rgb), _ptr(workspace, torch.uint8), workspace.numel(), n, s, flags,
+            _stream()), 'snerf_mlp_forward')
     return sigma, rgb
 
 
 def mlp_backward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, sigma, rgb, d_sigma, d_rgb,
                  grads: List[Optional[torch.Tensor]], workspace, flags: int) -> None:
     n, s = z.shape
-    _lib.check(_lib.load().snerf_mlp_backward(
-        C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
-        _ptr(z), _ptr(sigma), _ptr(rgb), _ptr(d_sigma), _ptr(d_rgb), pointer_table(grads), _ptr(workspace, torch.uint8),
-        workspace.numel(), n, s, flags, _stream()), 'snerf_mlp_backward')
+    LAUNCHES['count'] += (45 if flags & FLAG_PRECISE else 2)   # tensor path: dgrad chain + wgrad
+    with _timed('mlp_backward'):
+        _lib.check(_lib.load().snerf_mlp_backward(
+            C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
+            _ptr(z), _ptr(sigma), _ptr(rgb), _ptr(d_sigma), _ptr(d_rgb), pointer_table(grads), _ptr(workspace, torch.uint8),
+            workspace.numel(), n, s, flags, _stream()), 'snerf_mlp_backward')
 
 
 def tensor_selftest() -> List[float]:

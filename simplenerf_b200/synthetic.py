@@ -128,3 +128,16 @@ def densify_state(state: Dict[str, torch.Tensor], scale: float = 30.0, shift: fl
             t[0] += shift
             out[name] = t
     return out
+
+
+def deterministic_state(shapes: Dict[str, tuple], seed: int) -> Dict[str, torch.Tensor]:
+    """Host-independent stand-in for nn.Linear's default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) drawn from
+    numpy's PCG64 (stable across torch builds), in sorted-name order.  ``shapes``: state_dict name -> shape."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    state = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        fan_in = shape[-1] if name.endswith('weight') else tuple(shapes[name[:-4] + 'weight'])[-1]
+        bound = 1.0 / np.sqrt(fan_in)
+        state[name] = torch.from_numpy(rng.uniform(-bound, bound, size=shape).astype(np.float32))
+    return state
