@@ -165,6 +165,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from simplenerf_b200 import _lib, ops, synthetic
+    from simplenerf_b200.distributed import allreduce_gradients
     from simplenerf_b200.models import get_model
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -198,13 +199,7 @@ def run_ours(args):
         loss = training_loss(out, batch['target_rgb'], batch['target_depth'])
         loss.backward()
         if world > 1:   # ray-sharded data parallel: sum of shard gradients / world == gradient of the global mean loss
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat /= world
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+            allreduce_gradients(params, weight=1.0 / world)
         opt.step()
         return loss
 

@@ -89,10 +89,12 @@ class MlpBlock(torch.nn.Module):
             t[P_RGB_W], t[P_RGB_B] = self.views_output_linear.weight, self.views_output_linear.bias
         return t
 
-    def packed(self, params: List[Optional[torch.Tensor]]) -> torch.Tensor:
-        """bf16 weight image for the tensor path; a derived cache, rebuilt when a parameter changes."""
-        key = tuple((p.data_ptr(), p._version) for p in params if p is not None)
-        if self._packed is None or key != self._packed_key:
+    def packed(self, params: List[Optional[torch.Tensor]], force: bool = False) -> torch.Tensor:
+        """bf16 weight image for the tensor path; a derived cache of the fp32 parameters.  It is rebuilt on every
+        training forward (``force``: fused optimizers update parameters without bumping ``_version``) and, in eval,
+        whenever a parameter's storage or version changed or the module switched between train() and eval()."""
+        key = tuple((p.data_ptr(), p._version) for p in params if p is not None) + (self.training,)
+        if force or self._packed is None or key != self._packed_key:
             dev = params[0].device
             if self._packed is None or self._packed.device != dev:
                 self._packed = torch.empty(ops.packed_weights_bytes(self.desc), dtype=torch.uint8, device=dev)
@@ -168,7 +170,7 @@ class _RenderStream(torch.autograd.Function):
         for i, slot in enumerate(opts['param_mask']):
             if slot:
                 table[i] = next(it)
-        packed = None if opts['precise'] else block.packed(table)
+        packed = None if opts['precise'] else block.packed(table, force=need_grad)
         ws = torch.empty(ops.mlp_workspace_bytes(block.desc, n, s, flags), dtype=torch.uint8, device=z.device)
         sigma, rgb = ops.mlp_forward(block.desc, table, packed, pts_o, pts_d, view_dirs if block.view_degree else None,
                                      z, noise, ws, flags)
