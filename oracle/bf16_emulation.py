@@ -31,7 +31,13 @@ def mlp_forward_bf16(spec, params, pts, view_dirs, sigma_noise=None):
     x = e_bf[:, :spec.trunk_in]
     h32 = None
     for i in range(spec.depth):
-        h32 = F.relu(F.linear(x, bf(params[f'pts_linears.{i}.weight']), params[f'pts_linears.{i}.bias']))
+        acc = F.linear(x, bf(params[f'pts_linears.{i}.weight']))
+        if i < spec.depth - 1:
+            # hidden layers: packed epilogue, HFMA2.BF16.RELU(bf16(acc), 1, bf16(bias)) = one rounding of the sum
+            h32 = F.relu(bf(bf(acc) + bf(params[f'pts_linears.{i}.bias'])))
+        else:
+            # last trunk layer: fp32 epilogue (its un-rounded output feeds the fp32 sigma head)
+            h32 = F.relu(acc + params[f'pts_linears.{i}.bias'])
         x = bf(h32)
         if i in spec.skips:
             x = torch.cat([e_bf[:, :spec.trunk_in], x], -1)
@@ -43,7 +49,7 @@ def mlp_forward_bf16(spec, params, pts, view_dirs, sigma_noise=None):
     if not spec.view_dep_rgb:
         out['rgb'] = out['rgb_view_independent'] = torch.sigmoid(head[..., 1:4])
         return out
-    feat = bf(F.linear(x, bf(params['feature_linear.weight']), params['feature_linear.bias']))
+    feat = bf(bf(F.linear(x, bf(params['feature_linear.weight']))) + bf(params['feature_linear.bias']))
     wv = params['views_linears.0.weight']
     n_hi = spec.pts_enc_dim - spec.trunk_in
     venc = orc.positional_encoding(view_dirs, spec.view_degree)

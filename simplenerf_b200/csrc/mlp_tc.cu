@@ -4,13 +4,15 @@
 // Reference behaviour: src/models/SimpleNeRF01.py  run_network :363-392, PositionalEncoder :525-557,
 // MLP.forward :626-654, get_view_independent_outputs :656-685, get_view_dependent_outputs :687-715.
 //
-// Forward kernel (one CTA per SM, 128-point tiles, 352 threads):
+// Forward kernel (one CTA per SM, 128-point tiles, 480 threads):
 //   warp 0     weight loader   packed bf16 weight chunks [N x 64] stream L2 -> smem ring by bulk async copy (TMA)
 //   warp 1     MMA issuer      tcgen05.mma M=128, N=256|128, K=16; accumulators ping-pong in TMEM (2 x 256 cols)
-//   warps 2-5  epilogue        TMEM -> regs -> bias/ReLU -> bf16 -> swizzled smem panel (the next layer's A operand);
-//                              sigma / rgb heads in fp32 on CUDA cores from the un-rounded activations
-//   warps 6-9  encoder         rays + depth -> point -> positional encoding -> bf16 panel E of the NEXT tile
-//   warp 10    stash writer    (training) bulk-copies every activation panel to HBM for the backward pass
+//   warps 2-9  epilogue        TMEM -> regs -> bias/ReLU -> bf16 -> swizzled smem panel (the next layer's A operand);
+//                              two warps per SM sub-partition, each owning 32 of a panel's 64 columns; hidden layers
+//                              use one packed HFMA2.BF16.RELU per value pair, the sigma / rgb heads are fp32 dot
+//                              products on the un-rounded activations
+//   warps 10-13 encoder        rays + depth -> point -> positional encoding -> bf16 panel E of the NEXT tile
+//   warp 14    stash writer    (training) bulk-copies every activation panel to HBM for the backward pass
 // The epilogue hands activations to the MMA issuer panel by panel (64 columns), so layer l+1's MMAs start while
 // layer l's epilogue is still running; activations never leave the SM in eval mode.
 #include "common.cuh"
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restri
     if (threadIdx.x == 0) {
         float v[3] = {view_dirs[ray * 3], view_dirs[ray * 3 + 1], view_dirs[ray * 3 + 2]};
         float e[64];
-        encode_point(v, view_degree, e);
+        encode_point_accurate(v, view_degree, e);
         for (int c = 0; c < venc; ++c) ve[c] = e[c];
     }
     __syncthreads();
@@ -87,17 +89,21 @@ __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kFwdThreads = 352;
+constexpr int kFwdThreads = 480;                                       // 15 warps, see the role table above
+constexpr int kEpiWarps = 8;                                            // 2 per SM sub-partition
 constexpr uint32_t kOffH = 0;
 constexpr uint32_t kOffE = 65536;
 constexpr uint32_t kOffRing = kOffE + 2 * kPanelBytes;                 // 98304
 constexpr uint32_t kOffConst = kOffRing + kStages * kStageBytes;        // 196608
-constexpr uint32_t kConstBias = 0;                                      // [9][256] fp32
-constexpr uint32_t kConstHeadW = 9 * 256 * 4;                           // [4][256] fp32
+constexpr uint32_t kConstBias16 = 0;                                    // [9][256] bf16 (packed bias + ReLU path)
+constexpr uint32_t kConstBias32 = 9 * 256 * 2;                          // [256] fp32: bias of the last trunk layer (fp32 head path)
+constexpr uint32_t kConstHeadW = kConstBias32 + 256 * 4;                // [4][256] fp32
 constexpr uint32_t kConstRgbW = kConstHeadW + 4 * 256 * 4;              // [3][128] fp32
 constexpr uint32_t kConstMisc = kConstRgbW + 3 * 128 * 4;               // head bias[4], rgb bias[4]
+constexpr uint32_t kConstPart = kConstMisc + 64;                        // [128][4] fp32 partial head sums of the upper column half
 constexpr uint32_t kOffBars = kOffConst + 16384;
 constexpr uint32_t kFwdSmem = kOffBars + 512 + 1024;                    // + alignment slack
+static_assert(kConstPart + 128 * 4 * 4 <= 16384, "constant area overflow");
 
 struct FwdParams {
     const uint8_t* packed;
@@ -120,53 +126,72 @@ struct FwdBars {
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
+// bf16x2 (acc + bias), optionally ReLU, in one HFMA2: inputs are the packed accumulator pair and the packed bias pair
+__device__ __forceinline__ uint32_t bias_act_bf16x2(float lo, float hi, uint32_t bias2, bool relu) {
+    const __nv_bfloat162 x = __floats2bfloat162_rn(lo, hi);
+    const __nv_bfloat162 one = __floats2bfloat162_rn(1.f, 1.f);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&bias2);
+    const __nv_bfloat162 r = relu ? __hfma2_relu(x, one, b) : __hfma2(x, one, b);
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     FwdBars* bars = (FwdBars*)(smem + kOffBars);
-    float* s_bias = (float*)(smem + kOffConst + kConstBias);
+    __nv_bfloat16* s_bias16 = (__nv_bfloat16*)(smem + kOffConst + kConstBias16);
+    float* s_bias32 = (float*)(smem + kOffConst + kConstBias32);
     float* s_whead = (float*)(smem + kOffConst + kConstHeadW);
     float* s_wrgb = (float*)(smem + kOffConst + kConstRgbW);
     float* s_misc = (float*)(smem + kOffConst + kConstMisc);
+    float* s_part = (float*)(smem + kOffConst + kConstPart);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const bool save = p.stash != nullptr;
 
     // ---- setup ----
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], kCluster); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->enc_ready[i], 128); mbar_init(&bars->enc_free[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&bars->panel_ready[i], 128); mbar_init(&bars->panel_stored[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->panel_ready[i], kEpiWarps * 32); mbar_init(&bars->panel_stored[i], 1); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
     for (int i = threadIdx.x; i < 9 * 256; i += kFwdThreads) {
         const float* b = p.bias[i >> 8];
-        s_bias[i] = b ? b[i & 255] : 0.f;
+        s_bias16[i] = __float2bfloat16_rn(b ? b[i & 255] : 0.f);
     }
+    for (int i = threadIdx.x; i < 256; i += kFwdThreads) s_bias32[i] = p.bias[7][i];
     for (int i = threadIdx.x; i < p.head_out * 256; i += kFwdThreads) s_whead[i] = p.w_head[i];
     if (p.w_rgb) for (int i = threadIdx.x; i < 3 * 128; i += kFwdThreads) s_wrgb[i] = p.w_rgb[i];
     if (threadIdx.x < 4) s_misc[threadIdx.x] = threadIdx.x < p.head_out ? p.b_head[threadIdx.x] : 0.f;
-    if (threadIdx.x >= 4 && threadIdx.x < 7) s_misc[threadIdx.x] = p.b_rgb ? p.b_rgb[threadIdx.x - 4] : 0.f;
+    if (threadIdx.x >= 4 && threadIdx.x < 8) s_misc[threadIdx.x] = (p.b_rgb && threadIdx.x < 7) ? p.b_rgb[threadIdx.x - 4] : 0.f;
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();   // every CTA's barriers are initialised before a peer may signal them
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // every CTA of a cluster runs the same number of tiles (they share one weight ring); tiles >= n_tiles are dummies
+    const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1);
 
     if (warp == 0) {
         // ======================= weight loader =======================
+        // each CTA fetches 1/kCluster of every chunk and multicasts it into the ring of every CTA of the cluster
         if (lane == 0) {
+            const uint32_t rank = cluster_rank();
             uint32_t cnt = 0;
             for (int ti = 0; ti < my_tiles; ++ti)
                 for (int s = 0; s < p.n_steps; ++s) {
                     const TcStep& st = p.steps[s];
                     const uint32_t bytes = (uint32_t)st.n_rows * kRowBytes;
+                    const uint32_t slice = bytes / kCluster;
                     for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
                         const uint32_t stage = cnt % kStages, round = cnt / kStages;
-                        if (round > 0) mbar_wait(&bars->w_empty[stage], (round - 1) & 1);
+                        if (round > 0) mbar_wait(&bars->w_empty[stage], (round - 1) & 1);   // all CTAs released the slot
                         mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
-                        bulk_g2s(smem + kOffRing + stage * kStageBytes, p.packed + st.w_off + (uint32_t)c * bytes, bytes,
-                                 &bars->w_full[stage]);
+                        bulk_g2s_multicast(smem + kOffRing + stage * kStageBytes + rank * slice,
+                                           p.packed + st.w_off + (uint32_t)c * bytes + rank * slice, slice,
+                                           &bars->w_full[stage], kClusterMask);
                     }
                 }
         }
@@ -198,7 +223,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                         const uint32_t b_addr = smem_u32(smem + kOffRing + stage * kStageBytes);
                         for (int k = 0; k < st.ksteps[c]; ++k)
                             umma(d_tmem, umma_desc_kmajor(a_addr, k), umma_desc_kmajor(b_addr, k), idesc, (c | k) != 0);
-                        umma_commit(&bars->w_empty[stage]);
+                        umma_commit_multicast(&bars->w_empty[stage], kClusterMask);   // frees the slot in every CTA's ring
                     }
                     umma_commit(&bars->acc_full[it & 1]);
                     if (st.last_e_use) umma_commit(&bars->enc_free[ebuf]);
@@ -207,9 +232,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + kEpiWarps) {
         // ======================= epilogue =======================
-        const int q = warp & 3;
+        // warp (q, hf): TMEM lanes / tile rows 32q..32q+31, columns [32 hf, 32 hf + 32) of every 64-column panel
+        const int q = warp & 3, hf = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0;
@@ -225,102 +251,110 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 tc_fence_after();
                 const int n_pan = st.n_rows / 64;
                 const bool writes_h = (kind != EPI_VIEW) || save;
-                float head[4];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) head[h] = s_misc[(kind == EPI_VIEW ? 4 : 0) + h];
+                const bool has_head = kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4 || kind == EPI_VIEW;
+                float head[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int j = 0; j < 4; ++j) {
                     if (j < n_pan) {
-                        float v[64];
-                        {
-                            float t[32];
-                            tmem_ld32(lane_addr + (it & 1) * 256 + j * 64, t);
+                        const int col0 = j * 64 + hf * 32;
+                        float v[32];
+                        tmem_ld32(lane_addr + (it & 1) * 256 + col0, v);
+                        uint32_t pk[16];
+                        if (kind == EPI_RELU || kind == EPI_LINEAR) {
+                            const uint4* bb = reinterpret_cast<const uint4*>(s_bias16 + st.bias_row * 256 + col0);
+                            const bool relu = kind == EPI_RELU;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = t[i];
-                            tmem_ld32(lane_addr + (it & 1) * 256 + j * 64 + 32, t);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[32 + i] = t[i];
-                        }
-                        if (kind == EPI_VIEW) {
-                            const float4* vb = reinterpret_cast<const float4*>(p.view_bias + (size_t)ray * 128 + j * 64);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float4 b = __ldg(vb + i);
-                                v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
-                                v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
-                                v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
-                                v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
-                            }
-#pragma unroll
-                            for (int h = 0; h < 3; ++h) {
-                                const float4* w = reinterpret_cast<const float4*>(s_wrgb + h * 128 + j * 64);
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    const float4 ww = w[i];
-                                    head[h] = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, head[h]))));
-                                }
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 b = bb[i];
+                                pk[4 * i + 0] = bias_act_bf16x2(v[8 * i + 0], v[8 * i + 1], b.x, relu);
+                                pk[4 * i + 1] = bias_act_bf16x2(v[8 * i + 2], v[8 * i + 3], b.y, relu);
+                                pk[4 * i + 2] = bias_act_bf16x2(v[8 * i + 4], v[8 * i + 5], b.z, relu);
+                                pk[4 * i + 3] = bias_act_bf16x2(v[8 * i + 6], v[8 * i + 7], b.w, relu);
                             }
                         } else {
-                            const float4* bb = reinterpret_cast<const float4*>(s_bias + st.bias_row * 256 + j * 64);
-                            const bool relu = kind != EPI_LINEAR;
+                            if (kind == EPI_VIEW) {
+                                const float4* vb = reinterpret_cast<const float4*>(p.view_bias + (size_t)ray * 128 + col0);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float4 b = bb[i];
-                                v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-                            }
-                            if (relu) {
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 b = __ldg(vb + i);
+                                    v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
+                                    v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
+                                    v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
+                                    v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
+                                }
+                            } else {
+                                const float4* bb = reinterpret_cast<const float4*>(s_bias32 + col0);
 #pragma unroll
-                                for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
-                            }
-                            if (kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4) {
-                                const int nh = kind == EPI_RELU_HEAD1 ? 1 : 4;
-#pragma unroll
-                                for (int h = 0; h < 4; ++h) {
-                                    if (h < nh) {
-                                        const float4* w = reinterpret_cast<const float4*>(s_whead + h * 256 + j * 64);
-                                        float a = head[h];
-#pragma unroll
-                                        for (int i = 0; i < 16; ++i) {
-                                            const float4 ww = w[i];
-                                            a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
-                                        }
-                                        head[h] = a;
-                                    }
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 b = bb[i];
+                                    v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
+                                    v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
+                                    v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
+                                    v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
                                 }
                             }
+                            // fp32 heads on the un-rounded activations
+                            const float* wbase = kind == EPI_VIEW ? s_wrgb : s_whead;
+                            const int wld = kind == EPI_VIEW ? 128 : 256;
+                            const int nh = kind == EPI_RELU_HEAD1 ? 1 : (kind == EPI_VIEW ? 3 : 4);
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                if (h < nh) {
+                                    const float4* w = reinterpret_cast<const float4*>(wbase + h * wld + col0);
+                                    float a = head[h];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float4 ww = w[i];
+                                        a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
+                                    }
+                                    head[h] = a;
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
                         }
                         if (writes_h) {
                             if (save && it > 0) mbar_wait(&bars->panel_stored[j], (it - 1) & 1);
                             uint8_t* dst = smem + kOffH + j * kPanelBytes;
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const uint4 u = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                                                           pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
-                                *reinterpret_cast<uint4*>(dst + swz_offset(row, c)) = u;
-                            }
+                            for (int c = 0; c < 4; ++c)
+                                *reinterpret_cast<uint4*>(dst + swz_offset(row, hf * 4 + c)) =
+                                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                             fence_async_smem();
                         }
                     }
                     tc_fence_before();
                     mbar_arrive(&bars->panel_ready[j]);
                 }
-                if (valid) {
-                    if (kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4) {
-                        const float nz = p.noise ? p.noise[pt] : 0.f;
-                        p.sigma[pt] = fmaxf(head[0] + nz, 0.f);                                        // :668-672
-                        if (kind == EPI_RELU_HEAD4) {
+                if (has_head) {
+                    // combine the two column halves: the upper half hands its partial sums to the lower half
+                    if (hf == 1) {
 #pragma unroll
-                            for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
+                        for (int h = 0; h < 4; ++h) s_part[row * 4 + h] = head[h];
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                    if (hf == 0 && valid) {
+                        const float4 o = *reinterpret_cast<const float4*>(s_part + row * 4);
+                        const int mb = kind == EPI_VIEW ? 4 : 0;
+                        head[0] += o.x + s_misc[mb + 0]; head[1] += o.y + s_misc[mb + 1];
+                        head[2] += o.z + s_misc[mb + 2]; head[3] += o.w + s_misc[mb + 3];
+                        if (kind == EPI_VIEW) {
+#pragma unroll
+                            for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h]);             // :704-707
+                        } else {
+                            const float nz = p.noise ? p.noise[pt] : 0.f;
+                            p.sigma[pt] = fmaxf(head[0] + nz, 0.f);                                        // :668-672
+                            if (kind == EPI_RELU_HEAD4) {
+#pragma unroll
+                                for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
+                            }
                         }
-                    } else if (kind == EPI_VIEW) {
-#pragma unroll
-                        for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h]);             // :704-707
                     }
                 }
             }
         }
-    } else if (warp < 10) {
+    } else if (warp < 2 + kEpiWarps + 4) {
         // ======================= encoder =======================
-        const int row = (warp - 6) * 32 + lane;
+        const int row = (warp - 2 - kEpiWarps) * 32 + lane;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = blockIdx.x + ti * gridDim.x;
             const int ebuf = ti & 1;
@@ -359,7 +393,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     const int n_pan = st.n_rows / 64;
                     for (int j = 0; j < 4; ++j) {
                         mbar_wait(&bars->panel_ready[j], it & 1);
-                        if (j < n_pan) {
+                        if (j < n_pan && tile < p.n_tiles) {
                             bulk_s2g(base + (size_t)st.slot * 65536 + j * kPanelBytes, smem + kOffH + j * kPanelBytes, kPanelBytes);
                             bulk_commit();
                         }
@@ -374,6 +408,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
     __syncwarp();
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();   // no CTA leaves while a peer may still multicast into its ring or signal its barriers
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
@@ -416,9 +451,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
         SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
         attr = true;
     }
-    const int grid = w.n_tiles < num_sms() ? w.n_tiles : num_sms();
-    tc_forward_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(p);
-    SNERF_LAUNCH_OK("tc_forward_kernel");
+    SNERF_CUDA_OK(launch_clustered(tc_forward_kernel, chain_grid(w.n_tiles), kFwdThreads, kFwdSmem, st, p));
     return SNERF_OK;
 }
 

@@ -24,7 +24,8 @@ using namespace tc;
 // =================================================================================================
 // dgrad chain kernel
 // =================================================================================================
-constexpr int kBwdThreads = 352;
+constexpr int kBwdThreads = 480;   // loader, MMA, 8 epilogue, 4 prologue, stash writer
+constexpr int kBwdEpiWarps = 8;
 constexpr uint32_t kBOffH = 0;
 constexpr uint32_t kBOffP = 65536;                                  // 3 panels: dY_v (2) + head-pre (1)
 constexpr uint32_t kBOffRing = kBOffP + 3 * kPanelBytes;             // 114688
@@ -56,9 +57,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], kCluster); }
         for (int i = 0; i < 2; ++i) mbar_init(&bars->acc_full[i], 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&bars->panel_ready[i], 128); mbar_init(&bars->panel_stored[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->panel_ready[i], kBwdEpiWarps * 32); mbar_init(&bars->panel_stored[i], 1); }
         mbar_init(&bars->pro_ready, 128);
         mbar_init(&bars->pro_free, 1);
         mbar_init(&bars->pro_stored, 1);
@@ -68,24 +69,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     if (p.w_rgb) for (int i = threadIdx.x; i < 3 * 128; i += kBwdThreads) s_wrgb[i] = p.w_rgb[i];
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;   // uniform per cluster; tiles >= n_tiles are dummies
+    constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1);
 
     if (warp == 0) {
-        // ======================= weight loader =======================
+        // ======================= weight loader (1/kCluster of every chunk, multicast to the cluster) =======================
         if (lane == 0) {
+            const uint32_t rank = cluster_rank();
             uint32_t cnt = 0;
             for (int ti = 0; ti < my_tiles; ++ti)
                 for (int s = 0; s < p.n_steps; ++s) {
                     const TcStep& st = p.steps[s];
                     const uint32_t bytes = (uint32_t)st.n_rows * kRowBytes;
+                    const uint32_t slice = bytes / kCluster;
                     for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
                         const uint32_t stage = cnt % kStages, round = cnt / kStages;
                         if (round > 0) mbar_wait(&bars->w_empty[stage], (round - 1) & 1);
                         mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
-                        bulk_g2s(smem + kBOffRing + stage * kStageBytes, p.packed + st.w_off + (uint32_t)c * bytes, bytes,
-                                 &bars->w_full[stage]);
+                        bulk_g2s_multicast(smem + kBOffRing + stage * kStageBytes + rank * slice,
+                                           p.packed + st.w_off + (uint32_t)c * bytes + rank * slice, slice,
+                                           &bars->w_full[stage], kClusterMask);
                     }
                 }
         }
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                         const uint32_t b_addr = smem_u32(smem + kBOffRing + stage * kStageBytes);
                         for (int k = 0; k < st.ksteps[c]; ++k)
                             umma(d_tmem, umma_desc_kmajor(a_addr, k), umma_desc_kmajor(b_addr, k), idesc, (c | k) != 0);
-                        umma_commit(&bars->w_empty[stage]);
+                        umma_commit_multicast(&bars->w_empty[stage], kClusterMask);
                     }
                     umma_commit(&bars->acc_full[it & 1]);
                     if (st.last_e_use) umma_commit(&bars->pro_free);
@@ -124,9 +130,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                 }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + kBwdEpiWarps) {
         // ======================= epilogue: ReLU mask, bf16, next A operand =======================
-        const int q = warp & 3;
+        // warp (q, hf): rows 32q..32q+31, columns [32 hf, 32 hf + 32) of every panel
+        const int q = warp & 3, hf = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0;
@@ -135,59 +142,55 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
             const uint8_t* act_tile = p.act + (size_t)tile * p.tile_stash_bytes;
             for (int s = 0; s < p.n_steps; ++s, ++it) {
                 const TcStep& st = p.steps[s];
-                const bool masked = st.kind == BWD_MASK;
+                const bool masked = st.kind == BWD_MASK && tile < p.n_tiles;   // dummy tiles carry zero gradients
                 const uint8_t* mrow = act_tile + (size_t)st.mask_slot * 65536;
                 bool acc_ready = false;
                 for (int j = 0; j < 4; ++j) {
-                    uint4 mk[8];
+                    uint4 mk[4];
                     if (masked) {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            mk[c] = __ldg(reinterpret_cast<const uint4*>(mrow + j * kPanelBytes + swz_offset(row, c)));
+                        for (int c = 0; c < 4; ++c)
+                            mk[c] = __ldg(reinterpret_cast<const uint4*>(mrow + j * kPanelBytes + swz_offset(row, hf * 4 + c)));
                     }
                     if (!acc_ready) {
                         mbar_wait(&bars->acc_full[it & 1], (it >> 1) & 1);
                         tc_fence_after();
                         acc_ready = true;
                     }
-                    float v[64];
-                    {
-                        float t[32];
-                        tmem_ld32(lane_addr + (it & 1) * 256 + j * 64, t);
+                    float v[32];
+                    tmem_ld32(lane_addr + (it & 1) * 256 + j * 64 + hf * 32, v);
+                    uint32_t pk[16];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = t[i];
-                        tmem_ld32(lane_addr + (it & 1) * 256 + j * 64 + 32, t);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[32 + i] = t[i];
-                    }
+                    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
                     if (masked) {
+                        const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
+                        for (int c = 0; c < 4; ++c) {
                             const uint32_t w[4] = {mk[c].x, mk[c].y, mk[c].z, mk[c].w};
 #pragma unroll
                             for (int h = 0; h < 4; ++h) {
-                                if ((w[h] & 0xFFFFu) == 0u) v[8 * c + 2 * h] = 0.f;
-                                if ((w[h] >> 16) == 0u) v[8 * c + 2 * h + 1] = 0.f;
+                                // dY * [h > 0] on a bf16 pair: __hgt2 yields 1.0 / 0.0 per half
+                                const __nv_bfloat162 ind = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&w[h]), zero);
+                                const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&pk[4 * c + h]), ind);
+                                pk[4 * c + h] = *reinterpret_cast<const uint32_t*>(&r);
                             }
                         }
                     }
                     if (it > 0) mbar_wait(&bars->panel_stored[j], (it - 1) & 1);
                     uint8_t* dst = smem + kBOffH + j * kPanelBytes;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint4 u = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                                                   pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
-                        *reinterpret_cast<uint4*>(dst + swz_offset(row, c)) = u;
-                    }
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(dst + swz_offset(row, hf * 4 + c)) =
+                            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                     fence_async_smem();
                     tc_fence_before();
                     mbar_arrive(&bars->panel_ready[j]);
                 }
             }
         }
-    } else if (warp < 10) {
+    } else if (warp < 2 + kBwdEpiWarps + 4) {
         // ======================= prologue: head gradients of the next tile =======================
-        const int row = (warp - 6) * 32 + lane;
+        const int row = (warp - 2 - kBwdEpiWarps) * 32 + lane;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = blockIdx.x + ti * gridDim.x;
             const long long pt = (long long)tile * kTileRows + row;
@@ -205,7 +208,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                 const uint8_t* hv = p.act + (size_t)tile * p.tile_stash_bytes + (size_t)9 * 65536;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    mk[i] = __ldg(reinterpret_cast<const uint4*>(hv + (i >> 3) * kPanelBytes + swz_offset(row, i & 7)));
+                    mk[i] = tile < p.n_tiles ? __ldg(reinterpret_cast<const uint4*>(hv + (i >> 3) * kPanelBytes + swz_offset(row, i & 7)))
+                                             : make_uint4(0u, 0u, 0u, 0u);
             }
             if (ti > 0) {
                 mbar_wait(&bars->pro_free, (ti - 1) & 1);
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                 const int tile = blockIdx.x + ti * gridDim.x;
                 uint8_t* base = p.dy + (size_t)tile * p.tile_stash_bytes;
                 mbar_wait(&bars->pro_ready, ti & 1);
-                if (p.has_view) {
+                if (p.has_view && tile < p.n_tiles) {
                     bulk_s2g(base + (size_t)9 * 65536, smem + kBOffP, 2 * kPanelBytes);
                     bulk_commit();
                     bulk_wait_read<0>();
@@ -255,8 +259,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                     const TcStep& st = p.steps[s];
                     for (int j = 0; j < 4; ++j) {
                         mbar_wait(&bars->panel_ready[j], it & 1);
-                        bulk_s2g(base + (size_t)st.slot * 65536 + j * kPanelBytes, smem + kBOffH + j * kPanelBytes, kPanelBytes);
-                        bulk_commit();
+                        if (tile < p.n_tiles) {
+                            bulk_s2g(base + (size_t)st.slot * 65536 + j * kPanelBytes, smem + kBOffH + j * kPanelBytes, kPanelBytes);
+                            bulk_commit();
+                        }
                     }
                     bulk_wait_read<0>();
                     for (int j = 0; j < 4; ++j) mbar_arrive(&bars->panel_stored[j]);
@@ -268,6 +274,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     __syncwarp();
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
@@ -474,10 +481,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                             float v[32];
                             tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mb * 256 + sg.d_col + c0, v);
                             float* dst = job.dw + (size_t)out_row * job.ld + sg.dst_col;
+                            const bool vec = ((job.ld | sg.dst_col | sg.k_lo) & 3) == 0 && c0 >= sg.k_lo && c0 + 32 <= sg.k_hi &&
+                                             (reinterpret_cast<uintptr_t>(job.dw) & 15) == 0;
+                            if (vec) {   // whole 32-column chunk valid and 16-byte aligned: 8 vector reductions
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int n = c0 + i;
-                                if (n >= sg.k_lo && n < sg.k_hi) atomicAdd(dst + (n - sg.k_lo), v[i]);
+                                for (int i = 0; i < 32; i += 4) red_add_v4(dst + (c0 - sg.k_lo) + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    const int n = c0 + i;
+                                    if (n >= sg.k_lo && n < sg.k_hi) atomicAdd(dst + (n - sg.k_lo), v[i]);
+                                }
                             }
                         }
                     }
@@ -604,8 +618,7 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         SNERF_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
         attr = true;
     }
-    tc_dgrad_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(bp);
-    SNERF_LAUNCH_OK("tc_dgrad_kernel");
+    SNERF_CUDA_OK(launch_clustered(tc_dgrad_kernel, chain_grid(w.n_tiles), kBwdThreads, kBwdSmem, st, bp));
 
     // ---- (2) wgrad ----
     WgParams wp{};

@@ -194,9 +194,14 @@ class _RenderStream(torch.autograd.Function):
                                                 opts['white_bkgd'], grads_in)
         table: List[Optional[torch.Tensor]] = [None] * P_COUNT
         gtable: List[Optional[torch.Tensor]] = [None] * P_COUNT
-        sizes = [p.numel() for p in params]
-        flat = torch.zeros(sum(sizes), device=z.device)   # one contiguous gradient bucket per MLP
-        views = flat.split(sizes)
+        # one contiguous, zero-initialised gradient bucket per MLP; every tensor starts 16-byte aligned so that the
+        # wgrad kernel can flush with vector reductions
+        offsets, total = [], 0
+        for p in params:
+            offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        flat = torch.zeros(total, device=z.device)
+        views = [flat[o:o + p.numel()] for o, p in zip(offsets, params)]
         it = iter(zip(params, views))
         out_grads = []
         for i, slot in enumerate(opts['param_mask']):

@@ -8,46 +8,14 @@ from simplenerf_b200 import ops, synthetic
 from simplenerf_b200._lib import FLAG_PRECISE, FLAG_SAVE_FOR_BWD
 from simplenerf_b200.models.FusedSimpleNeRF01 import MlpBlock
 DEV = 'cuda:0'
-import torch.nn.functional as F
-
-
-class _Bf(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x):
-        return x.to(torch.bfloat16).to(torch.float32)
-
-    @staticmethod
-    def backward(ctx, g):
-        return g
-
-
-bf = _Bf.apply
+from oracle.bf16_emulation import mlp_forward_bf16
 
 
 def mlp_bf16_emulated(spec, P, pts, vd, noise):
-    """torch restatement of the tensor path's rounding points (straight-through in backward)."""
-    enc = orc.positional_encoding(pts, spec.pts_degree)
-    e_bf = bf(enc)
-    x = e_bf[:, :spec.trunk_in]
-    h32 = None
-    for i in range(spec.depth):
-        h32 = F.relu(F.linear(x, bf(P[f'pts_linears.{i}.weight']), P[f'pts_linears.{i}.bias']))
-        x = bf(h32)
-        if i in spec.skips:
-            x = torch.cat([e_bf[:, :spec.trunk_in], x], -1)
-    head = F.linear(h32, P['pts_output_linear.weight'], P['pts_output_linear.bias'])
-    sigma = F.relu(head[..., :1] + noise)
-    if not spec.view_dep_rgb:
-        return sigma, torch.sigmoid(head[..., 1:4])
-    feat = bf(F.linear(x, bf(P['feature_linear.weight']), P['feature_linear.bias']))
-    Wv = P['views_linears.0.weight']
-    nh = spec.pts_enc_dim - spec.trunk_in
-    venc = orc.positional_encoding(vd, spec.view_degree)
-    pre = F.linear(feat, bf(Wv[:, :256])) + F.linear(venc, Wv[:, 256 + nh:], P['views_linears.0.bias'])
-    if nh:
-        pre = pre + F.linear(e_bf[:, spec.trunk_in:], bf(Wv[:, 256:256 + nh]))
-    hv = F.relu(pre)
-    return sigma, torch.sigmoid(F.linear(hv, P['views_output_linear.weight'], P['views_output_linear.bias']))
+    out = mlp_forward_bf16(spec, P, pts, vd, noise)
+    return out["sigma"], out["rgb"]
+
+
 configs = synthetic.make_configs('simplenerf')
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 700
 gen = torch.Generator().manual_seed(2)
