@@ -113,6 +113,7 @@ struct FwdParams {
     const float *rays_o, *rays_d, *z, *noise;
     float *sigma, *rgb;
     uint8_t* stash;                // null in eval
+    long long* trace;              // debug: clock64 timestamps of CTA 0 (tools/trace_fwd.py), normally null
     long long n_points;
     int n_samples, n_tiles, n_steps, pts_degree, head_out;
     uint32_t tile_stash_bytes;
@@ -137,7 +138,7 @@ __device__ __forceinline__ uint32_t bias_act_bf16x2(float lo, float hi, uint32_t
 
 __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     FwdBars* bars = (FwdBars*)(smem + kOffBars);
     __nv_bfloat16* s_bias16 = (__nv_bfloat16*)(smem + kOffConst + kConstBias16);
     float* s_bias32 = (float*)(smem + kOffConst + kConstBias32);
@@ -249,6 +250,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 const int kind = st.kind;
                 mbar_wait(&bars->acc_full[it & 1], (it >> 1) & 1);
                 tc_fence_after();
+                const bool tr = p.trace && blockIdx.x == 0 && ti == 2 && warp == 4 && lane == 0;
+                if (tr) p.trace[256 + s * 16 + 0] = clock64();     // epilogue: accumulator complete
                 const int n_pan = st.n_rows / 64;
                 const bool writes_h = (kind != EPI_VIEW) || save;
                 const bool has_head = kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4 || kind == EPI_VIEW;
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                         const int col0 = j * 64 + hf * 32;
                         float v[32];
                         tmem_ld32(lane_addr + (it & 1) * 256 + col0, v);
+                        if (tr) p.trace[256 + s * 16 + 1 + j] = clock64();     // TMEM load of panel j done
                         uint32_t pk[16];
                         if (kind == EPI_RELU || kind == EPI_LINEAR) {
                             const uint4* bb = reinterpret_cast<const uint4*>(s_bias16 + st.bias_row * 256 + col0);
@@ -314,16 +318,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                         }
                         if (writes_h) {
                             if (save && it > 0) mbar_wait(&bars->panel_stored[j], (it - 1) & 1);
+                            if (tr && j == 1) p.trace[256 + s * 16 + 9] = clock64();      // math done (panel 1)
                             uint8_t* dst = smem + kOffH + j * kPanelBytes;
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
                                 *reinterpret_cast<uint4*>(dst + swz_offset(row, hf * 4 + c)) =
                                     make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                            if (tr && j == 1) p.trace[256 + s * 16 + 10] = clock64();     // stores issued
                             fence_async_smem();
+                            if (tr && j == 1) p.trace[256 + s * 16 + 11] = clock64();     // proxy fence done
                         }
                     }
                     tc_fence_before();
                     mbar_arrive(&bars->panel_ready[j]);
+                    if (tr) p.trace[256 + s * 16 + 5 + j] = clock64();         // panel j handed over
                 }
                 if (has_head) {
                     // combine the two column halves: the upper half hands its partial sums to the lower half
@@ -419,6 +427,8 @@ size_t tc_workspace_bytes(const MlpDims& m, const snerf_mlp_desc& d, int n_rays,
     return tc_ws_layout(m, build_plan(d, nullptr), n_rays, n_samples, flags).total;
 }
 
+static long long* g_trace = nullptr;   // set by snerfdbg_set_trace (debug only)
+
 int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o, const float* rays_d,
                const float* view_dirs, const float* z, const float* noise, float* sigma, float* rgb, void* ws, size_t ws_bytes,
                int n_rays, int n_samples, uint32_t flags, cudaStream_t st) {
@@ -442,6 +452,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     p.view_bias = (const float*)(wsb + w.view_bias);
     p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.noise = noise; p.sigma = sigma; p.rgb = rgb;
     p.stash = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.act : nullptr;
+    p.trace = g_trace;
     p.n_points = (long long)n_rays * n_samples;
     p.n_samples = n_samples; p.n_tiles = w.n_tiles; p.n_steps = pl.n_fwd; p.pts_degree = d.pts_degree; p.head_out = m.head_out;
     p.tile_stash_bytes = pl.tile_stash_bytes;
@@ -465,10 +476,12 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict
                                                        const uint8_t* __restrict__ b_img, uint32_t b_bytes,
                                                        float* __restrict__ d_out, const ProbeOp* __restrict__ ops, int n_ops,
                                                        uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
-                                                       uint32_t idesc, uint64_t desc_bits, int n_cols) {
+                                                       uint32_t idesc, uint64_t desc_bits, int n_cols, long long* timing) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar_load, bar_mma;
     __shared__ uint32_t tmem_base_s;
+    __shared__ ProbeOp s_ops[256];
+    for (int i = threadIdx.x; i < n_ops && i < 256; i += blockDim.x) s_ops[i] = ops[i];
     uint8_t* sa = smem;
     uint8_t* sb = smem + 65536;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -488,8 +501,9 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict
         bulk_g2s(sb, b_img, b_bytes, &bar_load);
         mbar_wait(&bar_load, 0);
         tc_fence_after();
+        const long long t_start = clock64();
         for (int i = 0; i < n_ops; ++i) {
-            const ProbeOp op = ops[i];
+            const ProbeOp op = s_ops[i];
             const uint32_t aa = smem_u32(sa) + op.a_off, ba = smem_u32(sb) + op.b_off;
             const uint64_t ad = (uint64_t)((aa >> 4) & 0x3FFFu) | ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) |
                                 ((uint64_t)((a_sbo >> 4) & 0x3FFFu) << 32) | desc_bits;
@@ -497,7 +511,11 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict
                                 ((uint64_t)((b_sbo >> 4) & 0x3FFFu) << 32) | desc_bits;
             umma(tmem_base + op.d_col, ad, bd, idesc, op.accumulate != 0);
         }
+        const long long t_issued = clock64();
         umma_commit(&bar_mma);
+        mbar_wait(&bar_mma, 0);
+        const long long t_done = clock64();
+        if (timing) { timing[0] = t_issued - t_start; timing[1] = t_done - t_start; }
     }
     __syncwarp();
     mbar_wait(&bar_mma, 0);
@@ -524,15 +542,17 @@ int tc_selftest(float* host_max_err, cudaStream_t) {
 using namespace snerf;
 extern "C" int snerf_has_tensor_path(void) { return 1; }
 
+extern "C" void snerfdbg_set_trace(long long* device_buffer_512) { snerf::g_trace = device_buffer_512; }
+
 // debug entry (not part of the public ABI): all pointers are device pointers
 extern "C" int snerfdbg_probe(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, float* d_out,
                               const void* ops, int n_ops, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
-                              uint32_t idesc, uint64_t desc_bits, int n_cols, void* stream) {
-    SNERF_REQUIRE(a_bytes <= 65536 && b_bytes <= 131072 && n_cols % 32 == 0 && n_cols <= 512, "probe: bad sizes");
+                              uint32_t idesc, uint64_t desc_bits, int n_cols, void* stream, long long* timing) {
+    SNERF_REQUIRE(a_bytes <= 65536 && b_bytes <= 131072 && n_cols % 32 == 0 && n_cols <= 512 && n_ops <= 256, "probe: bad sizes");
     SNERF_CUDA_OK(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 131072));
     tc_probe_kernel<<<1, 128, 65536 + 131072, (cudaStream_t)stream>>>((const uint8_t*)a_img, a_bytes, (const uint8_t*)b_img,
                                                                     b_bytes, d_out, (const ProbeOp*)ops, n_ops, a_lbo, a_sbo,
-                                                                    b_lbo, b_sbo, idesc, desc_bits, n_cols);
+                                                                    b_lbo, b_sbo, idesc, desc_bits, n_cols, timing);
     SNERF_LAUNCH_OK("tc_probe_kernel");
     return SNERF_OK;
 }

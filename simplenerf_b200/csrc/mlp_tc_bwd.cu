@@ -51,7 +51,7 @@ struct BwdBars {
 
 __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_constant__ BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     BwdBars* bars = (BwdBars*)(smem + kBOffBars);
     float* s_wrgb = (float*)(smem + kBOffConst);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -328,7 +328,7 @@ __device__ __forceinline__ float bf16_at(const uint8_t* panel_base, int r, int c
 
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     WgBars* bars = (WgBars*)(smem + kWgOffBars);
     float* s_dh = (float*)(smem + kWgOffDh);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;

@@ -1,0 +1,38 @@
+"""Timeline of one tile of the forward chain kernel (CTA 0, third tile): clock64 stamps of the MMA issuer and of one
+epilogue warp.  Debug tool for the pipeline analysis in profiles/."""
+import sys, os, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from simplenerf_b200 import ops, synthetic, _lib
+from simplenerf_b200._lib import FLAG_SAVE_FOR_BWD
+from simplenerf_b200.models.FusedSimpleNeRF01 import MlpBlock
+
+DEV = 'cuda:0'
+lib = _lib.load()
+save = '--save' in sys.argv
+cfg = synthetic.make_configs('simplenerf')['model']['coarse_mlp']
+block = MlpBlock(cfg).to(DEV)
+table = [None if p is None else p.detach() for p in block.param_table()]
+packed = block.packed(table)
+n_rays, s = 4096, 64
+b = synthetic.make_ray_batch('llff', n_rays, 3)
+o, d, vd = b['rays_o_ndc'].to(DEV), b['rays_d_ndc'].to(DEV), b['view_dirs'].to(DEV)
+z = torch.sort(torch.rand(n_rays, s, device=DEV), -1)[0].contiguous()
+flags = FLAG_SAVE_FOR_BWD if save else 0
+ws = torch.empty(ops.mlp_workspace_bytes(block.desc, n_rays, s, flags), dtype=torch.uint8, device=DEV)
+trace = torch.zeros(512, dtype=torch.int64, device=DEV)
+for _ in range(2):
+    ops.mlp_forward(block.desc, table, packed, o, d, vd, z, None, ws, flags)
+lib.snerfdbg_set_trace.argtypes = [ctypes.c_void_p]
+lib.snerfdbg_set_trace(trace.data_ptr())
+ops.mlp_forward(block.desc, table, packed, o, d, vd, z, None, ws, flags)
+torch.cuda.synchronize()
+lib.snerfdbg_set_trace(None)
+t = trace.cpu().numpy()
+t0 = t[256]   # epilogue: accumulator of step 0 complete
+rel = lambda v: int(v - t0) if v else None
+print('step | MMA issued || EPI: acc done | tmem-ld done p0..p3 | handed p0..p3 | panel1: math done, stores issued, fence done')
+for s_ in range(10):
+    m = t[s_ * 16: s_ * 16 + 16]; e = t[256 + s_ * 16: 256 + s_ * 16 + 16]
+    print(f'{s_:2d} | {rel(m[0])} || {rel(e[0])} | {[rel(x) for x in e[1:5]]} | {[rel(x) for x in e[5:9]]} | {[rel(x) for x in e[9:12]]}')
