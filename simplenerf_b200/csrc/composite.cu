@@ -1,9 +1,13 @@
-// Alpha compositing, forward and backward: one warp per ray, shuffle scans, fp32.
+// Alpha compositing, forward and backward: one warp per ray, fp32, HBM-bound.
 //
 // Reference behaviour (src/models/SimpleNeRF01.py): volume_rendering :430-483 and
-// convert_depth_from_ndc :485-502.  Lane l of the warp owns samples l, l+32, l+64, ... so that every
-// global access of sigma / z / per-sample outputs is a coalesced 128-byte row; the transmittance is an
-// exclusive product scan (5 shuffle steps per 32-sample chunk plus a running carry).
+// convert_depth_from_ndc :485-502.
+//
+// Layout of the work: lane l of the warp owns C = S/32 CONSECUTIVE samples (l*C .. l*C+C-1), so sigma, z and rgb are
+// read with 8/16-byte vector loads that are contiguous across the warp (fully coalesced 128-byte lines, no strided
+// rgb access), the transmittance needs one lane-local product plus ONE 5-step shuffle scan per ray, and every per-sample
+// output is a vector store.  Rays whose sample count is not a multiple of 32 take the strided fallback (lane l owns
+// samples l, l+32, ...).
 #include "common.cuh"
 
 namespace snerf {
@@ -27,116 +31,192 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Per-ray constants and the per-sample quantities every pass needs.
-template <int ITEMS>
-struct RayState {
-    float sig[ITEMS], zz[ITEMS], zm[ITEMS];   // sigma, z (ndc or metric), metric z
-    float delta[ITEMS], alpha[ITEMS], trans[ITEMS], w[ITEMS];
-    float acc, dsum, dsum_ndc;   // sum w, sum w*zm, sum w*z_ndc
-};
-
-template <int ITEMS>
-__device__ __forceinline__ void load_and_scan(const CompositeArgs& a, int ray, int lane, RayState<ITEMS>& r) {
-    const int s = a.s;
-    const float* sig = a.sigma + (size_t)ray * s;
-    const float* z = a.z + (size_t)ray * s;
-    const float* dvec = (a.ndc ? a.rays_d_ndc : a.rays_d) + (size_t)ray * 3;
-    const float dn = sqrtf(dvec[0] * dvec[0] + dvec[1] * dvec[1] + dvec[2] * dvec[2]);          // :436 / :441
-    const float tail = a.ndc ? 1.f : 1e10f;                                                     // :433 / :438
-    float oz = 0.f, dz = 1.f, tn = 0.f;
-    if (a.ndc) {
-        oz = a.rays_o[(size_t)ray * 3 + 2];
-        dz = a.rays_d[(size_t)ray * 3 + 2];
-        tn = -(1.f + oz) / dz;                                                                  // :498
-    }
+// ---- vector access of C consecutive floats (C even) -------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[C]) {
+    if constexpr (C % 4 == 0) {
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const int k = i * kWarp + lane;
-        r.sig[i] = 0.f;
-        r.zz[i] = 0.f;
-        float znext = 0.f;
-        if (k < s) {
-            r.sig[i] = sig[k];
-            r.zz[i] = z[k];
-            znext = (k + 1 < s) ? z[k + 1] : tail;
+        for (int i = 0; i < C / 4; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
-        r.delta[i] = (znext - r.zz[i]) * dn;                                                    // :435-436
-        r.alpha[i] = (k < s) ? 1.f - expf(-r.sig[i] * r.delta[i]) : 0.f;                        // :446
-        if (a.ndc) {
-            const float guard = (r.zz[i] == 1.f) ? 1e-3f : 0.f;                                 // :499
-            r.zm[i] = (oz + tn * dz) / dz * (1.f / (1.f - r.zz[i] + guard) - 1.f) + tn;         // :501
-        } else {
-            r.zm[i] = r.zz[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < C / 2; ++i) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(p) + i);
+            v[2 * i] = t.x; v[2 * i + 1] = t.y;
         }
     }
-    // exclusive product scan of (1 - alpha + 1e-10)                                            // :447
-    float carry = 1.f;
-    r.acc = r.dsum = r.dsum_ndc = 0.f;
+}
+template <int C>
+__device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v)[C]) {
+    if constexpr (C % 4 == 0) {
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const int k = i * kWarp + lane;
-        const float f = (k < s) ? (1.f - r.alpha[i]) + 1e-10f : 1.f;
-        float incl = f;
+        for (int i = 0; i < C / 4; ++i)
+            reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
 #pragma unroll
-        for (int o = 1; o < kWarp; o <<= 1) {
-            const float v = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl *= v;
-        }
-        float excl = __shfl_up_sync(kFull, incl, 1);
-        if (lane == 0) excl = 1.f;
-        r.trans[i] = carry * excl;
-        carry *= __shfl_sync(kFull, incl, kWarp - 1);
-        r.w[i] = r.alpha[i] * r.trans[i];                                                       // :448
-        r.acc += r.w[i];
-        r.dsum += r.w[i] * r.zm[i];
-        r.dsum_ndc += r.w[i] * r.zz[i];
+        for (int i = 0; i < C / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(v[2 * i], v[2 * i + 1]);
     }
-    r.acc = warp_sum(r.acc);                                                                    // :451
-    r.dsum = warp_sum(r.dsum);
-    r.dsum_ndc = warp_sum(r.dsum_ndc);
 }
 
-template <int ITEMS>
+// Per-ray quantities shared by forward and backward.  CONTIG: lane owns samples lane*C + i, else lane + 32*i.
+template <int C, bool CONTIG>
+struct RayState {
+    float sig[C], zz[C], zm[C];      // sigma, z (ndc or metric), metric z
+    float delta[C], alpha[C], trans[C], w[C];
+    float acc, dsum, dsum_ndc;       // sum w, sum w*zm, sum w*z_ndc
+
+    __device__ __forceinline__ int sample(int lane, int i) const { return CONTIG ? lane * C + i : i * kWarp + lane; }
+
+    __device__ __forceinline__ void load_and_scan(const CompositeArgs& a, int ray, int lane) {
+        const int s = a.s;
+        const float* sg = a.sigma + (size_t)ray * s;
+        const float* z = a.z + (size_t)ray * s;
+        const float* dvec = (a.ndc ? a.rays_d_ndc : a.rays_d) + (size_t)ray * 3;
+        const float dn = sqrtf(dvec[0] * dvec[0] + dvec[1] * dvec[1] + dvec[2] * dvec[2]);          // :436 / :441
+        const float tail = a.ndc ? 1.f : 1e10f;                                                     // :433 / :438
+        float k0 = 0.f, tn = 0.f;
+        if (a.ndc) {
+            const float oz = a.rays_o[(size_t)ray * 3 + 2], dz = a.rays_d[(size_t)ray * 3 + 2];
+            tn = -(1.f + oz) / dz;                                                                  // :498
+            k0 = (oz + tn * dz) / dz;                                                               // per-ray factor of :501
+        }
+        float znext[C];
+        if constexpr (CONTIG) {
+            load_vec<C>(sg + lane * C, sig);
+            load_vec<C>(z + lane * C, zz);
+            const float up = __shfl_down_sync(kFull, zz[0], 1);      // first depth of the next lane
+#pragma unroll
+            for (int i = 0; i < C - 1; ++i) znext[i] = zz[i + 1];
+            znext[C - 1] = lane == kWarp - 1 ? tail : up;
+        } else {
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const int k = i * kWarp + lane;
+                sig[i] = k < s ? sg[k] : 0.f;
+                zz[i] = k < s ? z[k] : 0.f;
+                znext[i] = (k + 1 < s) ? z[k + 1] : tail;
+            }
+        }
+        float fprod = 1.f;   // product of this lane's (1 - alpha + 1e-10)   (contiguous ownership)
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const bool live = CONTIG || (i * kWarp + lane < s);
+            delta[i] = (znext[i] - zz[i]) * dn;                                                     // :435-436
+            alpha[i] = live ? 1.f - __expf(-sig[i] * delta[i]) : 0.f;                               // :446
+            if (a.ndc) {
+                const float guard = (zz[i] == 1.f) ? 1e-3f : 0.f;                                   // :499
+                zm[i] = k0 * (__frcp_rn(1.f - zz[i] + guard) - 1.f) + tn;                           // :501
+            } else {
+                zm[i] = zz[i];
+            }
+            fprod *= (1.f - alpha[i]) + 1e-10f;
+        }
+        acc = dsum = dsum_ndc = 0.f;
+        if constexpr (CONTIG) {
+            // exclusive product scan over lanes, then walk the lane's own samples                  // :447
+            float incl = fprod;
+#pragma unroll
+            for (int o = 1; o < kWarp; o <<= 1) {
+                const float v = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl *= v;
+            }
+            float t = __shfl_up_sync(kFull, incl, 1);
+            if (lane == 0) t = 1.f;
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                trans[i] = t;
+                w[i] = alpha[i] * t;                                                                // :448
+                t *= (1.f - alpha[i]) + 1e-10f;
+                acc += w[i];
+                dsum += w[i] * zm[i];
+                dsum_ndc += w[i] * zz[i];
+            }
+        } else {
+            float carry = 1.f;
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const int k = i * kWarp + lane;
+                const float f = (k < s) ? (1.f - alpha[i]) + 1e-10f : 1.f;
+                float incl = f;
+#pragma unroll
+                for (int o = 1; o < kWarp; o <<= 1) {
+                    const float v = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl *= v;
+                }
+                float excl = __shfl_up_sync(kFull, incl, 1);
+                if (lane == 0) excl = 1.f;
+                trans[i] = carry * excl;
+                carry *= __shfl_sync(kFull, incl, kWarp - 1);
+                w[i] = alpha[i] * trans[i];
+                acc += w[i];
+                dsum += w[i] * zm[i];
+                dsum_ndc += w[i] * zz[i];
+            }
+        }
+        acc = warp_sum(acc);                                                                        // :451
+        dsum = warp_sum(dsum);
+        dsum_ndc = warp_sum(dsum_ndc);
+    }
+};
+
+template <int C, bool CONTIG>
 __global__ void __launch_bounds__(kCompWarps* kWarp) composite_fwd_kernel(const CompositeArgs a) {
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int ray = blockIdx.x * kCompWarps + warp;
     if (ray >= a.n_rays) return;
     const int s = a.s;
-    RayState<ITEMS> r;
-    load_and_scan<ITEMS>(a, ray, lane, r);
+    RayState<C, CONTIG> r;
+    r.load_and_scan(a, ray, lane);
 
     const float* rgb = a.rgb + (size_t)ray * s * 3;
     float cr = 0.f, cg = 0.f, cb = 0.f;
+    if constexpr (CONTIG) {
+        float c[3 * C];
+        load_vec<3 * C>(rgb + lane * 3 * C, c);
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const int k = i * kWarp + lane;
-        if (k < s) {
-            cr += r.w[i] * rgb[k * 3 + 0];                                                      // :449
-            cg += r.w[i] * rgb[k * 3 + 1];
-            cb += r.w[i] * rgb[k * 3 + 2];
-            const size_t o = (size_t)ray * s + k;
-            if (a.alpha) a.alpha[o] = r.alpha[i];
-            if (a.vis) a.vis[o] = r.trans[i];
-            if (a.weights) a.weights[o] = r.w[i];
+        for (int i = 0; i < C; ++i) {
+            cr += r.w[i] * c[3 * i];                                                                // :449
+            cg += r.w[i] * c[3 * i + 1];
+            cb += r.w[i] * c[3 * i + 2];
+        }
+        const size_t o = (size_t)ray * s + lane * C;
+        if (a.alpha) store_vec<C>(a.alpha + o, r.alpha);
+        if (a.vis) store_vec<C>(a.vis + o, r.trans);
+        if (a.weights) store_vec<C>(a.weights + o, r.w);
+    } else {
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const int k = i * kWarp + lane;
+            if (k < s) {
+                cr += r.w[i] * rgb[k * 3 + 0];
+                cg += r.w[i] * rgb[k * 3 + 1];
+                cb += r.w[i] * rgb[k * 3 + 2];
+                const size_t o = (size_t)ray * s + k;
+                if (a.alpha) a.alpha[o] = r.alpha[i];
+                if (a.vis) a.vis[o] = r.trans[i];
+                if (a.weights) a.weights[o] = r.w[i];
+            }
         }
     }
     cr = warp_sum(cr);
     cg = warp_sum(cg);
     cb = warp_sum(cb);
     const float inv = 1.f / (r.acc + 1e-6f);
-    const float depth = r.dsum * inv;                                                           // :453 / :459
-    const float depth_ndc = r.dsum_ndc * inv;                                                   // :456
+    const float depth = r.dsum * inv;                                                               // :453 / :459
+    const float depth_ndc = r.dsum_ndc * inv;                                                       // :456
     float var = 0.f, var_ndc = 0.f;
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
+    for (int i = 0; i < C; ++i) {
         const float e = r.zm[i] - depth, en = r.zz[i] - depth_ndc;
-        var += r.w[i] * e * e;                                                                  // :454 / :460
-        var_ndc += r.w[i] * en * en;                                                            // :457
+        var += r.w[i] * e * e;                                                                      // :454 / :460
+        var_ndc += r.w[i] * en * en;                                                                // :457
     }
     var = warp_sum(var);
     var_ndc = warp_sum(var_ndc);
     if (lane == 0) {
-        const float bg = a.white ? 1.f - r.acc : 0.f;                                           // :463
+        const float bg = a.white ? 1.f - r.acc : 0.f;                                               // :463
         a.rgb_map[(size_t)ray * 3 + 0] = cr + bg;
         a.rgb_map[(size_t)ray * 3 + 1] = cg + bg;
         a.rgb_map[(size_t)ray * 3 + 2] = cb + bg;
@@ -155,14 +235,14 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_fwd_kernel(const 
 //   G_k   = g_k alpha_k + dL/dT_k
 //   dL/dalpha_k = g_k T_k + d_alpha_k - (sum_{j>k} G_j T_j) / f_k
 //   dL/dsigma_k = dL/dalpha_k * delta_k * (1 - alpha_k)
-template <int ITEMS>
+template <int C, bool CONTIG>
 __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const CompositeArgs a) {
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int ray = blockIdx.x * kCompWarps + warp;
     if (ray >= a.n_rays) return;
     const int s = a.s;
-    RayState<ITEMS> r;
-    load_and_scan<ITEMS>(a, ray, lane, r);
+    RayState<C, CONTIG> r;
+    r.load_and_scan(a, ray, lane);
 
     const float inv = 1.f / (r.acc + 1e-6f);
     const float depth = r.dsum * inv, depth_ndc = r.dsum_ndc * inv;
@@ -180,80 +260,126 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const 
     const float gvn = (a.ndc && a.g_depth_var_ndc) ? a.g_depth_var_ndc[ray] : 0.f;
     // sum_j w_j (z_j - depth) = D - depth * acc  (tiny, but kept exact)
     const float resid = r.dsum - depth * r.acc, resid_ndc = r.dsum_ndc - depth_ndc * r.acc;
+    const bool per_sample_grads = a.g_weights || a.g_vis || a.g_alpha;
 
     const float* rgb = a.rgb + (size_t)ray * s * 3;
-    float g[ITEMS];
+    float g[C], gt[C];
+    float c[CONTIG ? 3 * C : 1];
+    if constexpr (CONTIG) load_vec<3 * C>(rgb + lane * 3 * C, c);
+    float lane_gt = 0.f;
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const int k = i * kWarp + lane;
+    for (int i = 0; i < C; ++i) {
+        const int k = r.sample(lane, i);
         g[i] = 0.f;
-        if (k < s) {
+        gt[i] = 0.f;
+        if (CONTIG || k < s) {
             const size_t o = (size_t)ray * s + k;
-            const float c0 = rgb[k * 3 + 0], c1 = rgb[k * 3 + 1], c2 = rgb[k * 3 + 2];
+            float c0, c1, c2;
+            if constexpr (CONTIG) { c0 = c[3 * i]; c1 = c[3 * i + 1]; c2 = c[3 * i + 2]; }
+            else { c0 = rgb[k * 3 + 0]; c1 = rgb[k * 3 + 1]; c2 = rgb[k * 3 + 2]; }
             const float e = r.zm[i] - depth, en = r.zz[i] - depth_ndc;
             float gi = gr * c0 + gg * c1 + gb * c2 + g_const;
             gi += gd * e * inv + gdn * en * inv;
             gi += gv * (e * e - 2.f * e * inv * resid) + gvn * (en * en - 2.f * en * inv * resid_ndc);
-            if (a.g_weights) gi += a.g_weights[o];
+            float big_g;
+            if (per_sample_grads) {
+                if (a.g_weights) gi += a.g_weights[o];
+                big_g = gi * r.alpha[i];
+                if (a.g_vis) big_g += a.g_vis[o];
+            } else {
+                big_g = gi * r.alpha[i];
+            }
             g[i] = gi;
-            a.d_rgb[o * 3 + 0] = r.w[i] * gr;
-            a.d_rgb[o * 3 + 1] = r.w[i] * gg;
-            a.d_rgb[o * 3 + 2] = r.w[i] * gb;
+            gt[i] = big_g * r.trans[i];
+            lane_gt += gt[i];
         }
     }
-    // reverse exclusive scan of G_k T_k
-    float carry = 0.f;
+    // d rgb = w * d rgb_map
+    if constexpr (CONTIG) {
+        float dr[3 * C];
 #pragma unroll
-    for (int i = ITEMS - 1; i >= 0; --i) {
-        const int k = i * kWarp + lane;
-        const size_t o = (size_t)ray * s + k;
-        float gt = 0.f;
-        if (k < s) {
-            float big_g = g[i] * r.alpha[i];
-            if (a.g_vis) big_g += a.g_vis[o];
-            gt = big_g * r.trans[i];
+        for (int i = 0; i < C; ++i) { dr[3 * i] = r.w[i] * gr; dr[3 * i + 1] = r.w[i] * gg; dr[3 * i + 2] = r.w[i] * gb; }
+        store_vec<3 * C>(a.d_rgb + ((size_t)ray * s + lane * C) * 3, dr);
+    } else {
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const int k = i * kWarp + lane;
+            if (k < s) {
+                const size_t o = (size_t)ray * s + k;
+                a.d_rgb[o * 3 + 0] = r.w[i] * gr;
+                a.d_rgb[o * 3 + 1] = r.w[i] * gg;
+                a.d_rgb[o * 3 + 2] = r.w[i] * gb;
+            }
         }
-        float incl = gt;
+    }
+    // suffix sums  sum_{j>k} G_j T_j
+    float ds[C];
+    if constexpr (CONTIG) {
+        float incl = lane_gt;    // inclusive suffix over lanes
 #pragma unroll
         for (int off = 1; off < kWarp; off <<= 1) {
             const float v = __shfl_down_sync(kFull, incl, off);
             if (lane + off < kWarp) incl += v;
         }
-        const float suffix = carry + (incl - gt);   // sum over j > k
-        carry += __shfl_sync(kFull, incl, 0);
-        if (k < s) {
+        float suffix = incl - lane_gt;           // everything owned by later lanes
+#pragma unroll
+        for (int i = C - 1; i >= 0; --i) {
             const float f = (1.f - r.alpha[i]) + 1e-10f;
-            float d_alpha = g[i] * r.trans[i] - suffix / f;
-            if (a.g_alpha) d_alpha += a.g_alpha[o];
-            a.d_sigma[o] = d_alpha * r.delta[i] * (1.f - r.alpha[i]);
+            float d_alpha = g[i] * r.trans[i] - suffix * __frcp_rn(f);
+            if (a.g_alpha) d_alpha += a.g_alpha[(size_t)ray * s + lane * C + i];
+            ds[i] = d_alpha * r.delta[i] * (1.f - r.alpha[i]);
+            suffix += gt[i];
+        }
+        store_vec<C>(a.d_sigma + (size_t)ray * s + lane * C, ds);
+    } else {
+        float carry = 0.f;
+#pragma unroll
+        for (int i = C - 1; i >= 0; --i) {
+            const int k = i * kWarp + lane;
+            float incl = gt[i];
+#pragma unroll
+            for (int off = 1; off < kWarp; off <<= 1) {
+                const float v = __shfl_down_sync(kFull, incl, off);
+                if (lane + off < kWarp) incl += v;
+            }
+            const float suffix = carry + (incl - gt[i]);
+            carry += __shfl_sync(kFull, incl, 0);
+            if (k < s) {
+                const size_t o = (size_t)ray * s + k;
+                const float f = (1.f - r.alpha[i]) + 1e-10f;
+                float d_alpha = g[i] * r.trans[i] - suffix / f;
+                if (a.g_alpha) d_alpha += a.g_alpha[o];
+                a.d_sigma[o] = d_alpha * r.delta[i] * (1.f - r.alpha[i]);
+            }
         }
     }
 }
 
-template <int ITEMS>
+template <int C, bool CONTIG>
 static int launch_composite(const CompositeArgs& a, bool backward, cudaStream_t st) {
     const int blocks = ceil_div(a.n_rays, kCompWarps);
     if (backward)
-        composite_bwd_kernel<ITEMS><<<blocks, kCompWarps * kWarp, 0, st>>>(a);
+        composite_bwd_kernel<C, CONTIG><<<blocks, kCompWarps * kWarp, 0, st>>>(a);
     else
-        composite_fwd_kernel<ITEMS><<<blocks, kCompWarps * kWarp, 0, st>>>(a);
+        composite_fwd_kernel<C, CONTIG><<<blocks, kCompWarps * kWarp, 0, st>>>(a);
     SNERF_LAUNCH_OK(backward ? "composite_bwd_kernel" : "composite_fwd_kernel");
     return SNERF_OK;
 }
 
 static int dispatch_composite(const CompositeArgs& a, bool backward, cudaStream_t st) {
     if (a.n_rays == 0) return SNERF_OK;
-    const int items = ceil_div(a.s, kWarp);
-    switch (items) {
-        case 1: return launch_composite<1>(a, backward, st);
-        case 2: return launch_composite<2>(a, backward, st);
-        case 3: return launch_composite<3>(a, backward, st);
-        case 4: return launch_composite<4>(a, backward, st);
-        case 5: case 6: return launch_composite<6>(a, backward, st);
-        case 7: case 8: return launch_composite<8>(a, backward, st);
+    switch (a.s) {   // vectorised, lane-contiguous kernels for the sample counts the model uses
+        case 64: return launch_composite<2, true>(a, backward, st);
+        case 128: return launch_composite<4, true>(a, backward, st);
+        case 192: return launch_composite<6, true>(a, backward, st);
+        case 256: return launch_composite<8, true>(a, backward, st);
         default: break;
     }
-    if (items <= 16) return launch_composite<16>(a, backward, st);
+    const int items = ceil_div(a.s, kWarp);
+    if (items <= 2) return launch_composite<2, false>(a, backward, st);
+    if (items <= 4) return launch_composite<4, false>(a, backward, st);
+    if (items <= 8) return launch_composite<8, false>(a, backward, st);
+    if (items <= 16) return launch_composite<16, false>(a, backward, st);
     return fail(SNERF_ERR_UNSUPPORTED, "composite: %d samples per ray > 512", a.s);
 }
 
@@ -273,7 +399,6 @@ extern "C" int snerf_composite_forward(const float* sigma, const float* rgb, con
     SNERF_REQUIRE(rgb_map && acc && depth && depth_var, "snerf_composite_forward: null per-ray output");
     SNERF_REQUIRE(!ndc || (rays_o && rays_d_ndc && depth_ndc && depth_var_ndc),
                   "snerf_composite_forward: NDC mode needs rays_o, rays_d_ndc, depth_ndc, depth_var_ndc");
-    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_composite_forward: bad sizes");
     CompositeArgs a{};
     a.sigma = sigma; a.rgb = rgb; a.z = z; a.rays_o = rays_o; a.rays_d = rays_d; a.rays_d_ndc = rays_d_ndc;
     a.rgb_map = rgb_map; a.acc = acc; a.depth = depth; a.depth_var = depth_var; a.depth_ndc = depth_ndc;
@@ -293,7 +418,6 @@ extern "C" int snerf_composite_backward(const float* sigma, const float* rgb, co
     if (n_rays == 0) return SNERF_OK;
     SNERF_REQUIRE(sigma && rgb && z && rays_d && d_sigma && d_rgb, "snerf_composite_backward: null pointer");
     SNERF_REQUIRE(!ndc || (rays_o && rays_d_ndc), "snerf_composite_backward: NDC mode needs rays_o and rays_d_ndc");
-    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_composite_backward: bad sizes");
     CompositeArgs a{};
     a.sigma = sigma; a.rgb = rgb; a.z = z; a.rays_o = rays_o; a.rays_d = rays_d; a.rays_d_ndc = rays_d_ndc;
     a.g_rgb_map = d_rgb_map; a.g_acc = d_acc; a.g_depth = d_depth; a.g_depth_var = d_depth_var;

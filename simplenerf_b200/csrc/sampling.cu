@@ -1,4 +1,4 @@
-// Ray-depth sampling kernels: stratified coarse sampling and the inverse-CDF resampler.
+// Ray-depth sampling kernels: stratified coarse sampling and the inverse-CDF resampler (HBM-bound).
 //
 // Reference behaviour (src/models/SimpleNeRF01.py):
 //   get_z_vals_coarse :272-302, get_z_vals_fine :304-315, sample_pdf :328-361.
@@ -9,7 +9,7 @@
 namespace snerf {
 
 // ------------------------------------------------------------------------------------------------
-// coarse: one thread per (ray, sample)
+// coarse: one thread per 4 consecutive samples (vector loads / stores)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float lerp_depth(float near, float far, float t, bool lindisp) {
     const float one_minus_t = __fsub_rn(1.f, t);
@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) sample_coarse_kernel(const float* __restr
                                                             const float* __restrict__ t_rand,
                                                             float* __restrict__ z_out, int n_rays, int s,
                                                             bool lindisp) {
+    // generic path: one thread per sample
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)n_rays * s) return;
     const int ray = (int)(gid / s), k = (int)(gid % s);
@@ -41,16 +42,52 @@ __global__ void __launch_bounds__(256) sample_coarse_kernel(const float* __restr
     z_out[gid] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), t_rand[gid]));                      // :301
 }
 
+// s % 4 == 0: thread handles samples 4q..4q+3 of one ray; q4 = s / 4 threads per ray
+__global__ void __launch_bounds__(256) sample_coarse_vec4_kernel(const float* __restrict__ near,
+                                                                 const float* __restrict__ far,
+                                                                 const float* __restrict__ t_vals,
+                                                                 const float* __restrict__ t_rand,
+                                                                 float* __restrict__ z_out, int n_rays, int s, int q4,
+                                                                 bool lindisp) {
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned ray = gid / (unsigned)q4;
+    if (ray >= (unsigned)n_rays) return;
+    const int k0 = (int)(gid - ray * q4) * 4;
+    const float nr = near[ray], fr = far[ray];
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(t_vals + k0));
+    float zc[6];   // depths k0-1 .. k0+4
+    zc[1] = lerp_depth(nr, fr, t4.x, lindisp);
+    zc[2] = lerp_depth(nr, fr, t4.y, lindisp);
+    zc[3] = lerp_depth(nr, fr, t4.z, lindisp);
+    zc[4] = lerp_depth(nr, fr, t4.w, lindisp);
+    float out[4] = {zc[1], zc[2], zc[3], zc[4]};
+    if (t_rand != nullptr) {
+        zc[0] = k0 > 0 ? lerp_depth(nr, fr, t_vals[k0 - 1], lindisp) : zc[1];
+        zc[5] = k0 + 4 < s ? lerp_depth(nr, fr, t_vals[k0 + 4], lindisp) : zc[4];
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(t_rand + (size_t)ray * s + k0));
+        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = k0 + i;
+            const float zk = zc[i + 1];
+            const float lo = k > 0 ? __fmul_rn(.5f, __fadd_rn(zk, zc[i])) : zk;                 // :295-297
+            const float hi = k < s - 1 ? __fmul_rn(.5f, __fadd_rn(zc[i + 2], zk)) : zk;
+            out[i] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), rr[i]));                        // :301
+        }
+    }
+    *reinterpret_cast<float4*>(z_out + (size_t)ray * s + k0) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
 // ------------------------------------------------------------------------------------------------
-// fine: one warp per ray.  smem per warp: cdf[nb] | bins[nb] | sort[npad]
+// fine, generic shapes: one warp per ray.  smem per warp: cdf[nb] | bins[nb] | sort[npad]
 // ------------------------------------------------------------------------------------------------
 constexpr int kFineWarps = 4;
 
 __global__ void __launch_bounds__(kFineWarps* kWarp)
-    sample_fine_kernel(const float* __restrict__ z_coarse, const float* __restrict__ w_coarse,
-                       const float* __restrict__ u, int u_stride, float* __restrict__ z_fine,
-                       float* __restrict__ samples_dbg, float* __restrict__ cdf_dbg, int* __restrict__ below_dbg,
-                       int* __restrict__ above_dbg, int n_rays, int sc, int n_new, int npad) {
+    sample_fine_generic_kernel(const float* __restrict__ z_coarse, const float* __restrict__ w_coarse,
+                               const float* __restrict__ u, int u_stride, float* __restrict__ z_fine,
+                               float* __restrict__ samples_dbg, float* __restrict__ cdf_dbg, int* __restrict__ below_dbg,
+                               int* __restrict__ above_dbg, int n_rays, int sc, int n_new, int npad) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int ray = blockIdx.x * kFineWarps + warp;
@@ -63,16 +100,13 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
     const float* zc = z_coarse + (size_t)ray * sc;
     const float* wc = w_coarse + (size_t)ray * sc;
 
-    // bins = .5 * (z[1:] + z[:-1])  (:310) ; also seed the sort buffer with the coarse depths
     for (int i = lane; i < sc; i += kWarp) {
         const float zi = zc[i];
         sorted[i] = zi;
-        if (i < nb) bins[i] = __fmul_rn(.5f, __fadd_rn(zc[i + 1], zi));
+        if (i < nb) bins[i] = __fmul_rn(.5f, __fadd_rn(zc[i + 1], zi));                            // :310
     }
     for (int i = sc + n_new + lane; i < npad; i += kWarp) sorted[i] = __int_as_float(0x7f800000);
 
-    // weights + 1e-5, normaliser.  torch's CPU sum is an fp32 cascade whose order depends on the host
-    // vector width; the correctly rounded sum (fp64 accumulate) is the closest host-independent match.
     const int ipl = ceil_div(nw, kWarp);   // contiguous items per lane
     const int first = lane * ipl;
     double lane_sum = 0.0;
@@ -84,9 +118,6 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
     const float norm = (float)total;                                                            // :332
-
-    // cdf = [0, cumsum(pdf)]: torch's CPU cumsum accumulates in fp64 and rounds every prefix to fp32
-    // (SURVEY.md H2); a fp64 warp scan reproduces that.
     double lane_pdf = 0.0;
     for (int j = 0; j < ipl; ++j) {
         const int i = first + j;
@@ -98,7 +129,7 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
         const double v = __shfl_up_sync(kFull, incl, o);
         if (lane >= o) incl += v;
     }
-    double run = incl - lane_pdf;   // exclusive prefix of the lanes before this one
+    double run = incl - lane_pdf;
     if (lane == 0) cdf[0] = 0.f;                                                                // :334
     for (int j = 0; j < ipl; ++j) {
         const int i = first + j;
@@ -111,7 +142,6 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
     if (cdf_dbg != nullptr)
         for (int i = lane; i < nb; i += kWarp) cdf_dbg[(size_t)ray * nb + i] = cdf[i];
 
-    // invert the cdf (:345-359)
     const float* urow = u + (size_t)ray * u_stride;
     for (int s = lane; s < n_new; s += kWarp) {
         const float us = urow[s];
@@ -134,9 +164,7 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
         if (above_dbg != nullptr) above_dbg[(size_t)ray * n_new + s] = above;
     }
     __syncwarp();
-
-    // sort(cat(z_coarse, samples)) (:314): in-smem bitonic network over npad (power of two) slots
-    for (int k = 2; k <= npad; k <<= 1) {
+    for (int k = 2; k <= npad; k <<= 1) {                                                       // :314
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = lane; i < npad / 2; i += kWarp) {
                 const int a = 2 * j * (i / j) + (i % j);
@@ -155,6 +183,184 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
     for (int i = lane; i < tot; i += kWarp) z_fine[(size_t)ray * tot + i] = sorted[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// fine, the model's shape (64 coarse depths, 32*NPL new samples): one warp per ray, everything in registers
+// except three small smem rows.  The new samples are sorted with a register bitonic network (shuffles), then
+// merged with the already sorted coarse depths by rank (binary searches), so no 256-slot smem sort is needed.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFastWarps = 8;
+constexpr int kSc = 64;
+
+template <int NPL>
+__device__ __forceinline__ void bitonic_sort_registers(float (&v)[NPL], int lane) {
+    constexpr int N = NPL * kWarp;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= NPL) {
+                const int d = j / NPL;                        // partner lane distance
+                const bool lower = (lane & d) == 0;           // this lane holds the lower-index element of each pair
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    const int idx = lane * NPL + r;
+                    const bool up = (idx & k) == 0;           // ascending block
+                    const float o = __shfl_xor_sync(kFull, v[r], d);
+                    const bool take_min = lower == up;
+                    v[r] = take_min ? fminf(v[r], o) : fmaxf(v[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    if ((r & j) == 0) {
+                        const int idx = lane * NPL + r;
+                        const bool up = (idx & k) == 0;
+                        const float a = v[r], b = v[r + j];
+                        v[r] = up ? fminf(a, b) : fmaxf(a, b);
+                        v[r + j] = up ? fmaxf(a, b) : fminf(a, b);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(kFastWarps* kWarp)
+    sample_fine_fast_kernel(const float* __restrict__ z_coarse, const float* __restrict__ w_coarse,
+                            const float* __restrict__ u, int u_stride, float* __restrict__ z_fine,
+                            float* __restrict__ samples_dbg, float* __restrict__ cdf_dbg, int* __restrict__ below_dbg,
+                            int* __restrict__ above_dbg, int n_rays) {
+    constexpr int NNEW = NPL * kWarp, TOT = kSc + NNEW, NB = kSc - 1;
+    __shared__ float s_all[kFastWarps][kSc + kSc + kSc + NNEW + TOT];
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int ray = blockIdx.x * kFastWarps + warp;
+    if (ray >= n_rays) return;
+    float* cdf = s_all[warp];            // [64] (63 used)
+    float* bins = cdf + kSc;             // [64] (63 used)
+    float* zcs = bins + kSc;             // [64] coarse depths
+    float* ss = zcs + kSc;               // [NNEW] sorted new samples
+    float* outm = ss + NNEW;             // [TOT] merged row
+
+    // ---- coarse depths, mid points, weights: lane owns coarse indices 2*lane, 2*lane+1 ----
+    const float2 z2 = __ldg(reinterpret_cast<const float2*>(z_coarse + (size_t)ray * kSc) + lane);
+    const float2 w2 = __ldg(reinterpret_cast<const float2*>(w_coarse + (size_t)ray * kSc) + lane);
+    const float znext = __shfl_down_sync(kFull, z2.x, 1);
+    *reinterpret_cast<float2*>(zcs + 2 * lane) = z2;
+    bins[2 * lane] = __fmul_rn(.5f, __fadd_rn(z2.y, z2.x));                                     // :310
+    if (lane < kWarp - 1) bins[2 * lane + 1] = __fmul_rn(.5f, __fadd_rn(znext, z2.y));
+    // interior weights k = 1 .. 62, + 1e-5                                                      // :331
+    const float wa = lane > 0 ? __fadd_rn(w2.x, 1e-5f) : 0.f;              // k = 2*lane
+    const float wb = lane < kWarp - 1 ? __fadd_rn(w2.y, 1e-5f) : 0.f;      // k = 2*lane + 1
+    double total = (double)wa + (double)wb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+    const float norm = (float)total;                                                            // :332
+    const float pa = lane > 0 ? __fdiv_rn(wa, norm) : 0.f;
+    const float pb = lane < kWarp - 1 ? __fdiv_rn(wb, norm) : 0.f;
+    // cdf[k] = sum_{k' <= k} pdf(k'): torch's CPU cumsum keeps an fp64 running sum, rounded per prefix  :333
+    const double lane_pdf = (double)pa + (double)pb;
+    double incl = lane_pdf;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+        const double v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const double before = incl - lane_pdf;
+    cdf[2 * lane] = (float)(before + (double)pa);                                               // cdf[0] = 0  (:334)
+    if (lane < kWarp - 1) cdf[2 * lane + 1] = (float)(before + (double)pa + (double)pb);
+    __syncwarp();
+    if (cdf_dbg != nullptr) {
+        cdf_dbg[(size_t)ray * NB + 2 * lane] = cdf[2 * lane];
+        if (lane < kWarp - 1) cdf_dbg[(size_t)ray * NB + 2 * lane + 1] = cdf[2 * lane + 1];
+    }
+
+    // ---- invert the cdf for this lane's NPL uniforms (:345-359) ----
+    float us[NPL], smp[NPL];
+    const float* urow = u + (size_t)ray * u_stride + lane * NPL;
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NPL / 4; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(urow) + i);
+            us[4 * i] = t.x; us[4 * i + 1] = t.y; us[4 * i + 2] = t.z; us[4 * i + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) us[i] = __ldg(urow + i);
+    }
+    int lo[NPL], hi[NPL];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) { lo[r] = 0; hi[r] = NB; }
+#pragma unroll
+    for (int step = 0; step < 6; ++step) {          // NB = 63 < 2^6: searchsorted(right=True)
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            if (lo[r] < hi[r]) {
+                const int mid = (lo[r] + hi[r]) >> 1;
+                if (cdf[mid] <= us[r]) lo[r] = mid + 1; else hi[r] = mid;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        const int below = max(lo[r] - 1, 0);                                                    // :346
+        const int above = min(lo[r], NB - 1);                                                   // :347
+        const float c0 = cdf[below], c1 = cdf[above];
+        float denom = __fsub_rn(c1, c0);                                                        // :356
+        if (denom < 1e-5f) denom = 1.f;                                                         // :357
+        const float t = __fdiv_rn(__fsub_rn(us[r], c0), denom);                                 // :358
+        const float b0 = bins[below], b1 = bins[above];
+        smp[r] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));                                // :359
+        if (samples_dbg != nullptr) samples_dbg[(size_t)ray * NNEW + lane * NPL + r] = smp[r];
+        if (below_dbg != nullptr) below_dbg[(size_t)ray * NNEW + lane * NPL + r] = below;
+        if (above_dbg != nullptr) above_dbg[(size_t)ray * NNEW + lane * NPL + r] = above;
+    }
+
+    // ---- sort the new samples (values only), then merge by rank with the sorted coarse depths (:314) ----
+    bitonic_sort_registers<NPL>(smp, lane);
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) ss[lane * NPL + r] = smp[r];
+    __syncwarp();
+    // new sample at sorted position i goes to  i + #(coarse <= sample)
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        int l = 0, h = kSc;
+#pragma unroll
+        for (int step = 0; step < 7; ++step) {
+            if (l < h) {
+                const int mid = (l + h) >> 1;
+                if (zcs[mid] <= smp[r]) l = mid + 1; else h = mid;
+            }
+        }
+        outm[lane * NPL + r + l] = smp[r];
+    }
+    // coarse depth k goes to  k + #(samples < depth)
+    {
+        const float zv[2] = {z2.x, z2.y};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            int l = 0, h = NNEW;
+#pragma unroll
+            for (int step = 0; step < 9; ++step) {
+                if (l < h) {
+                    const int mid = (l + h) >> 1;
+                    if (ss[mid] < zv[q]) l = mid + 1; else h = mid;
+                }
+            }
+            outm[2 * lane + q + l] = zv[q];
+        }
+    }
+    __syncwarp();
+    float* dst = z_fine + (size_t)ray * TOT;
+    if constexpr (TOT % 64 == 0) {
+#pragma unroll
+        for (int i = 0; i < TOT / 64; ++i)
+            *reinterpret_cast<float2*>(dst + i * 64 + 2 * lane) = *reinterpret_cast<const float2*>(outm + i * 64 + 2 * lane);
+    } else {
+        for (int i = lane; i < TOT; i += kWarp) dst[i] = outm[i];
+    }
+}
+
 }  // namespace snerf
 
 using namespace snerf;
@@ -164,10 +370,20 @@ extern "C" int snerf_sample_coarse(const float* near, const float* far, const fl
     SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_sample_coarse: bad sizes (%d rays, %d samples)", n_rays, n_samples);
     if (n_rays == 0) return SNERF_OK;   // empty batch: nothing to launch (pointers may be null)
     SNERF_REQUIRE(near && far && t_vals && z_out, "snerf_sample_coarse: null pointer");
+    const bool lindisp = (flags & SNERF_FLAG_LINDISP) != 0;
     const long long total = (long long)n_rays * n_samples;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(t_vals) | reinterpret_cast<uintptr_t>(t_rand) |
+                           reinterpret_cast<uintptr_t>(z_out)) & 15) == 0;
+    if (n_samples % 4 == 0 && aligned && total / 4 < (1LL << 31)) {
+        const int q4 = n_samples / 4;
+        const long long threads = (long long)n_rays * q4;
+        sample_coarse_vec4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            near, far, t_vals, t_rand, z_out, n_rays, n_samples, q4, lindisp);
+        SNERF_LAUNCH_OK("sample_coarse_vec4_kernel");
+        return SNERF_OK;
+    }
     const int blocks = (int)((total + 255) / 256);
-    sample_coarse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, t_vals, t_rand, z_out, n_rays, n_samples,
-                                                                   (flags & SNERF_FLAG_LINDISP) != 0);
+    sample_coarse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, t_vals, t_rand, z_out, n_rays, n_samples, lindisp);
     SNERF_LAUNCH_OK("sample_coarse_kernel");
     return SNERF_OK;
 }
@@ -181,18 +397,34 @@ extern "C" int snerf_sample_fine(const float* z_coarse, const float* weights_coa
     SNERF_REQUIRE(z_coarse && weights_coarse && u && z_fine, "snerf_sample_fine: null pointer");
     SNERF_REQUIRE(u_stride == 0 || u_stride >= n_new, "snerf_sample_fine: u_stride %d < n_new %d", u_stride, n_new);
     if (s_coarse + n_new > 1024) return fail(SNERF_ERR_UNSUPPORTED, "snerf_sample_fine: %d + %d samples > 1024", s_coarse, n_new);
-    if (n_rays == 0) return SNERF_OK;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(z_coarse) | reinterpret_cast<uintptr_t>(weights_coarse) |
+                           reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(z_fine)) & 15) == 0 && u_stride % 4 == 0;
+    if (s_coarse == kSc && aligned && (n_new == 64 || n_new == 128 || n_new == 256)) {
+        const int blocks = ceil_div(n_rays, kFastWarps);
+        const cudaStream_t st = (cudaStream_t)stream;
+        if (n_new == 64)
+            sample_fine_fast_kernel<2><<<blocks, kFastWarps * kWarp, 0, st>>>(z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg,
+                                                                             cdf_dbg, below_dbg, above_dbg, n_rays);
+        else if (n_new == 128)
+            sample_fine_fast_kernel<4><<<blocks, kFastWarps * kWarp, 0, st>>>(z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg,
+                                                                             cdf_dbg, below_dbg, above_dbg, n_rays);
+        else
+            sample_fine_fast_kernel<8><<<blocks, kFastWarps * kWarp, 0, st>>>(z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg,
+                                                                             cdf_dbg, below_dbg, above_dbg, n_rays);
+        SNERF_LAUNCH_OK("sample_fine_fast_kernel");
+        return SNERF_OK;
+    }
     int npad = 2;
     while (npad < s_coarse + n_new) npad <<= 1;
     const size_t smem = (size_t)kFineWarps * (2 * (s_coarse - 1) + npad) * sizeof(float);
     static bool attr_set = false;
     if (smem > 48 * 1024 && !attr_set) {
-        SNERF_CUDA_OK(cudaFuncSetAttribute(sample_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(sample_fine_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    sample_fine_kernel<<<ceil_div(n_rays, kFineWarps), kFineWarps * kWarp, smem, (cudaStream_t)stream>>>(
+    sample_fine_generic_kernel<<<ceil_div(n_rays, kFineWarps), kFineWarps * kWarp, smem, (cudaStream_t)stream>>>(
         z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays, s_coarse,
         n_new, npad);
-    SNERF_LAUNCH_OK("sample_fine_kernel");
+    SNERF_LAUNCH_OK("sample_fine_generic_kernel");
     return SNERF_OK;
 }

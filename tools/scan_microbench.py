@@ -1,0 +1,64 @@
+"""C5 microbench: compositing forward/backward, hierarchical resampling and stratified sampling, achieved HBM GB/s
+against the algorithmic bytes of SURVEY.md section 8(d) (20S+68 / 24S+68 / 36S+48 bytes per ray, 1792 / 1280 bytes per
+ray for sample_pdf+merge, 4S(+4S) bytes per ray for the stratified sampler)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import torch
+from simplenerf_b200 import ops
+
+DEV = 'cuda:0'
+PEAK = 6548.2
+if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')):
+    PEAK = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+rows = []
+for s in (64, 128, 256):
+    for logn in (16, 18, 20, 22):
+        n = 1 << logn
+        if n * s * 4 * 9 > 60e9:
+            continue
+        g = torch.Generator(device=DEV).manual_seed(1000 + logn * 10 + s // 64)
+        sigma = torch.relu(3 * torch.randn((n, s), device=DEV, generator=g))
+        rgb = torch.sigmoid(torch.randn((n, s, 3), device=DEV, generator=g))
+        z = torch.sort(torch.rand((n, s), device=DEV, generator=g), -1)[0].contiguous()
+        o = torch.randn((n, 3), device=DEV, generator=g)
+        d = torch.nn.functional.normalize(torch.randn((n, 3), device=DEV, generator=g), dim=-1) * 2
+        d[:, 2] = -d[:, 2].abs() - 0.1
+        t = timeit(lambda: ops.composite_forward(sigma, rgb, z, o, d, d, True, False, per_sample=()))
+        rows.append(('composite_fwd (render contract)', s, n, (20 * s + 68) * n, t))
+        t = timeit(lambda: ops.composite_forward(sigma, rgb, z, o, d, d, True, False, per_sample=('weights',)))
+        rows.append(('composite_fwd (+weights)', s, n, (24 * s + 68) * n, t))
+        g_rgb, g_depth = torch.randn((n, 3), device=DEV), torch.randn(n, device=DEV)
+        t = timeit(lambda: ops.composite_backward(sigma, rgb, z, o, d, d, True, False, {'rgb': g_rgb, 'depth': g_depth}))
+        rows.append(('composite_bwd', s, n, (36 * s + 48) * n, t))
+        if s == 64:
+            w = torch.rand((n, 64), device=DEV, generator=g)
+            u = torch.rand((n, 128), device=DEV, generator=g)
+            t = timeit(lambda: ops.sample_fine(z, w, u))
+            rows.append(('sample_pdf+merge (u supplied)', 64, n, 1792 * n, t))
+            lin = torch.linspace(0, 1, 128).to(DEV)
+            t = timeit(lambda: ops.sample_fine(z, w, lin))
+            rows.append(('sample_pdf+merge (linspace row)', 64, n, 1280 * n, t))
+            near, far, tv = torch.zeros(n, device=DEV), torch.ones(n, device=DEV), torch.linspace(0, 1, 64).to(DEV)
+            tr = torch.rand((n, 64), device=DEV, generator=g)
+            t = timeit(lambda: ops.sample_coarse(near, far, tv, tr))
+            rows.append(('stratified sampler (t_rand supplied)', 64, n, 8 * 64 * n, t))
+        del sigma, rgb, z
+print(f'| kernel | S | rays | algorithmic MB | time us | GB/s | frac of measured {PEAK:.0f} GB/s |')
+print('|---|---|---|---|---|---|---|')
+for name, s, n, b, t in rows:
+    print(f'| {name} | {s} | 2^{n.bit_length() - 1} | {b / 1e6:.1f} | {t * 1e6:.1f} | {b / t / 1e9:.0f} | {b / t / 1e9 / PEAK:.2f} |')
