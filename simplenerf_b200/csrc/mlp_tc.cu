@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     const uint32_t d_tmem = tmem + (it & 1) * 256;
                     const uint32_t idesc = umma_idesc(128, st.n_rows, false, false);
                     uint32_t waited = 0;
+                    const bool tr = p.trace && blockIdx.x == 0 && ti == 2;
                     for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
                         const int pn = st.panel[c];
                         uint32_t a_addr;
@@ -218,13 +219,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                             if (it > 0 && !(waited & (1u << pn))) { mbar_wait(&bars->panel_ready[pn], (it - 1) & 1); waited |= 1u << pn; }
                             a_addr = smem_u32(smem + kOffH + pn * kPanelBytes);
                         }
+                        if (tr && c < 5) p.trace[s * 16 + c] = clock64();             // A panel available
                         const uint32_t stage = cnt % kStages;
                         mbar_wait(&bars->w_full[stage], (cnt / kStages) & 1);
                         tc_fence_after();
+                        if (tr && c < 5) p.trace[s * 16 + 5 + c] = clock64();         // weight chunk landed
                         const uint32_t b_addr = smem_u32(smem + kOffRing + stage * kStageBytes);
                         for (int k = 0; k < st.ksteps[c]; ++k)
                             umma(d_tmem, umma_desc_kmajor(a_addr, k), umma_desc_kmajor(b_addr, k), idesc, (c | k) != 0);
                         umma_commit_multicast(&bars->w_empty[stage], kClusterMask);   // frees the slot in every CTA's ring
+                        if (tr && c < 5) p.trace[s * 16 + 10 + c] = clock64();        // MMAs of the chunk issued
                     }
                     umma_commit(&bars->acc_full[it & 1]);
                     if (st.last_e_use) umma_commit(&bars->enc_free[ebuf]);
@@ -332,6 +336,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     tc_fence_before();
                     mbar_arrive(&bars->panel_ready[j]);
                     if (tr) p.trace[256 + s * 16 + 5 + j] = clock64();         // panel j handed over
+                    if (p.trace && blockIdx.x == 0 && ti == 2 && lane == 0 && s >= 1 && s <= 2)
+                        p.trace[512 + (warp - 2) * 8 + (s - 1) * 4 + j] = clock64();   // every epilogue warp: panel j handed over
                 }
                 if (has_head) {
                     // combine the two column halves: the upper half hands its partial sums to the lower half

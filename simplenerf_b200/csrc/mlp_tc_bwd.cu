@@ -286,7 +286,9 @@ constexpr int kWgStages = 3;
 constexpr uint32_t kWgStageBytes = 65536;
 constexpr uint32_t kHalfPanel = 8192;                               // 64 points x 128 bytes
 constexpr uint32_t kWgOffDh = kWgStages * kWgStageBytes;             // [64][4] fp32 head-pre gradients of the current stage
-constexpr uint32_t kWgOffBars = kWgOffDh + 1024;
+constexpr int kRawSlots = 4;                                        // ring of per-stage point inputs for the encoder warps
+constexpr uint32_t kWgOffRaw = kWgOffDh + 1024;                     // [kRawSlots][10][64] fp32: z, o(3), d(3), view dir(3)
+constexpr uint32_t kWgOffBars = kWgOffRaw + kRawSlots * 10 * 64 * 4;
 constexpr uint32_t kWgSmem = kWgOffBars + 512 + 1024;
 constexpr int kMaxJobs = 16;
 
@@ -299,7 +301,9 @@ struct WgJob {
     uint8_t b_enc, b_venc;        // computed operand panels appended after the streamed ones
     uint8_t n_segs;
     uint16_t aux_off;             // byte offset / 1024 of the computed panels inside a stage
-    uint16_t pad;
+    uint8_t with_head;            // MMA job whose B operand is h8: the reducer warps also form dW_head = d head_pre^T h8
+    uint8_t pad;
+    int16_t cta0, n_cta;          // CTAs [cta0, cta0 + n_cta) own this job; CTA cta0 + i takes tiles i, i + n_cta, ...
     float* dw;
     float* db;
     int32_t ld;
@@ -312,11 +316,15 @@ struct WgParams {
     long long n_points;
     int n_samples, n_tiles, n_jobs, pts_degree, view_degree, head_out;
     uint32_t tile_stash_bytes;
+    float *head_dw, *head_db;     // destination of the merged head-matrix gradient (with_head jobs)
+    int head_ld;
+    long long* trace;             // debug: per CTA {job, cycles} (tools/wgrad_balance.py), normally null
+    int debug;                    // debug: bit0 encoders write zeros, bit1 no MMAs, bit2 no reducer work
     WgJob jobs[kMaxJobs];
 };
 
 struct WgBars {
-    uint64_t full[kWgStages], empty[kWgStages], aux_ready[kWgStages], acc_done, acc_free;
+    uint64_t full[kWgStages], empty[kWgStages], aux_ready[kWgStages], acc_done, acc_free, raw_ready[kRawSlots], raw_free[kRawSlots];
     uint32_t tmem_base;
 };
 
@@ -341,6 +349,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         }
         mbar_init(&bars->acc_done, 1);
         mbar_init(&bars->acc_free, 256);
+        for (int i = 0; i < kRawSlots; ++i) { mbar_init(&bars->raw_ready[i], 64); mbar_init(&bars->raw_free[i], 128); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
@@ -348,129 +357,197 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int n_stages_per_job = my_tiles * 2;
+    // one job per CTA for the whole launch: the accumulator of the job's weight matrix stays in TMEM over every tile
+    // this CTA owns and is flushed once (fp32 reductions), so the flush traffic is one matrix per CTA
+    int jb = -1;
+    for (int j = 0; j < p.n_jobs; ++j)
+        if ((int)blockIdx.x >= p.jobs[j].cta0 && (int)blockIdx.x < p.jobs[j].cta0 + p.jobs[j].n_cta) jb = j;
+    const WgJob& job = p.jobs[jb < 0 ? 0 : jb];
+    const int part = (int)blockIdx.x - job.cta0, nparts = job.n_cta;
+    const long long t_start = clock64();
+    const int my_tiles = (jb < 0 || part >= p.n_tiles) ? 0 : (p.n_tiles - part + nparts - 1) / nparts;
+    const int n_stages = my_tiles * 2;
 
     if (warp == 0) {
         // ======================= loader: stashed panels -> smem stages =======================
         if (lane == 0) {
-            uint32_t cnt = 0;
-            for (int jb = 0; jb < p.n_jobs; ++jb) {
-                const WgJob& job = p.jobs[jb];
-                const uint32_t bytes = (uint32_t)(job.a_panels + job.b_panels) * kHalfPanel;
-                for (int sg = 0; sg < n_stages_per_job; ++sg, ++cnt) {
-                    const int tile = blockIdx.x + (sg >> 1) * gridDim.x, half = sg & 1;
-                    const uint32_t stage = cnt % kWgStages, round = cnt / kWgStages;
-                    if (round > 0) mbar_wait(&bars->empty[stage], (round - 1) & 1);
-                    uint8_t* dst = smem + stage * kWgStageBytes;
-                    mbar_arrive_expect_tx(&bars->full[stage], bytes);
-                    const size_t toff = (size_t)tile * p.tile_stash_bytes + (size_t)half * kHalfPanel;
-                    for (int j = 0; j < job.a_panels; ++j)
-                        bulk_g2s(dst + j * kHalfPanel, p.dy + toff + (size_t)job.a_slot * 65536 + j * kPanelBytes, kHalfPanel,
-                                 &bars->full[stage]);
-                    for (int j = 0; j < job.b_panels; ++j)
-                        bulk_g2s(dst + 32768 + j * kHalfPanel, p.act + toff + (size_t)job.b_slot * 65536 + j * kPanelBytes,
-                                 kHalfPanel, &bars->full[stage]);
-                }
+            const uint32_t bytes = (uint32_t)(job.a_panels + job.b_panels) * kHalfPanel;
+            for (int sg = 0; sg < n_stages; ++sg) {
+                const int tile = part + (sg >> 1) * nparts, half = sg & 1;
+                const uint32_t stage = sg % kWgStages, round = sg / kWgStages;
+                if (round > 0) mbar_wait(&bars->empty[stage], (round - 1) & 1);
+                uint8_t* dst = smem + stage * kWgStageBytes;
+                mbar_arrive_expect_tx(&bars->full[stage], bytes);
+                const size_t toff = (size_t)tile * p.tile_stash_bytes + (size_t)half * kHalfPanel;
+                for (int j = 0; j < job.a_panels; ++j)
+                    bulk_g2s(dst + j * kHalfPanel, p.dy + toff + (size_t)job.a_slot * 65536 + j * kPanelBytes, kHalfPanel,
+                             &bars->full[stage]);
+                for (int j = 0; j < job.b_panels; ++j)
+                    bulk_g2s(dst + 32768 + j * kHalfPanel, p.act + toff + (size_t)job.b_slot * 65536 + j * kPanelBytes,
+                             kHalfPanel, &bars->full[stage]);
             }
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
         if (lane == 0) {
-            uint32_t cnt = 0, flushes = 0;
-            for (int jb = 0; jb < p.n_jobs; ++jb) {
-                const WgJob& job = p.jobs[jb];
-                const bool aux = job.b_enc || job.b_venc;
-                const int n1 = job.b_panels * 64;
-                const int n2 = ((int)job.b_enc + (int)job.b_venc) * 64;
-                const int n_mb = job.a_panels / 2;
-                if (job.kind == 0 && flushes > 0) { mbar_wait(&bars->acc_free, (flushes - 1) & 1); tc_fence_after(); }
-                for (int sg = 0; sg < n_stages_per_job; ++sg, ++cnt) {
-                    const uint32_t stage = cnt % kWgStages;
-                    mbar_wait(&bars->full[stage], (cnt / kWgStages) & 1);
-                    if (job.kind != 0) { mbar_arrive(&bars->empty[stage]); continue; }
-                    if (aux) mbar_wait(&bars->aux_ready[stage], (cnt / kWgStages) & 1);
-                    tc_fence_after();
-                    const uint32_t sbase = smem_u32(smem + stage * kWgStageBytes);
-                    for (int k = 0; k < 4; ++k) {
-                        const bool accumulate = (sg | k) != 0;
-                        for (int mb = 0; mb < n_mb; ++mb) {
-                            const uint64_t ad = umma_desc_mnmajor(sbase + mb * 2 * kHalfPanel, k, kHalfPanel);
-                            if (n1 > 0)
-                                umma(tmem + mb * 256, ad, umma_desc_mnmajor(sbase + 32768, k, kHalfPanel),
-                                     umma_idesc(128, n1, true, true), accumulate);
-                            if (n2 > 0)
-                                umma(tmem + mb * 256 + n1, ad, umma_desc_mnmajor(sbase + (uint32_t)job.aux_off * 1024u, k, kHalfPanel),
-                                     umma_idesc(128, n2, true, true), accumulate);
-                        }
+            const bool aux = job.b_enc || job.b_venc;
+            const int n1 = job.b_panels * 64;
+            const int n2 = ((int)job.b_enc + (int)job.b_venc) * 64;
+            const int n_mb = job.a_panels / 2;
+            for (int sg = 0; sg < n_stages; ++sg) {
+                const uint32_t stage = sg % kWgStages;
+                mbar_wait(&bars->full[stage], (sg / kWgStages) & 1);
+                if (job.kind != 0) { mbar_arrive(&bars->empty[stage]); continue; }
+                if (aux) mbar_wait(&bars->aux_ready[stage], (sg / kWgStages) & 1);
+                tc_fence_after();
+                const uint32_t sbase = smem_u32(smem + stage * kWgStageBytes);
+                for (int k = 0; k < ((p.debug & 2) ? 0 : 4); ++k) {
+                    const bool accumulate = (sg | k) != 0;
+                    for (int mb = 0; mb < n_mb; ++mb) {
+                        const uint64_t ad = umma_desc_mnmajor(sbase + mb * 2 * kHalfPanel, k, kHalfPanel);
+                        if (n1 > 0)
+                            umma(tmem + mb * 256, ad, umma_desc_mnmajor(sbase + 32768, k, kHalfPanel),
+                                 umma_idesc(128, n1, true, true), accumulate);
+                        if (n2 > 0)
+                            umma(tmem + mb * 256 + n1, ad, umma_desc_mnmajor(sbase + (uint32_t)job.aux_off * 1024u, k, kHalfPanel),
+                                 umma_idesc(128, n2, true, true), accumulate);
                     }
-                    umma_commit(&bars->empty[stage]);
                 }
-                if (job.kind == 0) { umma_commit(&bars->acc_done); ++flushes; }
+                umma_commit(&bars->empty[stage]);
+            }
+            if (job.kind == 0 && n_stages > 0) umma_commit(&bars->acc_done);
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ======================= fetchers: per-point inputs of the recomputed encodings -> smem ring =======================
+        // (asynchronous 4-byte copies completing on an mbarrier: several stages stay in flight and the encoder warps,
+        // whose proxy fence would otherwise wait for their own outstanding loads, never touch global memory)
+        if (job.kind == 0 && (job.b_enc || job.b_venc)) {
+            const int r = (warp - 2) * 32 + lane;
+            float* s_raw = (float*)(smem + kWgOffRaw);
+            for (int sg = 0; sg < n_stages; ++sg) {
+                const int slot = sg % kRawSlots, round = sg / kRawSlots;
+                const int tile = part + (sg >> 1) * nparts, half = sg & 1;
+                long long pt = (long long)tile * kTileRows + half * 64 + r;
+                if (pt >= p.n_points) pt = p.n_points - 1;     // rows past the end carry zero gradients; any finite input will do
+                const int ray = p.n_points < (1LL << 31) ? (int)((unsigned)pt / (unsigned)p.n_samples) : (int)(pt / p.n_samples);
+                if (round > 0) mbar_wait(&bars->raw_free[slot], (round - 1) & 1);
+                float* dst = s_raw + slot * 640 + r;
+                if (job.b_enc) {
+                    cp_async4(dst, p.z + pt);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { cp_async4(dst + (1 + c) * 64, p.rays_o + ray * 3 + c); cp_async4(dst + (4 + c) * 64, p.rays_d + ray * 3 + c); }
+                }
+                if (job.b_venc) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) cp_async4(dst + (7 + c) * 64, p.view_dirs + ray * 3 + c);
+                }
+                cp_async_arrive_noinc(&bars->raw_ready[slot]);
             }
         }
     } else if (warp >= 4 && warp < 12) {
         // ======================= reducers: bias sums, head matrices, TMEM flush =======================
         const int t = (warp - 4) * 32 + lane;            // column owned by this thread
         const int q = warp & 3, colhalf = (warp - 4) >> 2;
-        uint32_t cnt = 0, flushes = 0;
-        for (int jb = 0; jb < p.n_jobs; ++jb) {
-            const WgJob& job = p.jobs[jb];
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            float acc_b = 0.f;
-            const int nh = job.kind == 1 ? p.head_out : 3;
-            for (int sg = 0; sg < n_stages_per_job; ++sg, ++cnt) {
-                const int tile = blockIdx.x + (sg >> 1) * gridDim.x, half = sg & 1;
-                const uint32_t stage = cnt % kWgStages;
-                const uint8_t* sb = smem + stage * kWgStageBytes;
-                if (job.kind != 0) {
-                    // head-pre gradients of the 64 points of this stage
-                    if (t < 64) {
-                        const long long pt = (long long)tile * kTileRows + half * 64 + t;
-                        float d[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (pt < p.n_points) {
-                            const float ds = p.sigma[pt] > 0.f ? p.d_sigma[pt] : 0.f;
-                            float g[3];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc_b = 0.f, acc_hb = 0.f;
+        const bool head = job.kind != 0 || job.with_head;   // this job forms a head matrix from its streamed B operand
+        const int nh = job.kind == 2 ? 3 : p.head_out;
+        // smem byte offsets of column `col`, rows 8g + i (i = 0..7), inside a set of [64 x 64] half panels: + g * 1024
+        auto column_offsets = [](int col, uint32_t (&off)[8]) {
+            const uint32_t base = (uint32_t)(col >> 6) * kHalfPanel + (uint32_t)(col & 7) * 2u, chunk = (uint32_t)(col & 63) >> 3;
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const float r = p.rgb[pt * 3 + c];
-                                g[c] = p.d_rgb[pt * 3 + c] * r * (1.f - r);
-                            }
-                            if (job.kind == 1) { d[0] = ds; if (p.head_out == 4) { d[1] = g[0]; d[2] = g[1]; d[3] = g[2]; } }
-                            else { d[0] = g[0]; d[1] = g[1]; d[2] = g[2]; }
-                        }
+            for (int i = 0; i < 8; ++i) off[i] = base + (uint32_t)i * kRowBytes + ((chunk ^ (uint32_t)i) << 4);
+        };
+        auto bf16_ld = [](const uint8_t* a) { return __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(a) << 16); };
+        const bool do_bias = job.kind == 0 && job.db != nullptr && t < job.a_panels * 64 && !(p.debug & 4);
+        uint32_t off_a[8], off_b[8];
+        column_offsets(t, off_a);
+        // head matrix: thread owns column hcol of the B operand and the row groups [g0, g0 + ng)
+        const int ncol = job.b_panels * 64;                 // 256 (h8) or 128 (hv)
+        const int hcol = ncol > 0 ? t % ncol : 0;
+        const int ng = ncol == 128 ? 4 : 8, g0 = ncol == 128 ? (t >> 7) * 4 : 0;
+        column_offsets(hcol, off_b);
+        // head-pre gradients of one stage (64 points): threads 0..63 fetch the raw inputs one stage ahead (loads only, so
+        // that nothing waits on them before the next iteration) and finish the arithmetic when the stage comes up
+        struct RawHead { float sig, dsig, r[3], dr[3]; };
+        auto fetch_dh = [&](int sg, RawHead& w) {
+            w.sig = 0.f; w.dsig = 0.f;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) s_dh[t * 4 + c] = d[c];
-                    }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                }
-                mbar_wait(&bars->full[stage], (cnt / kWgStages) & 1);
-                if (job.kind == 0) {
-                    if (job.db != nullptr && t < job.a_panels * 64) {
-                        for (int r = 0; r < 64; ++r) acc_b += bf16_at(sb, r, t);
-                    }
+            for (int c = 0; c < 3; ++c) { w.r[c] = 0.f; w.dr[c] = 0.f; }
+            if (!head || t >= 64 || sg >= n_stages) return;
+            const int tile = part + (sg >> 1) * nparts, half = sg & 1;
+            const long long pt = (long long)tile * kTileRows + half * 64 + t;
+            if (pt >= p.n_points) return;
+            if (job.kind == 2 || p.head_out == 4) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { w.r[c] = __ldg(p.rgb + pt * 3 + c); w.dr[c] = __ldg(p.d_rgb + pt * 3 + c); }
+            }
+            if (job.kind != 2) { w.sig = __ldg(p.sigma + pt); w.dsig = __ldg(p.d_sigma + pt); }
+        };
+        auto finish_dh = [&](const RawHead& w) {
+            float g[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[c] = w.dr[c] * w.r[c] * (1.f - w.r[c]);             // sigmoid'
+            if (job.kind == 2) return make_float4(g[0], g[1], g[2], 0.f);
+            const float ds = w.sig > 0.f ? w.dsig : 0.f;                                       // relu'
+            return p.head_out == 4 ? make_float4(ds, g[0], g[1], g[2]) : make_float4(ds, 0.f, 0.f, 0.f);
+        };
+        RawHead raw;
+        fetch_dh(0, raw);
+        for (int sg = 0; sg < n_stages; ++sg) {
+            const uint32_t stage = sg % kWgStages;
+            const uint8_t* sb = smem + stage * kWgStageBytes;
+            if (head) {
+                if (t < 64) *reinterpret_cast<float4*>(s_dh + t * 4) = finish_dh(raw);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                fetch_dh(sg + 1, raw);       // in flight while this stage is reduced
+            }
+            mbar_wait(&bars->full[stage], (sg / kWgStages) & 1);
+            if (do_bias) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc_b += bf16_ld(sb + off_a[i] + g * 1024);
+            }
+            if (head) {
+                const uint8_t* hb = sb + 32768 + g0 * 1024;
+                const float* dh = s_dh + g0 * 32;
+                if (nh == 1) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[0] = fmaf(dh[(g * 8 + i) * 4], bf16_ld(hb + off_b[i] + g * 1024), acc[0]);
                 } else {
-                    const int ncol = job.b_panels * 64;
-                    if (t < ncol) {
-                        for (int r = 0; r < 64; ++r) {
-                            const float x = bf16_at(sb + 32768, r, t);
-                            const float4 d = *reinterpret_cast<const float4*>(s_dh + r * 4);
+                    for (int g = 0; g < ng; ++g)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float x = bf16_ld(hb + off_b[i] + g * 1024);
+                            const float4 d = *reinterpret_cast<const float4*>(dh + (g * 8 + i) * 4);
                             acc[0] = fmaf(d.x, x, acc[0]); acc[1] = fmaf(d.y, x, acc[1]);
                             acc[2] = fmaf(d.z, x, acc[2]); acc[3] = fmaf(d.w, x, acc[3]);
                         }
-                    }
-                    if (t < nh) {
-                        for (int r = 0; r < 64; ++r) acc_b += s_dh[r * 4 + t];
-                    }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->empty[stage]);
+                if (t < nh) {
+                    for (int r = 0; r < 64; ++r) acc_hb += s_dh[r * 4 + t];
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            // ---- job results ----
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->empty[stage]);
+        }
+        // ---- job results ----
+        if (n_stages > 0) {
+            if (head) {
+                float* hdw = job.kind == 0 ? p.head_dw : job.dw;
+                float* hdb = job.kind == 0 ? p.head_db : job.db;
+                const int hld = job.kind == 0 ? p.head_ld : job.ld;
+                if (ncol > 0)
+                    for (int h = 0; h < nh; ++h) atomicAdd(hdw + (size_t)h * hld + hcol, acc[h]);
+                if (t < nh && hdb != nullptr) atomicAdd(hdb + t, acc_hb);
+            }
             if (job.kind == 0) {
                 if (job.db != nullptr && t < job.a_panels * 64) atomicAdd(job.db + t, acc_b);
-                mbar_wait(&bars->acc_done, flushes & 1);
+                mbar_wait(&bars->acc_done, 0);
                 tc_fence_after();
                 const int n_mb = job.a_panels / 2;
                 for (int mb = 0; mb < n_mb; ++mb) {
@@ -497,78 +574,66 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&bars->acc_free);
-                ++flushes;
-            } else {
-                const int ncol = job.b_panels * 64;
-                if (t < ncol)
-                    for (int h = 0; h < nh; ++h) atomicAdd(job.dw + (size_t)h * job.ld + t, acc[h]);
-                if (t < nh && job.db != nullptr) atomicAdd(job.db + t, acc_b);
             }
         }
     } else if (warp >= 12) {
         // ======================= encoders: recomputed encoding operands =======================
         const int e = (warp - 12) * 32 + lane;
         const int r = e >> 1, hf = e & 1;
-        uint32_t cnt = 0;
-        for (int jb = 0; jb < p.n_jobs; ++jb) {
-            const WgJob& job = p.jobs[jb];
-            const bool aux = job.kind == 0 && (job.b_enc || job.b_venc);
-            for (int sg = 0; sg < n_stages_per_job; ++sg, ++cnt) {
-                const int tile = blockIdx.x + (sg >> 1) * gridDim.x, half = sg & 1;
-                const uint32_t stage = cnt % kWgStages, round = cnt / kWgStages;
-                if (!aux) {   // keep one aux_ready phase per stage use so that parities stay in step with `full`
-                    if (round > 0) mbar_wait(&bars->empty[stage], (round - 1) & 1);
-                    mbar_arrive(&bars->aux_ready[stage]);
-                    continue;
-                }
-                const long long pt = (long long)tile * kTileRows + half * 64 + r;
-                const bool valid = pt < p.n_points;
-                const int ray = valid ? (int)(pt / p.n_samples) : 0;
-                float enc[64];
-#pragma unroll
-                for (int i = 0; i < 64; ++i) enc[i] = 0.f;
+        const bool aux = job.kind == 0 && (job.b_enc || job.b_venc);
+        if (aux) {
+            const float* s_raw = (const float*)(smem + kWgOffRaw);
+            const int venc = 3 * (1 + 2 * p.view_degree);
+            for (int sg = 0; sg < n_stages; ++sg) {
+                const uint32_t stage = sg % kWgStages, round = sg / kWgStages;
+                const int slot = sg % kRawSlots;
+                mbar_wait(&bars->raw_ready[slot], (sg / kRawSlots) & 1);
+                const float* src = s_raw + slot * 640 + r;
+                float x[3] = {0.f, 0.f, 0.f}, vdir[3] = {0.f, 0.f, 0.f};
                 if (job.b_enc) {
-                    float x[3] = {0.f, 0.f, 0.f};
-                    if (valid) {
-                        const float zz = p.z[pt];
+                    const float zz = src[0];
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) x[c] = fmaf(p.rays_d[ray * 3 + c], zz, p.rays_o[ray * 3 + c]);
+                    for (int c = 0; c < 3; ++c) x[c] = fmaf(src[(4 + c) * 64], zz, src[(1 + c) * 64]);
+                }
+                if (job.b_venc) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) vdir[c] = src[(7 + c) * 64];
+                }
+                mbar_arrive(&bars->raw_free[slot]);
+                uint32_t pe[16], pv[16];    // this thread's 32 columns, packed bf16 pairs
+                if (p.debug & 1) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { pe[i] = 0u; pv[i] = 0u; }
+                } else
+                if (job.b_enc) {
+                    if (hf == 0) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pe[i] = pack_bf16(encode_element(x, p.pts_degree, 2 * i), encode_element(x, p.pts_degree, 2 * i + 1));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pe[i] = pack_bf16(encode_element(x, p.pts_degree, 32 + 2 * i), encode_element(x, p.pts_degree, 33 + 2 * i));
                     }
-                    encode_point(x, p.pts_degree, enc);
+                }
+                if (job.b_venc && !(p.debug & 1)) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float a = (hf == 0 && 2 * i < venc) ? encode_element(vdir, p.view_degree, 2 * i) : 0.f;
+                        const float b = (hf == 0 && 2 * i + 1 < venc) ? encode_element(vdir, p.view_degree, 2 * i + 1) : 0.f;
+                        pv[i] = pack_bf16(a, b);
+                    }
                 }
                 if (round > 0) mbar_wait(&bars->empty[stage], (round - 1) & 1);
                 uint8_t* dst = smem + stage * kWgStageBytes + (uint32_t)job.aux_off * 1024u;
                 if (job.b_enc) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int ch = hf * 4 + c;
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = hf ? enc[32 + 8 * c + i] : enc[8 * c + i];
-                        *reinterpret_cast<uint4*>(dst + swz_offset(r, ch)) =
-                            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    }
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(dst + swz_offset(r, hf * 4 + c)) = make_uint4(pe[4 * c], pe[4 * c + 1], pe[4 * c + 2], pe[4 * c + 3]);
                     dst += kHalfPanel;
                 }
                 if (job.b_venc) {
-                    float ve[64];
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) ve[i] = 0.f;
-                    if (hf == 0) {
-                        float vd[3] = {p.view_dirs[ray * 3], p.view_dirs[ray * 3 + 1], p.view_dirs[ray * 3 + 2]};
-                        encode_point(vd, p.view_degree, ve);
-                        const int venc = 3 * (1 + 2 * p.view_degree);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) if (i >= venc) ve[i] = 0.f;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int ch = hf * 4 + c;
-                        *reinterpret_cast<uint4*>(dst + swz_offset(r, ch)) =
-                            make_uint4(pack_bf16(ve[8 * c], ve[8 * c + 1]), pack_bf16(ve[8 * c + 2], ve[8 * c + 3]),
-                                       pack_bf16(ve[8 * c + 4], ve[8 * c + 5]), pack_bf16(ve[8 * c + 6], ve[8 * c + 7]));
-                    }
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(dst + swz_offset(r, hf * 4 + c)) = make_uint4(pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3]);
                 }
                 fence_async_smem();
                 mbar_arrive(&bars->aux_ready[stage]);
@@ -578,8 +643,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     __syncwarp();
     tc_fence_before();
     __syncthreads();
+    if (p.trace && threadIdx.x == 0) { p.trace[2 * blockIdx.x] = jb; p.trace[2 * blockIdx.x + 1] = clock64() - t_start; }
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
+
+static long long* g_wg_trace = nullptr;
+static int g_wg_debug = 0;   // set by snerfdbg_set_wgrad_trace (debug only)
 
 // =================================================================================================
 // driver
@@ -671,13 +740,62 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         r.kind = 2; r.b_slot = 9; r.b_panels = 2; r.dw = grads[SNERF_P_RGB_W]; r.ld = m.view_width; r.db = grads[SNERF_P_RGB_B];
         wp.jobs[nj++] = r;
     }
-    WgJob h{};                                          // dW_head = d head_pre^T h8
-    h.kind = 1; h.b_slot = 7; h.b_panels = 4; h.dw = grads[SNERF_P_HEAD_W]; h.ld = m.width; h.db = grads[SNERF_P_HEAD_B];
-    wp.jobs[nj++] = h;
+    wp.trace = g_wg_trace; wp.debug = g_wg_debug;
+    wp.head_dw = grads[SNERF_P_HEAD_W]; wp.head_db = grads[SNERF_P_HEAD_B]; wp.head_ld = m.width;
+    if (m.has_view) {
+        // dW_head = d head_pre^T h8 rides on the feature job, whose streamed B operand is the same h8
+        for (int j = 0; j < nj; ++j)
+            if (wp.jobs[j].kind == 0 && wp.jobs[j].a_slot == 8) wp.jobs[j].with_head = 1;
+    } else {
+        WgJob h{};
+        h.kind = 1; h.b_slot = 7; h.b_panels = 4; h.dw = grads[SNERF_P_HEAD_W]; h.ld = m.width; h.db = grads[SNERF_P_HEAD_B];
+        wp.jobs[nj++] = h;
+    }
     wp.n_jobs = nj;
-    tc_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(wp);
+    // CTAs per job in proportion to the bytes the job streams per tile (the kernel is HBM-bound)
+    {
+        const int G = num_sms();
+        double cost[kMaxJobs], total = 0.0;
+        for (int j = 0; j < nj; ++j) {
+            const WgJob& jb = wp.jobs[j];
+            // measured with tools/wgrad_balance.py (cycles of work per tile, relative): streaming dominates, the
+            // recomputed encodings and the CUDA-core head matrices add their own latency
+            cost[j] = (jb.a_panels + jb.b_panels) * 12.5;
+            if (jb.kind == 0 && jb.b_panels == 0) cost[j] = 125.0;                    // dY x encoding only
+            if (jb.b_enc && jb.b_panels > 0) cost[j] += 70.0;                         // view job of the points-augmented model
+            if (jb.with_head) cost[j] += 68.0;
+            if (jb.kind == 1) cost[j] = 136.0;
+            if (jb.kind == 2) cost[j] = 109.0;
+            total += cost[j];
+        }
+        int n[kMaxJobs], used = 0;
+        for (int j = 0; j < nj; ++j) {
+            n[j] = (int)(G * cost[j] / total);
+            if (n[j] < 1) n[j] = 1;
+            used += n[j];
+        }
+        while (used < G) {   // hand the remaining CTAs to the most loaded jobs
+            int best = 0;
+            for (int j = 1; j < nj; ++j)
+                if (cost[j] / n[j] > cost[best] / n[best]) best = j;
+            ++n[best]; ++used;
+        }
+        while (used > G) {
+            int best = -1;
+            for (int j = 0; j < nj; ++j)
+                if (n[j] > 1 && (best < 0 || cost[j] / n[j] < cost[best] / n[best])) best = j;
+            --n[best]; --used;
+        }
+        int c0 = 0;
+        for (int j = 0; j < nj; ++j) { wp.jobs[j].cta0 = (int16_t)c0; wp.jobs[j].n_cta = (int16_t)n[j]; c0 += n[j]; }
+    }
+    (void)grid;
+    tc_wgrad_kernel<<<num_sms(), kWgThreads, kWgSmem, st>>>(wp);
     SNERF_LAUNCH_OK("tc_wgrad_kernel");
     return SNERF_OK;
 }
 
 }  // namespace snerf
+
+extern "C" void snerfdbg_set_wgrad_trace(long long* device_buffer) { snerf::g_wg_trace = device_buffer; }
+extern "C" void snerfdbg_set_wgrad_debug(int bits) { snerf::g_wg_debug = bits; }

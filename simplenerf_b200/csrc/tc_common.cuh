@@ -101,6 +101,15 @@ __device__ __forceinline__ void bulk_wait_all() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- 4-byte asynchronous copies (LDGSTS) completing on an mbarrier ----------------------------------------
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// one arrival on `bar` (counted in its init value) once every cp.async issued so far by this thread has landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---- thread-block clusters --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;

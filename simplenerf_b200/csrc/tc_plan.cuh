@@ -154,6 +154,18 @@ __device__ __forceinline__ void encode_point(const float x[3], int degree, float
     }
 }
 
+// one element of encode_point (same arithmetic, so a recomputed operand equals the forward one bit for bit)
+__device__ __forceinline__ float encode_element(const float x[3], int degree, int idx) {
+    if (idx < 3) return idx == 0 ? x[0] : (idx == 1 ? x[1] : x[2]);
+    const int j = idx - 3, k = j / 6, rem = j - 6 * k;
+    const int c = rem >= 3 ? rem - 3 : rem;
+    const float xc = c == 0 ? x[0] : (c == 1 ? x[1] : x[2]);
+    const float u = (xc * 0.15915494309189535f) * (float)(1 << (k & 15));
+    const float f = u - rintf(u);
+    const float v = rem >= 3 ? __cosf(f * 6.283185307179586f) : __sinf(f * 6.283185307179586f);
+    return k < degree ? v : 0.f;     // a select, not a branch: the elements of a row interleave freely
+}
+
 // accurate variant (fp32 consumers: the per-ray view-direction bias)
 __device__ __forceinline__ void encode_point_accurate(const float x[3], int degree, float* enc) {
     enc[0] = x[0]; enc[1] = x[1]; enc[2] = x[2];

@@ -21,7 +21,7 @@ o, d, vd = b['rays_o_ndc'].to(DEV), b['rays_d_ndc'].to(DEV), b['view_dirs'].to(D
 z = torch.sort(torch.rand(n_rays, s, device=DEV), -1)[0].contiguous()
 flags = FLAG_SAVE_FOR_BWD if save else 0
 ws = torch.empty(ops.mlp_workspace_bytes(block.desc, n_rays, s, flags), dtype=torch.uint8, device=DEV)
-trace = torch.zeros(512, dtype=torch.int64, device=DEV)
+trace = torch.zeros(1024, dtype=torch.int64, device=DEV)
 for _ in range(2):
     ops.mlp_forward(block.desc, table, packed, o, d, vd, z, None, ws, flags)
 lib.snerfdbg_set_trace.argtypes = [ctypes.c_void_p]
@@ -32,7 +32,15 @@ lib.snerfdbg_set_trace(None)
 t = trace.cpu().numpy()
 t0 = t[256]   # epilogue: accumulator of step 0 complete
 rel = lambda v: int(v - t0) if v else None
-print('step | MMA issued || EPI: acc done | tmem-ld done p0..p3 | handed p0..p3 | panel1: math done, stores issued, fence done')
+print('EPI  step | acc done | tmem-ld done p0..p3 | handed p0..p3 | panel1: math done, stores issued, fence done')
 for s_ in range(10):
-    m = t[s_ * 16: s_ * 16 + 16]; e = t[256 + s_ * 16: 256 + s_ * 16 + 16]
-    print(f'{s_:2d} | {rel(m[0])} || {rel(e[0])} | {[rel(x) for x in e[1:5]]} | {[rel(x) for x in e[5:9]]} | {[rel(x) for x in e[9:12]]}')
+    e = t[256 + s_ * 16: 256 + s_ * 16 + 16]
+    print(f'{s_:2d} | {rel(e[0])} | {[rel(x) for x in e[1:5]]} | {[rel(x) for x in e[5:9]]} | {[rel(x) for x in e[9:12]]}')
+print('MMA  step | A panel available c0..c4 | weight chunk landed c0..c4 | chunk issued c0..c4')
+for s_ in range(10):
+    m = t[s_ * 16: s_ * 16 + 16]
+    print(f'{s_:2d} | {[rel(x) for x in m[0:5]]} | {[rel(x) for x in m[5:10]]} | {[rel(x) for x in m[10:15]]}')
+print('all epilogue warps (warp, q, hf): handed p0..p3 of steps 1 and 2')
+for w in range(8):
+    v = t[512 + w * 8: 512 + w * 8 + 8]
+    print(f'warp {w + 2} q={(w + 2) & 3} hf={w >> 2}: {[rel(x) for x in v]}')
