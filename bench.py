@@ -56,30 +56,45 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thread = None
 
+    def _sample(self):
+        import pynvml
+        self.samples.append(pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
     def _run(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             while not self._stop.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                time.sleep(0.02)
+                self._sample()
+                time.sleep(0.005)
         except Exception as exc:   # noqa: BLE001
             self.reasons.add(f'sampler_error:{type(exc).__name__}')
 
     def __enter__(self):
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
+        try:   # NVML is initialised before the timed region starts, so the first sample falls inside it
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception as exc:   # noqa: BLE001
+            self.reasons.add(f'sampler_error:{type(exc).__name__}')
         return self
+
+    def mark(self):
+        """One synchronous sample (called while the GPU is still busy, just before the closing synchronize)."""
+        try:
+            self._sample()
+        except Exception as exc:   # noqa: BLE001
+            self.reasons.add(f'sampler_error:{type(exc).__name__}')
 
     def __exit__(self, *exc):
         self._stop.set()
-        self._thread.join(timeout=2)
+        if self._thread is not None:
+            self._thread.join(timeout=2)
 
     def summary(self):
         s = sorted(self.samples)
@@ -203,7 +218,7 @@ def run_ours(args):
         opt.step()
         return loss
 
-    def timed(fn, steps):
+    def timed(fn, steps, mark=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -212,6 +227,8 @@ def run_ours(args):
         for _ in range(steps):
             fn()
         e1.record()
+        if mark is not None:
+            mark()   # the host runs ahead of the device: the GPU is still inside the timed region here
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -241,7 +258,7 @@ def run_ours(args):
     ops.TIMER['hook'] = Timer
     launches0 = ops.LAUNCHES['count']
     with ClockSampler(local) as clocks:
-        ms_total = timed(lambda: step(resident), args.steps)
+        ms_total = timed(lambda: step(resident), args.steps, clocks.mark)
     launches = ops.LAUNCHES['count'] - launches0
     ops.TIMER['hook'] = None
     mlp_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in events.items()}
@@ -251,7 +268,7 @@ def run_ours(args):
     # ---- e2e: batch in pinned host memory, copied every step; loss read back ----
     def e2e_step():
         batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
-        return float(step(batch))     # device -> host read of the loss
+        return float(step(batch).detach())     # device -> host read of the loss
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     e2e_value = world * n / (ms_e2e * 1e-3)

@@ -114,6 +114,7 @@ struct FwdParams {
     float *sigma, *rgb;
     uint8_t* stash;                // null in eval
     long long* trace;              // debug: clock64 timestamps of CTA 0 (tools/trace_fwd.py), normally null
+    int debug;                     // debug (timing experiments, results become garbage): bit0 no panel stores, bit1 no epilogue math, bit2 no weight copies
     long long n_points;
     int n_samples, n_tiles, n_steps, pts_degree, head_out;
     uint32_t tile_stash_bytes;
@@ -148,15 +149,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
     float* s_part = (float*)(smem + kOffConst + kConstPart);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const bool save = p.stash != nullptr;
+    // roles by warp id -- the sub-partition arbiter issues the highest eligible warp id first, so the latency-critical
+    // epilogue warps sit on top and the helpers below them:  0-3 encoders | 4 stash writer | 5 weight loader | 6-13 epilogue | 14 MMA issuer (single thread, must never starve)
+    constexpr int kWarpStash = 4, kWarpLoader = 5, kWarpEpi0 = 6, kWarpMma = 14;
 
     // ---- setup ----
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], kCluster); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->enc_ready[i], 128); mbar_init(&bars->enc_free[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&bars->panel_ready[i], kEpiWarps * 32); mbar_init(&bars->panel_stored[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->panel_ready[i], kEpiWarps * 16); mbar_init(&bars->panel_stored[i], 1); }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+    if (warp == kWarpMma) tmem_alloc<512>(&bars->tmem_base);
     for (int i = threadIdx.x; i < 9 * 256; i += kFwdThreads) {
         const float* b = p.bias[i >> 8];
         s_bias16[i] = __float2bfloat16_rn(b ? b[i & 255] : 0.f);
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
     const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1);
 
-    if (warp == 0) {
+    if (warp == kWarpLoader) {
         // ======================= weight loader =======================
         // each CTA fetches 1/kCluster of every chunk and multicasts it into the ring of every CTA of the cluster
         if (lane == 0) {
@@ -188,7 +192,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     const uint32_t slice = bytes / kCluster;
                     for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
                         const uint32_t stage = cnt % kStages, round = cnt / kStages;
-                        if (round > 0) mbar_wait(&bars->w_empty[stage], (round - 1) & 1);   // all CTAs released the slot
+                        if (round > 0) mbar_wait_sleep(&bars->w_empty[stage], (round - 1) & 1, 32);   // all CTAs released the slot
+                        if (p.debug & 4) { mbar_arrive(&bars->w_full[stage]); continue; }
                         mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
                         bulk_g2s_multicast(smem + kOffRing + stage * kStageBytes + rank * slice,
                                            p.packed + st.w_off + (uint32_t)c * bytes + rank * slice, slice,
@@ -196,10 +201,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     }
                 }
         }
-    } else if (warp == 1) {
+    } else if (warp == kWarpMma) {
         // ======================= MMA issuer =======================
+        // tcgen05.mma issue is nearly synchronous (the queue holds about one pending instruction), so every cycle this
+        // thread spends between two issues beyond the ~140-cycle execution of an MMA idles the tensor pipe; a barrier
+        // wait that succeeds at once still costs ~190 cycles.  The barriers of chunk c+1 are therefore probed BETWEEN
+        // the MMAs of chunk c (non-blocking test_wait, hidden behind the running MMA); the blocking wait is the fallback.
         if (lane == 0) {
             uint32_t cnt = 0, it = 0;
+            bool w_ok = false;                         // weight chunk `cnt` already seen landed
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int ebuf = ti & 1;
                 bool enc_waited = false;
@@ -211,6 +221,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     const bool tr = p.trace && blockIdx.x == 0 && ti == 2;
                     for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
                         const int pn = st.panel[c];
+                        const uint32_t stage = cnt % kStages;
+                        if (!w_ok) mbar_wait(&bars->w_full[stage], (cnt / kStages) & 1);
                         uint32_t a_addr;
                         if (pn == kPanelE) {
                             if (!enc_waited) { mbar_wait(&bars->enc_ready[ebuf], (ti >> 1) & 1); enc_waited = true; }
@@ -219,28 +231,38 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                             if (it > 0 && !(waited & (1u << pn))) { mbar_wait(&bars->panel_ready[pn], (it - 1) & 1); waited |= 1u << pn; }
                             a_addr = smem_u32(smem + kOffH + pn * kPanelBytes);
                         }
-                        if (tr && c < 5) p.trace[s * 16 + c] = clock64();             // A panel available
-                        const uint32_t stage = cnt % kStages;
-                        mbar_wait(&bars->w_full[stage], (cnt / kStages) & 1);
                         tc_fence_after();
-                        if (tr && c < 5) p.trace[s * 16 + 5 + c] = clock64();         // weight chunk landed
+                        if (tr && c < 5) p.trace[s * 16 + c] = clock64();             // operands available
                         const uint32_t b_addr = smem_u32(smem + kOffRing + stage * kStageBytes);
-                        for (int k = 0; k < st.ksteps[c]; ++k)
-                            umma(d_tmem, umma_desc_kmajor(a_addr, k), umma_desc_kmajor(b_addr, k), idesc, (c | k) != 0);
+                        const int nk = st.ksteps[c];
+                        const uint32_t nstage = (cnt + 1) % kStages, nparity = ((cnt + 1) / kStages) & 1;
+                        const int npn = c + 1 < st.n_chunks ? st.panel[c + 1] : -1;
+                        umma(d_tmem, umma_desc_kmajor(a_addr, 0), umma_desc_kmajor(b_addr, 0), idesc, c != 0);
+                        w_ok = mbar_test_wait(&bars->w_full[nstage], nparity);        // next weight chunk (hidden behind the MMA)
+                        if (nk > 1) umma(d_tmem, umma_desc_kmajor(a_addr, 1), umma_desc_kmajor(b_addr, 1), idesc, true);
+                        if (npn >= 0 && npn != kPanelE && it > 0 && !(waited & (1u << npn)) &&
+                            mbar_test_wait(&bars->panel_ready[npn], (it - 1) & 1))     // next activation panel
+                            waited |= 1u << npn;
+                        for (int k = 2; k < nk; ++k)
+                            umma(d_tmem, umma_desc_kmajor(a_addr, k), umma_desc_kmajor(b_addr, k), idesc, true);
                         umma_commit_multicast(&bars->w_empty[stage], kClusterMask);   // frees the slot in every CTA's ring
                         if (tr && c < 5) p.trace[s * 16 + 10 + c] = clock64();        // MMAs of the chunk issued
                     }
                     umma_commit(&bars->acc_full[it & 1]);
                     if (st.last_e_use) umma_commit(&bars->enc_free[ebuf]);
-                    // every epilogue of step it-1 has finished before step it+1 may reuse its accumulator
+                    // every epilogue warp of step it-1 has drained its accumulator before step it+1 may overwrite it
+                    if (it > 0 && !(waited & 4u)) mbar_wait(&bars->panel_ready[2], (it - 1) & 1);
                     if (it > 0 && !(waited & 8u)) mbar_wait(&bars->panel_ready[3], (it - 1) & 1);
                 }
             }
         }
-    } else if (warp < 2 + kEpiWarps) {
+    } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 8) {
         // ======================= epilogue =======================
-        // warp (q, hf): TMEM lanes / tile rows 32q..32q+31, columns [32 hf, 32 hf + 32) of every 64-column panel
-        const int q = warp & 3, hf = (warp - 2) >> 2;
+        // warp (q, w2): TMEM lanes / tile rows 32q..32q+31; it owns the whole 64-column panels w2 and w2 + 2 of every step,
+        // so the per-panel synchronisation (proxy fence, tcgen05 fence, mbarrier arrive) is paid once per 64 columns while
+        // the partner warp of the same sub-partition works on the neighbouring panel.  TMEM -> registers is software
+        // pipelined in 32-column units: the load of unit u+1 is in flight while unit u is converted and stored.
+        const int q = warp & 3, w2 = (warp - kWarpEpi0) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0;
@@ -254,19 +276,32 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 const int kind = st.kind;
                 mbar_wait(&bars->acc_full[it & 1], (it >> 1) & 1);
                 tc_fence_after();
-                const bool tr = p.trace && blockIdx.x == 0 && ti == 2 && warp == 4 && lane == 0;
-                if (tr) p.trace[256 + s * 16 + 0] = clock64();     // epilogue: accumulator complete
+                const bool tr = p.trace && blockIdx.x == 0 && ti == 2 && q == 0 && lane == 0;
+                if (tr && w2 == 0) p.trace[256 + s * 16 + 0] = clock64();     // epilogue: accumulator complete
                 const int n_pan = st.n_rows / 64;
+                const int n_own = n_pan > w2 + 2 ? 2 : (n_pan > w2 ? 1 : 0);     // panels with data owned by this warp
                 const bool writes_h = (kind != EPI_VIEW) || save;
                 const bool has_head = kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4 || kind == EPI_VIEW;
                 float head[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int j = 0; j < 4; ++j) {
-                    if (j < n_pan) {
-                        const int col0 = j * 64 + hf * 32;
+                const uint32_t acc_addr = lane_addr + (it & 1) * 256;
+                uint32_t rr[2][32];
+                if (n_own > 0) tmem_ld32_issue(acc_addr + w2 * 64, rr[0]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = u >> 1, h = u & 1, j = w2 + 2 * jj;
+                    if (jj < n_own) {
+                        const int col0 = j * 64 + h * 32;
+                        tmem_ld_wait(rr[u & 1]);
+                        if (u + 1 < 2 * n_own) tmem_ld32_issue(acc_addr + (w2 + 2 * ((u + 1) >> 1)) * 64 + ((u + 1) & 1) * 32, rr[(u + 1) & 1]);
                         float v[32];
-                        tmem_ld32(lane_addr + (it & 1) * 256 + col0, v);
-                        if (tr) p.trace[256 + s * 16 + 1 + j] = clock64();     // TMEM load of panel j done
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[u & 1][i]);
+                        if (tr && h == 0) p.trace[256 + s * 16 + 1 + j] = clock64();     // first TMEM load of panel j done
                         uint32_t pk[16];
+                        if (p.debug & 2) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pk[i] = rr[u & 1][2 * i];
+                        } else
                         if (kind == EPI_RELU || kind == EPI_LINEAR) {
                             const uint4* bb = reinterpret_cast<const uint4*>(s_bias16 + st.bias_row * 256 + col0);
                             const bool relu = kind == EPI_RELU;
@@ -305,48 +340,45 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                             const int wld = kind == EPI_VIEW ? 128 : 256;
                             const int nh = kind == EPI_RELU_HEAD1 ? 1 : (kind == EPI_VIEW ? 3 : 4);
 #pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                if (h < nh) {
-                                    const float4* w = reinterpret_cast<const float4*>(wbase + h * wld + col0);
-                                    float a = head[h];
+                            for (int hh = 0; hh < 4; ++hh) {
+                                if (hh < nh) {
+                                    const float4* w = reinterpret_cast<const float4*>(wbase + hh * wld + col0);
+                                    float a = head[hh];
 #pragma unroll
                                     for (int i = 0; i < 8; ++i) {
                                         const float4 ww = w[i];
                                         a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
                                     }
-                                    head[h] = a;
+                                    head[hh] = a;
                                 }
                             }
 #pragma unroll
                             for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
                         }
-                        if (writes_h) {
-                            if (save && it > 0) mbar_wait(&bars->panel_stored[j], (it - 1) & 1);
-                            if (tr && j == 1) p.trace[256 + s * 16 + 9] = clock64();      // math done (panel 1)
+                        if (writes_h && !(p.debug & 1)) {
+                            if (h == 0 && save && it > 0) mbar_wait(&bars->panel_stored[j], (it - 1) & 1);
                             uint8_t* dst = smem + kOffH + j * kPanelBytes;
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
-                                *reinterpret_cast<uint4*>(dst + swz_offset(row, hf * 4 + c)) =
+                                *reinterpret_cast<uint4*>(dst + swz_offset(row, h * 4 + c)) =
                                     make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                            if (tr && j == 1) p.trace[256 + s * 16 + 10] = clock64();     // stores issued
-                            fence_async_smem();
-                            if (tr && j == 1) p.trace[256 + s * 16 + 11] = clock64();     // proxy fence done
                         }
                     }
-                    tc_fence_before();
-                    mbar_arrive(&bars->panel_ready[j]);
-                    if (tr) p.trace[256 + s * 16 + 5 + j] = clock64();         // panel j handed over
-                    if (p.trace && blockIdx.x == 0 && ti == 2 && lane == 0 && s >= 1 && s <= 2)
-                        p.trace[512 + (warp - 2) * 8 + (s - 1) * 4 + j] = clock64();   // every epilogue warp: panel j handed over
+                    if (h == 1) {
+                        if (jj < n_own && writes_h && !(p.debug & 1)) fence_async_smem();
+                        tc_fence_before();
+                        mbar_arrive(&bars->panel_ready[j]);
+                        if (tr) p.trace[256 + s * 16 + 5 + j] = clock64();         // panel j handed over
+                    }
                 }
                 if (has_head) {
-                    // combine the two column halves: the upper half hands its partial sums to the lower half
-                    if (hf == 1) {
+                    // combine the two panel sets: the odd-panel warp hands its partial sums to the even-panel warp
+                    if (w2 == 1) {
 #pragma unroll
                         for (int h = 0; h < 4; ++h) s_part[row * 4 + h] = head[h];
                     }
                     asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-                    if (hf == 0 && valid) {
+                    if (w2 == 0 && valid) {
                         const float4 o = *reinterpret_cast<const float4*>(s_part + row * 4);
                         const int mb = kind == EPI_VIEW ? 4 : 0;
                         head[0] += o.x + s_misc[mb + 0]; head[1] += o.y + s_misc[mb + 1];
@@ -366,9 +398,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 }
             }
         }
-    } else if (warp < 2 + kEpiWarps + 4) {
+    } else if (warp < 4) {
         // ======================= encoder =======================
-        const int row = (warp - 2 - kEpiWarps) * 32 + lane;
+        const int row = warp * 32 + lane;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = blockIdx.x + ti * gridDim.x;
             const int ebuf = ti & 1;
@@ -384,7 +416,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 64; ++i) enc[i] = 0.f;
             encode_point(x, p.pts_degree, enc);
-            if (ti >= 2) mbar_wait(&bars->enc_free[ebuf], ((ti >> 1) - 1) & 1);
+            if (ti >= 2) mbar_wait_sleep(&bars->enc_free[ebuf], ((ti >> 1) - 1) & 1, 256);
             uint8_t* dst = smem + kOffE + ebuf * kPanelBytes;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -395,7 +427,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
             fence_async_smem();
             mbar_arrive(&bars->enc_ready[ebuf]);
         }
-    } else {
+    } else if (warp == kWarpStash) {
         // ======================= stash writer (training) =======================
         if (save && lane == 0) {
             uint32_t it = 0;
@@ -406,7 +438,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     const TcStep& st = p.steps[s];
                     const int n_pan = st.n_rows / 64;
                     for (int j = 0; j < 4; ++j) {
-                        mbar_wait(&bars->panel_ready[j], it & 1);
+                        mbar_wait_sleep(&bars->panel_ready[j], it & 1, 64);
                         if (j < n_pan && tile < p.n_tiles) {
                             bulk_s2g(base + (size_t)st.slot * 65536 + j * kPanelBytes, smem + kOffH + j * kPanelBytes, kPanelBytes);
                             bulk_commit();
@@ -423,7 +455,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();   // no CTA leaves while a peer may still multicast into its ring or signal its barriers
-    if (warp == 1) tmem_dealloc<512>(tmem);
+    if (warp == kWarpMma) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -434,6 +466,7 @@ size_t tc_workspace_bytes(const MlpDims& m, const snerf_mlp_desc& d, int n_rays,
 }
 
 static long long* g_trace = nullptr;   // set by snerfdbg_set_trace (debug only)
+static int g_fwd_debug = 0;
 
 int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o, const float* rays_d,
                const float* view_dirs, const float* z, const float* noise, float* sigma, float* rgb, void* ws, size_t ws_bytes,
@@ -458,7 +491,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     p.view_bias = (const float*)(wsb + w.view_bias);
     p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.noise = noise; p.sigma = sigma; p.rgb = rgb;
     p.stash = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.act : nullptr;
-    p.trace = g_trace;
+    p.trace = g_trace; p.debug = g_fwd_debug;
     p.n_points = (long long)n_rays * n_samples;
     p.n_samples = n_samples; p.n_tiles = w.n_tiles; p.n_steps = pl.n_fwd; p.pts_degree = d.pts_degree; p.head_out = m.head_out;
     p.tile_stash_bytes = pl.tile_stash_bytes;
@@ -477,6 +510,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
 // images and returns the accumulator (tools/tc_probe.py).
 // ------------------------------------------------------------------------------------------------
 struct ProbeOp { uint32_t a_off, b_off, d_col, accumulate; };
+__device__ int g_probe_chunk = 0, g_probe_waits = 0;
 
 __global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict__ a_img, uint32_t a_bytes,
                                                        const uint8_t* __restrict__ b_img, uint32_t b_bytes,
@@ -484,7 +518,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict
                                                        uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
                                                        uint32_t idesc, uint64_t desc_bits, int n_cols, long long* timing) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar_load, bar_mma;
+    __shared__ uint64_t bar_load, bar_mma, bar_aux;
     __shared__ uint32_t tmem_base_s;
     __shared__ ProbeOp s_ops[256];
     for (int i = threadIdx.x; i < n_ops && i < 256; i += blockDim.x) s_ops[i] = ops[i];
@@ -494,6 +528,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict
     if (threadIdx.x == 0) {
         mbar_init(&bar_load, 1);
         mbar_init(&bar_mma, 1);
+        mbar_init(&bar_aux, 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc<512>(&tmem_base_s);
@@ -507,6 +542,8 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict
         bulk_g2s(sb, b_img, b_bytes, &bar_load);
         mbar_wait(&bar_load, 0);
         tc_fence_after();
+        const int chunk = *(volatile int*)&g_probe_chunk, nwaits = *(volatile int*)&g_probe_waits;
+        int next_commit = chunk > 0 ? chunk : 1 << 30;
         const long long t_start = clock64();
         for (int i = 0; i < n_ops; ++i) {
             const ProbeOp op = s_ops[i];
@@ -516,6 +553,11 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict
             const uint64_t bd = (uint64_t)((ba >> 4) & 0x3FFFu) | ((uint64_t)((b_lbo >> 4) & 0x3FFFu) << 16) |
                                 ((uint64_t)((b_sbo >> 4) & 0x3FFFu) << 32) | desc_bits;
             umma(tmem_base + op.d_col, ad, bd, idesc, op.accumulate != 0);
+            if (i + 1 == next_commit) {   // issue pattern of the chain kernels: commit + barrier probes per chunk
+                next_commit += chunk;
+                umma_commit(&bar_aux);
+                for (int w = 0; w < nwaits; ++w) { mbar_wait(&bar_load, 0); tc_fence_after(); }
+            }
         }
         const long long t_issued = clock64();
         umma_commit(&bar_mma);
@@ -549,6 +591,11 @@ using namespace snerf;
 extern "C" int snerf_has_tensor_path(void) { return 1; }
 
 extern "C" void snerfdbg_set_trace(long long* device_buffer_512) { snerf::g_trace = device_buffer_512; }
+extern "C" void snerfdbg_set_fwd_debug(int bits) { snerf::g_fwd_debug = bits; }
+extern "C" void snerfdbg_set_probe_pattern(int chunk, int waits) {
+    cudaMemcpyToSymbol(snerf::g_probe_chunk, &chunk, sizeof(int));
+    cudaMemcpyToSymbol(snerf::g_probe_waits, &waits, sizeof(int));
+}
 
 // debug entry (not part of the public ABI): all pointers are device pointers
 extern "C" int snerfdbg_probe(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, float* d_out,

@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     BwdBars* bars = (BwdBars*)(smem + kBOffBars);
     float* s_wrgb = (float*)(smem + kBOffConst);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    // roles by warp id (highest id = highest issue priority): 0-3 prologue | 4 stash writer | 5 weight loader | 6-13 epilogue | 14 MMA issuer (single thread, must never starve)
+    constexpr int kWarpStash = 4, kWarpLoader = 5, kWarpEpi0 = 6, kWarpMma = 14;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], kCluster); }
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
         mbar_init(&bars->pro_stored, 1);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+    if (warp == kWarpMma) tmem_alloc<512>(&bars->tmem_base);
     if (p.w_rgb) for (int i = threadIdx.x; i < 3 * 128; i += kBwdThreads) s_wrgb[i] = p.w_rgb[i];
     tc_fence_before();
     __syncthreads();
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;   // uniform per cluster; tiles >= n_tiles are dummies
     constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1);
 
-    if (warp == 0) {
+    if (warp == kWarpLoader) {
         // ======================= weight loader (1/kCluster of every chunk, multicast to the cluster) =======================
         if (lane == 0) {
             const uint32_t rank = cluster_rank();
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                     const uint32_t slice = bytes / kCluster;
                     for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
                         const uint32_t stage = cnt % kStages, round = cnt / kStages;
-                        if (round > 0) mbar_wait(&bars->w_empty[stage], (round - 1) & 1);
+                        if (round > 0) mbar_wait_sleep(&bars->w_empty[stage], (round - 1) & 1, 32);
                         mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
                         bulk_g2s_multicast(smem + kBOffRing + stage * kStageBytes + rank * slice,
                                            p.packed + st.w_off + (uint32_t)c * bytes + rank * slice, slice,
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                     }
                 }
         }
-    } else if (warp == 1) {
+    } else if (warp == kWarpMma) {
         // ======================= MMA issuer =======================
         if (lane == 0) {
             uint32_t cnt = 0, it = 0;
@@ -108,6 +110,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                     uint32_t waited = 0;
                     for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
                         const int pn = st.panel[c];
+                        const uint32_t stage = cnt % kStages;
+                        mbar_wait(&bars->w_full[stage], (cnt / kStages) & 1);     // usually long landed: checked off the critical path
                         uint32_t a_addr;
                         if (pn >= kPanelP) {
                             if (!pro_waited) { mbar_wait(&bars->pro_ready, ti & 1); pro_waited = true; }
@@ -116,8 +120,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                             if (it > 0 && !(waited & (1u << pn))) { mbar_wait(&bars->panel_ready[pn], (it - 1) & 1); waited |= 1u << pn; }
                             a_addr = smem_u32(smem + kBOffH + pn * kPanelBytes);
                         }
-                        const uint32_t stage = cnt % kStages;
-                        mbar_wait(&bars->w_full[stage], (cnt / kStages) & 1);
                         tc_fence_after();
                         const uint32_t b_addr = smem_u32(smem + kBOffRing + stage * kStageBytes);
                         for (int k = 0; k < st.ksteps[c]; ++k)
@@ -130,10 +132,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                 }
             }
         }
-    } else if (warp < 2 + kBwdEpiWarps) {
+    } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 8) {
         // ======================= epilogue: ReLU mask, bf16, next A operand =======================
         // warp (q, hf): rows 32q..32q+31, columns [32 hf, 32 hf + 32) of every panel
-        const int q = warp & 3, hf = (warp - 2) >> 2;
+        const int q = warp & 3, hf = (warp - kWarpEpi0) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0;
@@ -188,9 +190,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                 }
             }
         }
-    } else if (warp < 2 + kBwdEpiWarps + 4) {
+    } else if (warp < 4) {
         // ======================= prologue: head gradients of the next tile =======================
-        const int row = (warp - 2 - kBwdEpiWarps) * 32 + lane;
+        const int row = warp * 32 + lane;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = blockIdx.x + ti * gridDim.x;
             const long long pt = (long long)tile * kTileRows + row;
@@ -212,8 +214,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                                              : make_uint4(0u, 0u, 0u, 0u);
             }
             if (ti > 0) {
-                mbar_wait(&bars->pro_free, (ti - 1) & 1);
-                mbar_wait(&bars->pro_stored, (ti - 1) & 1);
+                mbar_wait_sleep(&bars->pro_free, (ti - 1) & 1, 256);
+                mbar_wait_sleep(&bars->pro_stored, (ti - 1) & 1, 256);
             }
             uint8_t* pb = smem + kBOffP;
             if (p.has_view) {
@@ -241,14 +243,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
             fence_async_smem();
             mbar_arrive(&bars->pro_ready);
         }
-    } else {
+    } else if (warp == kWarpStash) {
         // ======================= stash writer =======================
         if (lane == 0) {
             uint32_t it = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = blockIdx.x + ti * gridDim.x;
                 uint8_t* base = p.dy + (size_t)tile * p.tile_stash_bytes;
-                mbar_wait(&bars->pro_ready, ti & 1);
+                mbar_wait_sleep(&bars->pro_ready, ti & 1, 64);
                 if (p.has_view && tile < p.n_tiles) {
                     bulk_s2g(base + (size_t)9 * 65536, smem + kBOffP, 2 * kPanelBytes);
                     bulk_commit();
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                 for (int s = 0; s < p.n_steps; ++s, ++it) {
                     const TcStep& st = p.steps[s];
                     for (int j = 0; j < 4; ++j) {
-                        mbar_wait(&bars->panel_ready[j], it & 1);
+                        mbar_wait_sleep(&bars->panel_ready[j], it & 1, 64);
                         if (tile < p.n_tiles) {
                             bulk_s2g(base + (size_t)st.slot * 65536 + j * kPanelBytes, smem + kBOffH + j * kPanelBytes, kPanelBytes);
                             bulk_commit();
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 1) tmem_dealloc<512>(tmem);
+    if (warp == kWarpMma) tmem_dealloc<512>(tmem);
 }
 
 // =================================================================================================
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             for (int sg = 0; sg < n_stages; ++sg) {
                 const int tile = part + (sg >> 1) * nparts, half = sg & 1;
                 const uint32_t stage = sg % kWgStages, round = sg / kWgStages;
-                if (round > 0) mbar_wait(&bars->empty[stage], (round - 1) & 1);
+                if (round > 0) mbar_wait_sleep(&bars->empty[stage], (round - 1) & 1, 32);
                 uint8_t* dst = smem + stage * kWgStageBytes;
                 mbar_arrive_expect_tx(&bars->full[stage], bytes);
                 const size_t toff = (size_t)tile * p.tile_stash_bytes + (size_t)half * kHalfPanel;
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                 long long pt = (long long)tile * kTileRows + half * 64 + r;
                 if (pt >= p.n_points) pt = p.n_points - 1;     // rows past the end carry zero gradients; any finite input will do
                 const int ray = p.n_points < (1LL << 31) ? (int)((unsigned)pt / (unsigned)p.n_samples) : (int)(pt / p.n_samples);
-                if (round > 0) mbar_wait(&bars->raw_free[slot], (round - 1) & 1);
+                if (round > 0) mbar_wait_sleep(&bars->raw_free[slot], (round - 1) & 1, 128);
                 float* dst = s_raw + slot * 640 + r;
                 if (job.b_enc) {
                     cp_async4(dst, p.z + pt);

@@ -12,18 +12,22 @@ def idesc(m, n, a_mn=0, b_mn=0):
 dev = 'cuda:0'
 a = torch.zeros(65536, dtype=torch.uint8, device=dev); b = torch.zeros(131072, dtype=torch.uint8, device=dev)
 d = torch.zeros((128, 512), device=dev); tm = torch.zeros(2, dtype=torch.int64, device=dev)
-for n in (256, 128, 64):
-    for count in (16, 64, 256):
-        for same in (True, False):
-            ops = []
-            for i in range(count):
-                k = i % 4; pan = 0 if same else (i // 4) % 4
-                ops.append((16384 * pan + 32 * k, (32768 * pan if n == 256 else 16384 * pan) + 32 * k, 0, int(i > 0)))
-            o = torch.tensor(np.array(ops, np.int64), dtype=torch.int64).to(torch.int32).to(dev)
-            for rep in range(2):
-                rc = lib.snerfdbg_probe(a.data_ptr(), 65536, b.data_ptr(), 131072, d.data_ptr(), o.data_ptr(), count, 16, 1024, 16, 1024,
-                                        idesc(128, n), (1 << 46) | (2 << 61), 512, None, tm.data_ptr())
-                assert rc == 0
-                torch.cuda.synchronize()
-            t = tm.cpu().numpy()
-            print(f'N={n:3d} count={count:3d} same_operand={same}: issue {t[0]/count:6.1f} cyc/MMA, complete {t[1]/count:6.1f} cyc/MMA', flush=True)
+lib.snerfdbg_set_probe_pattern.argtypes = [C.c_int, C.c_int]
+for chunk, waits in ((0, 0), (4, 0), (4, 1), (4, 2), (8, 2), (1, 0)):
+  lib.snerfdbg_set_probe_pattern(chunk, waits)
+  print(f'-- commit every {chunk} MMAs, {waits} ready-barrier waits per chunk')
+  for n in (256,):
+    for count in (64, 256):
+        for same in (False,):
+              ops = []
+              for i in range(count):
+                  k = i % 4; pan = 0 if same else (i // 4) % 4
+                  ops.append((16384 * pan + 32 * k, (32768 * pan if n == 256 else 16384 * pan) + 32 * k, 0, int(i > 0)))
+              o = torch.tensor(np.array(ops, np.int64), dtype=torch.int64).to(torch.int32).to(dev)
+              for rep in range(2):
+                  rc = lib.snerfdbg_probe(a.data_ptr(), 65536, b.data_ptr(), 131072, d.data_ptr(), o.data_ptr(), count, 16, 1024, 16, 1024,
+                                          idesc(128, n), (1 << 46) | (2 << 61), 512, None, tm.data_ptr())
+                  assert rc == 0
+                  torch.cuda.synchronize()
+              t = tm.cpu().numpy()
+              print(f'N={n:3d} count={count:3d} same_operand={same}: issue {t[0]/count:6.1f} cyc/MMA, complete {t[1]/count:6.1f} cyc/MMA', flush=True)

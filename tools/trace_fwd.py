@@ -25,10 +25,19 @@ trace = torch.zeros(1024, dtype=torch.int64, device=DEV)
 for _ in range(2):
     ops.mlp_forward(block.desc, table, packed, o, d, vd, z, None, ws, flags)
 lib.snerfdbg_set_trace.argtypes = [ctypes.c_void_p]
+lib.snerfdbg_set_fwd_debug.argtypes = [ctypes.c_int]
+dbg = [int(a[6:]) for a in sys.argv if a.startswith('--dbg=')]
+lib.snerfdbg_set_fwd_debug(dbg[0] if dbg else 0)
 lib.snerfdbg_set_trace(trace.data_ptr())
 ops.mlp_forward(block.desc, table, packed, o, d, vd, z, None, ws, flags)
 torch.cuda.synchronize()
 lib.snerfdbg_set_trace(None)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    ops.mlp_forward(block.desc, table, packed, o, d, vd, z, None, ws, flags)
+e1.record(); torch.cuda.synchronize()
+print(f'forward kernel (4096 rays x 64): {e0.elapsed_time(e1) / 5 * 1e3:.1f} us')
 t = trace.cpu().numpy()
 t0 = t[256]   # epilogue: accumulator of step 0 complete
 rel = lambda v: int(v - t0) if v else None
