@@ -87,23 +87,33 @@ __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward kernel
+// forward kernel (CTA pairs, two tiles in flight)
 // ------------------------------------------------------------------------------------------------
-constexpr int kFwdThreads = 480;                                       // 15 warps, see the role table above
+// A cluster of two CTAs works on "super tiles" of 256 points: CTA r owns rows [128 r, 128 r + 128) -- its activation
+// panels, its half of every weight chunk (N/2 rows of B) and its 128 accumulator rows in its own TMEM -- and the
+// leader's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256) for both.  Each pair keeps TWO super tiles in
+// flight (slots 0/1, one 256-column accumulator each) and the issuer alternates between them step by step, so the
+// epilogue of one tile (TMEM -> bias/ReLU -> bf16 -> smem) runs under the MMAs of the other.
+// Measured (tools/pair_probe.py, tools/mma_rate.py): 129 cycles per M256 N256 K16 pair MMA against 165 cycles per
+// M128 N256 K16 single-CTA MMA, i.e. 2.5x the issue rate per row, and half the weight bytes per SM.
+constexpr int kFwdThreads = 480;                                       // 15 warps, see the role table
 constexpr int kEpiWarps = 8;                                            // 2 per SM sub-partition
-constexpr uint32_t kOffH = 0;
-constexpr uint32_t kOffE = 65536;
-constexpr uint32_t kOffRing = kOffE + 2 * kPanelBytes;                 // 98304
-constexpr uint32_t kOffConst = kOffRing + kStages * kStageBytes;        // 196608
+constexpr int kPStages = 4;                                             // weight ring: this CTA's half chunks; 4 = one whole layer
+constexpr uint32_t kPStageBytes = 16384;
+constexpr uint32_t kOffH = 0;                                           // [2 slots][4 panels]
+constexpr uint32_t kOffE = 2 * 65536;                                   // encoding panel (one, rewritten before every use)
+constexpr uint32_t kOffRing = kOffE + kPanelBytes;                      // 147456
+constexpr uint32_t kOffConst = kOffRing + kPStages * kPStageBytes;      // 212992
 constexpr uint32_t kConstBias16 = 0;                                    // [9][256] bf16 (packed bias + ReLU path)
 constexpr uint32_t kConstBias32 = 9 * 256 * 2;                          // [256] fp32: bias of the last trunk layer (fp32 head path)
 constexpr uint32_t kConstHeadW = kConstBias32 + 256 * 4;                // [4][256] fp32
 constexpr uint32_t kConstRgbW = kConstHeadW + 4 * 256 * 4;              // [3][128] fp32
 constexpr uint32_t kConstMisc = kConstRgbW + 3 * 128 * 4;               // head bias[4], rgb bias[4]
-constexpr uint32_t kConstPart = kConstMisc + 64;                        // [128][4] fp32 partial head sums of the upper column half
+constexpr uint32_t kConstPart = kConstMisc + 64;                        // [2 slots][128][4] fp32 partial head sums of the odd panels
 constexpr uint32_t kOffBars = kOffConst + 16384;
 constexpr uint32_t kFwdSmem = kOffBars + 512 + 1024;                    // + alignment slack
-static_assert(kConstPart + 128 * 4 * 4 <= 16384, "constant area overflow");
+static_assert(kConstPart + 2 * 128 * 4 * 4 <= 16384, "constant area overflow");
+static_assert(kFwdSmem <= 232448, "shared memory budget");
 
 struct FwdParams {
     const uint8_t* packed;
@@ -113,8 +123,8 @@ struct FwdParams {
     const float *rays_o, *rays_d, *z, *noise;
     float *sigma, *rgb;
     uint8_t* stash;                // null in eval
-    long long* trace;              // debug: clock64 timestamps of CTA 0 (tools/trace_fwd.py), normally null
-    int debug;                     // debug (timing experiments, results become garbage): bit0 no panel stores, bit1 no epilogue math, bit2 no weight copies
+    long long* trace;              // debug: clock64 timestamps of pair 0 (tools/trace_fwd.py), normally null
+    int debug;                     // debug (timing experiments, results become garbage): bit0 no panel stores, bit1 no TMEM loads / epilogue math, bit2 no weight copies
     long long n_points;
     int n_samples, n_tiles, n_steps, pts_degree, head_out;
     uint32_t tile_stash_bytes;
@@ -122,7 +132,14 @@ struct FwdParams {
 };
 
 struct FwdBars {
-    uint64_t w_full[kStages], w_empty[kStages], acc_full[2], panel_ready[4], panel_stored[4], enc_ready[2], enc_free[2];
+    uint64_t w_full[kPStages];     // leader: own bytes + the peer's relay (2 arrivals); peer: own bytes (1)
+    uint64_t w_empty[kPStages];    // MMA commit, multicast to both CTAs
+    uint64_t acc_full[2];          // per slot: MMA commit, multicast
+    uint64_t tile_ready[2];        // leader only: 2 x 8 epilogue warps -- accumulator drained, next A operand in smem
+    uint64_t stash_ready[2];       // local: 8 epilogue warps
+    uint64_t stash_done[2];        // local: stash writer finished reading the slot's panels
+    uint64_t enc_ready;            // leader only: 2 x 4 encoder warps; one phase per use of the encoding panel
+    uint64_t enc_free;             // MMA commit, multicast: the MMAs reading the encoding panel have completed
     uint32_t tmem_base;
 };
 
@@ -137,6 +154,15 @@ __device__ __forceinline__ uint32_t bias_act_bf16x2(float lo, float hi, uint32_t
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// Every role walks the same job list: tiles 2g and 2g+1 of this pair occupy slots 0 and 1 and their steps interleave.
+// jx = g * n_steps + s is the job's index within its slot (barrier phases count per slot).
+#define SNERF_FOR_EACH_JOB(my_super, n_steps)                   \
+    for (int g = 0; 2 * g < (my_super); ++g)                    \
+        for (int s = 0; s < (n_steps); ++s)                     \
+            for (int x = 0; x < 2; ++x)                         \
+                if (2 * g + x < (my_super))
+
+template <bool kTrace>
 __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -149,18 +175,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
     float* s_part = (float*)(smem + kOffConst + kConstPart);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const bool save = p.stash != nullptr;
+    const uint32_t rank = cluster_rank();
     // roles by warp id -- the sub-partition arbiter issues the highest eligible warp id first, so the latency-critical
-    // epilogue warps sit on top and the helpers below them:  0-3 encoders | 4 stash writer | 5 weight loader | 6-13 epilogue | 14 MMA issuer (single thread, must never starve)
+    // epilogue warps sit on top and the helpers below them:
+    //   0-3 encoders | 4 stash writer | 5 weight loader | 6-13 epilogue | 14 MMA issuer (leader) / weight relay (peer)
     constexpr int kWarpStash = 4, kWarpLoader = 5, kWarpEpi0 = 6, kWarpMma = 14;
 
     // ---- setup ----
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], kCluster); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->enc_ready[i], 128); mbar_init(&bars->enc_free[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&bars->panel_ready[i], kEpiWarps * 16); mbar_init(&bars->panel_stored[i], 1); }
+        for (int i = 0; i < kPStages; ++i) { mbar_init(&bars->w_full[i], rank == 0 ? 2 : 1); mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->acc_full[i], 1);
+            mbar_init(&bars->tile_ready[i], 2 * kEpiWarps);
+            mbar_init(&bars->stash_ready[i], kEpiWarps);
+            mbar_init(&bars->stash_done[i], 1);
+        }
+        mbar_init(&bars->enc_ready, 2 * 4);
+        mbar_init(&bars->enc_free, 1);
         mbar_fence_init();
     }
-    if (warp == kWarpMma) tmem_alloc<512>(&bars->tmem_base);
+    if (warp == kWarpMma) tmem_alloc2<512>(&bars->tmem_base);
     for (int i = threadIdx.x; i < 9 * 256; i += kFwdThreads) {
         const float* b = p.bias[i >> 8];
         s_bias16[i] = __float2bfloat16_rn(b ? b[i & 255] : 0.f);
@@ -172,227 +206,268 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
     if (threadIdx.x >= 4 && threadIdx.x < 8) s_misc[threadIdx.x] = (p.b_rgb && threadIdx.x < 7) ? p.b_rgb[threadIdx.x - 4] : 0.f;
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();   // every CTA's barriers are initialised before a peer may signal them
+    cluster_sync_all();   // both CTAs' barriers are initialised before either signals the other
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    // every CTA of a cluster runs the same number of tiles (they share one weight ring); tiles >= n_tiles are dummies
-    const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1);
+    // pair pi takes super tiles pi, pi + n_pairs, ...; every pair runs the same count (tiles >= n_tiles are dummies)
+    const int n_pairs = (int)gridDim.x / 2, pi = (int)blockIdx.x / 2;
+    const int n_super = (p.n_tiles + 1) / 2;
+    const int my_super = (n_super + n_pairs - 1) / n_pairs;
+    auto tile_of = [&](int i) { return 2 * (pi + i * n_pairs) + (int)rank; };
 
     if (warp == kWarpLoader) {
-        // ======================= weight loader =======================
-        // each CTA fetches 1/kCluster of every chunk and multicasts it into the ring of every CTA of the cluster
+        // ======================= weight loader: this CTA's N/2 rows of every chunk =======================
+        // When both slots are occupied and a step's chunks fit the ring, the chunks are loaded ONCE and used by both
+        // tiles (the issuer releases a stage after the second tile's MMAs); otherwise once per tile.
         if (lane == 0) {
-            const uint32_t rank = cluster_rank();
             uint32_t cnt = 0;
-            for (int ti = 0; ti < my_tiles; ++ti)
+            for (int g = 0; 2 * g < my_super; ++g) {
+                const bool two = 2 * g + 1 < my_super;
                 for (int s = 0; s < p.n_steps; ++s) {
                     const TcStep& st = p.steps[s];
-                    const uint32_t bytes = (uint32_t)st.n_rows * kRowBytes;
-                    const uint32_t slice = bytes / kCluster;
-                    for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
-                        const uint32_t stage = cnt % kStages, round = cnt / kStages;
-                        if (round > 0) mbar_wait_sleep(&bars->w_empty[stage], (round - 1) & 1, 32);   // all CTAs released the slot
-                        if (p.debug & 4) { mbar_arrive(&bars->w_full[stage]); continue; }
-                        mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
-                        bulk_g2s_multicast(smem + kOffRing + stage * kStageBytes + rank * slice,
-                                           p.packed + st.w_off + (uint32_t)c * bytes + rank * slice, slice,
-                                           &bars->w_full[stage], kClusterMask);
-                    }
-                }
-        }
-    } else if (warp == kWarpMma) {
-        // ======================= MMA issuer =======================
-        // tcgen05.mma issue is nearly synchronous (the queue holds about one pending instruction), so every cycle this
-        // thread spends between two issues beyond the ~140-cycle execution of an MMA idles the tensor pipe; a barrier
-        // wait that succeeds at once still costs ~190 cycles.  The barriers of chunk c+1 are therefore probed BETWEEN
-        // the MMAs of chunk c (non-blocking test_wait, hidden behind the running MMA); the blocking wait is the fallback.
-        if (lane == 0) {
-            uint32_t cnt = 0, it = 0;
-            bool w_ok = false;                         // weight chunk `cnt` already seen landed
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int ebuf = ti & 1;
-                bool enc_waited = false;
-                for (int s = 0; s < p.n_steps; ++s, ++it) {
-                    const TcStep& st = p.steps[s];
-                    const uint32_t d_tmem = tmem + (it & 1) * 256;
-                    const uint32_t idesc = umma_idesc(128, st.n_rows, false, false);
-                    uint32_t waited = 0;
-                    const bool tr = p.trace && blockIdx.x == 0 && ti == 2;
-                    for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
-                        const int pn = st.panel[c];
-                        const uint32_t stage = cnt % kStages;
-                        if (!w_ok) mbar_wait(&bars->w_full[stage], (cnt / kStages) & 1);
-                        uint32_t a_addr;
-                        if (pn == kPanelE) {
-                            if (!enc_waited) { mbar_wait(&bars->enc_ready[ebuf], (ti >> 1) & 1); enc_waited = true; }
-                            a_addr = smem_u32(smem + kOffE + ebuf * kPanelBytes);
-                        } else {
-                            if (it > 0 && !(waited & (1u << pn))) { mbar_wait(&bars->panel_ready[pn], (it - 1) & 1); waited |= 1u << pn; }
-                            a_addr = smem_u32(smem + kOffH + pn * kPanelBytes);
+                    const uint32_t bytes = (uint32_t)st.n_rows * kRowBytes, half = bytes / 2;
+                    const int reps = (two && st.n_chunks > kPStages) ? 2 : 1;
+                    for (int r = 0; r < reps; ++r)
+                        for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
+                            const uint32_t stage = cnt % kPStages, round = cnt / kPStages;
+                            if (round > 0) mbar_wait(&bars->w_empty[stage], (round - 1) & 1);
+                            if (p.debug & 4) { mbar_arrive(&bars->w_full[stage]); continue; }
+                            mbar_arrive_expect_tx(&bars->w_full[stage], half);
+                            bulk_g2s(smem + kOffRing + stage * kPStageBytes, p.packed + st.w_off + (uint32_t)c * bytes + rank * half, half,
+                                     &bars->w_full[stage]);
                         }
-                        tc_fence_after();
-                        if (tr && c < 5) p.trace[s * 16 + c] = clock64();             // operands available
-                        const uint32_t b_addr = smem_u32(smem + kOffRing + stage * kStageBytes);
-                        const int nk = st.ksteps[c];
-                        const uint32_t nstage = (cnt + 1) % kStages, nparity = ((cnt + 1) / kStages) & 1;
-                        const int npn = c + 1 < st.n_chunks ? st.panel[c + 1] : -1;
-                        umma(d_tmem, umma_desc_kmajor(a_addr, 0), umma_desc_kmajor(b_addr, 0), idesc, c != 0);
-                        w_ok = mbar_test_wait(&bars->w_full[nstage], nparity);        // next weight chunk (hidden behind the MMA)
-                        if (nk > 1) umma(d_tmem, umma_desc_kmajor(a_addr, 1), umma_desc_kmajor(b_addr, 1), idesc, true);
-                        if (npn >= 0 && npn != kPanelE && it > 0 && !(waited & (1u << npn)) &&
-                            mbar_test_wait(&bars->panel_ready[npn], (it - 1) & 1))     // next activation panel
-                            waited |= 1u << npn;
-                        for (int k = 2; k < nk; ++k)
-                            umma(d_tmem, umma_desc_kmajor(a_addr, k), umma_desc_kmajor(b_addr, k), idesc, true);
-                        umma_commit_multicast(&bars->w_empty[stage], kClusterMask);   // frees the slot in every CTA's ring
-                        if (tr && c < 5) p.trace[s * 16 + 10 + c] = clock64();        // MMAs of the chunk issued
-                    }
-                    umma_commit(&bars->acc_full[it & 1]);
-                    if (st.last_e_use) umma_commit(&bars->enc_free[ebuf]);
-                    // every epilogue warp of step it-1 has drained its accumulator before step it+1 may overwrite it
-                    if (it > 0 && !(waited & 4u)) mbar_wait(&bars->panel_ready[2], (it - 1) & 1);
-                    if (it > 0 && !(waited & 8u)) mbar_wait(&bars->panel_ready[3], (it - 1) & 1);
                 }
             }
         }
-    } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 8) {
+    } else if (warp == kWarpMma && rank != 0) {
+        // ======================= peer: relay "my half of the chunk has landed" to the leader =======================
+        // (a bulk copy cannot complete on the other CTA's mbarrier: tools/pair_probe.py mode 1 never completes)
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int g = 0; 2 * g < my_super; ++g) {
+                const bool two = 2 * g + 1 < my_super;
+                for (int s = 0; s < p.n_steps; ++s) {
+                    const TcStep& st = p.steps[s];
+                    const int n = ((two && st.n_chunks > kPStages) ? 2 : 1) * st.n_chunks;
+                    for (int c = 0; c < n; ++c, ++cnt) {
+                        const uint32_t stage = cnt % kPStages;
+                        mbar_wait(&bars->w_full[stage], (cnt / kPStages) & 1);
+                        mbar_arrive_cluster(cluster_addr(&bars->w_full[stage], 0));
+                    }
+                }
+            }
+        }
+    } else if (warp == kWarpMma) {
+        // ======================= MMA issuer (leader CTA, one elected lane) =======================
+        // The pair MMA queue is deep, so barrier latencies hide behind queued work as long as this warp's own instruction
+        // stream stays short: the whole warp walks the job list converged (uniform datapath, no per-instruction election
+        // loops), descriptors are 32-bit low words advanced by adds, and the barrier of the NEXT chunk / job is probed
+        // (non-blocking) right after the current MMAs are issued; the blocking wait is only the fallback.
+        {
+            uint32_t stage = 0, wpar = 0;                      // ring position and the parity of its current phase
+            uint32_t eu = 0;                                   // uses of the encoding panel so far
+            const uint32_t ring_lo = desc_lo_kmajor(smem_u32(smem + kOffRing));
+            const uint32_t h_lo = desc_lo_kmajor(smem_u32(smem + kOffH)), e_lo = desc_lo_kmajor(smem_u32(smem + kOffE));
+            bool w_ok = false, t_ok = false;
+            // release: this is the last tile using the step's weight chunks; landed: the chunks were seen by the other tile
+            auto issue_job = [&](const int x, const int g, const int s, const bool release, const bool landed) {
+                const TcStep& st = p.steps[s];
+                const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+                const uint32_t d_tmem = tmem + x * 256;
+                const uint32_t idesc = umma_idesc(256, st.n_rows, false, false);
+                const bool tr = kTrace && p.trace && blockIdx.x == 0 && g == 1 && lane == 0;
+                // the epilogue of the slot's previous job has drained the accumulator and written this job's A panels
+                if (jx > 0 && !t_ok) mbar_wait(&bars->tile_ready[x], (jx - 1) & 1);
+                if (tr) p.trace[(x * 16 + s) * 16 + 0] = clock64();
+                const int nc = st.n_chunks;
+                for (int c = 0; c < nc; ++c) {
+                    const int pn = st.panel[c], nk = st.ksteps[c];
+                    if (!landed && !w_ok) mbar_wait(&bars->w_full[stage], wpar);
+                    if (pn == kPanelE) mbar_wait(&bars->enc_ready, eu & 1);
+                    tc_fence_after();
+                    if (tr && c < 5) p.trace[(x * 16 + s) * 16 + 4 + c] = clock64();
+                    const uint32_t a_lo = pn == kPanelE ? e_lo : h_lo + x * (65536 >> 4) + pn * (kPanelBytes >> 4);
+                    const uint32_t b_lo = ring_lo + stage * (kPStageBytes >> 4);
+                    uint64_t* done = &bars->w_empty[stage];
+                    if (elect_one()) {
+                        umma2_lo(d_tmem, a_lo, b_lo, idesc, c != 0);
+                        if (nk == 4) {
+                            umma2_lo(d_tmem, a_lo + 2, b_lo + 2, idesc, 1);
+                            umma2_lo(d_tmem, a_lo + 4, b_lo + 4, idesc, 1);
+                            umma2_lo(d_tmem, a_lo + 6, b_lo + 6, idesc, 1);
+                        } else {
+                            for (int k = 1; k < nk; ++k) umma2_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, 1);
+                        }
+                        if (release) umma_commit2(done, 3);                          // frees the slot in both CTAs' rings
+                        if (pn == kPanelE) umma_commit2(&bars->enc_free, 3);         // the encoders may rewrite the panel
+                    }
+                    __syncwarp();
+                    if (pn == kPanelE) ++eu;
+                    if (++stage == kPStages) { stage = 0; wpar ^= 1; }
+                    if (!landed) w_ok = mbar_test_wait(&bars->w_full[stage], wpar);  // next chunk: probe now, blocking wait as fallback
+                    if (tr && c < 5) p.trace[(x * 16 + s) * 16 + 9 + c] = clock64();
+                }
+                if (elect_one()) umma_commit2(&bars->acc_full[x], 3);
+                __syncwarp();
+                if (tr) p.trace[(x * 16 + s) * 16 + 1] = clock64();
+            };
+            for (int g = 0; 2 * g < my_super; ++g) {
+                const bool two = 2 * g + 1 < my_super;
+                for (int s = 0; s < p.n_steps; ++s) {
+                    const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+                    const bool shared = two && p.steps[s].n_chunks <= kPStages;
+                    const uint32_t stage0 = stage, wpar0 = wpar;
+                    issue_job(0, g, s, !shared, false);
+                    if (two) {
+                        t_ok = jx > 0 && mbar_test_wait(&bars->tile_ready[1], (jx - 1) & 1);
+                        if (shared) { stage = stage0; wpar = wpar0; }
+                        issue_job(1, g, s, true, shared);
+                        if (shared) w_ok = mbar_test_wait(&bars->w_full[stage], wpar);
+                    }
+                    // next job: slot 0, index jx + 1 within the slot (also across the tile boundary)
+                    t_ok = mbar_test_wait(&bars->tile_ready[0], jx & 1);
+                }
+            }
+        }
+    } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + kEpiWarps) {
         // ======================= epilogue =======================
-        // warp (q, w2): TMEM lanes / tile rows 32q..32q+31; it owns the whole 64-column panels w2 and w2 + 2 of every step,
-        // so the per-panel synchronisation (proxy fence, tcgen05 fence, mbarrier arrive) is paid once per 64 columns while
-        // the partner warp of the same sub-partition works on the neighbouring panel.  TMEM -> registers is software
-        // pipelined in 32-column units: the load of unit u+1 is in flight while unit u is converted and stored.
+        // warp (q, w2): TMEM lanes / tile rows 32q..32q+31; it owns the whole 64-column panels w2 and w2 + 2 of every step.
+        // TMEM -> registers is software pipelined in 32-column units: the load of unit u+1 is in flight while unit u is
+        // converted and stored.  One elected lane per warp signals the stash writer and the leader's MMA thread.
         const int q = warp & 3, w2 = (warp - kWarpEpi0) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t it = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            const int tile = blockIdx.x + ti * gridDim.x;
+        const uint32_t ready0 = cluster_addr(&bars->tile_ready[0], 0), ready1 = cluster_addr(&bars->tile_ready[1], 0);
+        SNERF_FOR_EACH_JOB(my_super, p.n_steps) {
+            const TcStep& st = p.steps[s];
+            const int kind = st.kind;
+            const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+            const int tile = tile_of(2 * g + x);
             const long long pt = (long long)tile * kTileRows + row;
             const bool valid = pt < p.n_points;
-            const int ray = valid ? (int)(pt / p.n_samples) : 0;
-            for (int s = 0; s < p.n_steps; ++s, ++it) {
-                const TcStep& st = p.steps[s];
-                const int kind = st.kind;
-                mbar_wait(&bars->acc_full[it & 1], (it >> 1) & 1);
-                tc_fence_after();
-                const bool tr = p.trace && blockIdx.x == 0 && ti == 2 && q == 0 && lane == 0;
-                if (tr && w2 == 0) p.trace[256 + s * 16 + 0] = clock64();     // epilogue: accumulator complete
-                const int n_pan = st.n_rows / 64;
-                const int n_own = n_pan > w2 + 2 ? 2 : (n_pan > w2 ? 1 : 0);     // panels with data owned by this warp
-                const bool writes_h = (kind != EPI_VIEW) || save;
-                const bool has_head = kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4 || kind == EPI_VIEW;
-                float head[4] = {0.f, 0.f, 0.f, 0.f};
-                const uint32_t acc_addr = lane_addr + (it & 1) * 256;
-                uint32_t rr[2][32];
-                if (n_own > 0) tmem_ld32_issue(acc_addr + w2 * 64, rr[0]);
+            const int ray = (kind == EPI_VIEW && valid) ? (int)((unsigned)pt / (unsigned)p.n_samples) : 0;   // host guarantees n_points < 2^31
+            mbar_wait(&bars->acc_full[x], jx & 1);
+            tc_fence_after();
+            const bool tr = kTrace && p.trace && blockIdx.x == 0 && g == 1 && warp == kWarpEpi0 && lane == 0;
+            if (tr) p.trace[(x * 16 + s) * 16 + 2] = clock64();
+            const int n_pan = st.n_rows / 64;
+            const int n_own = (p.debug & 2) ? 0 : (n_pan > w2 + 2 ? 2 : (n_pan > w2 ? 1 : 0));     // panels with data owned by this warp
+            const bool writes_h = ((kind != EPI_VIEW) || save) && !(p.debug & 1);
+            const bool has_head = kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4 || kind == EPI_VIEW;
+            float head[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint32_t acc_addr = lane_addr + x * 256;
+            uint8_t* hbase = smem + kOffH + x * 65536;
+            uint32_t rr[2][32];
+            if (n_own > 0) tmem_ld32_issue(acc_addr + w2 * 64, rr[0]);
+            // the stash writer has finished reading the panels of the slot's previous job
+            if (save && jx > 0 && n_own > 0) mbar_wait(&bars->stash_done[x], (jx - 1) & 1);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int jj = u >> 1, h = u & 1, j = w2 + 2 * jj;
-                    if (jj < n_own) {
-                        const int col0 = j * 64 + h * 32;
-                        tmem_ld_wait(rr[u & 1]);
-                        if (u + 1 < 2 * n_own) tmem_ld32_issue(acc_addr + (w2 + 2 * ((u + 1) >> 1)) * 64 + ((u + 1) & 1) * 32, rr[(u + 1) & 1]);
-                        float v[32];
+            for (int u = 0; u < 4; ++u) {
+                const int jj = u >> 1, h = u & 1, j = w2 + 2 * jj;
+                if (jj < n_own) {
+                    const int col0 = j * 64 + h * 32;
+                    tmem_ld_wait(rr[u & 1]);
+                    if (u + 1 < 2 * n_own) tmem_ld32_issue(acc_addr + (w2 + 2 * ((u + 1) >> 1)) * 64 + ((u + 1) & 1) * 32, rr[(u + 1) & 1]);
+                    float v[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[u & 1][i]);
-                        if (tr && h == 0) p.trace[256 + s * 16 + 1 + j] = clock64();     // first TMEM load of panel j done
-                        uint32_t pk[16];
-                        if (p.debug & 2) {
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[u & 1][i]);
+                    uint32_t pk[16];
+                    if (kind == EPI_RELU || kind == EPI_LINEAR) {
+                        const uint4* bb = reinterpret_cast<const uint4*>(s_bias16 + st.bias_row * 256 + col0);
+                        const bool relu = kind == EPI_RELU;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) pk[i] = rr[u & 1][2 * i];
-                        } else
-                        if (kind == EPI_RELU || kind == EPI_LINEAR) {
-                            const uint4* bb = reinterpret_cast<const uint4*>(s_bias16 + st.bias_row * 256 + col0);
-                            const bool relu = kind == EPI_RELU;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint4 b = bb[i];
-                                pk[4 * i + 0] = bias_act_bf16x2(v[8 * i + 0], v[8 * i + 1], b.x, relu);
-                                pk[4 * i + 1] = bias_act_bf16x2(v[8 * i + 2], v[8 * i + 3], b.y, relu);
-                                pk[4 * i + 2] = bias_act_bf16x2(v[8 * i + 4], v[8 * i + 5], b.z, relu);
-                                pk[4 * i + 3] = bias_act_bf16x2(v[8 * i + 6], v[8 * i + 7], b.w, relu);
-                            }
-                        } else {
-                            if (kind == EPI_VIEW) {
-                                const float4* vb = reinterpret_cast<const float4*>(p.view_bias + (size_t)ray * 128 + col0);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 b = __ldg(vb + i);
-                                    v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
-                                    v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
-                                    v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
-                                    v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
-                                }
-                            } else {
-                                const float4* bb = reinterpret_cast<const float4*>(s_bias32 + col0);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 b = bb[i];
-                                    v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
-                                    v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
-                                    v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
-                                    v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
-                                }
-                            }
-                            // fp32 heads on the un-rounded activations
-                            const float* wbase = kind == EPI_VIEW ? s_wrgb : s_whead;
-                            const int wld = kind == EPI_VIEW ? 128 : 256;
-                            const int nh = kind == EPI_RELU_HEAD1 ? 1 : (kind == EPI_VIEW ? 3 : 4);
-#pragma unroll
-                            for (int hh = 0; hh < 4; ++hh) {
-                                if (hh < nh) {
-                                    const float4* w = reinterpret_cast<const float4*>(wbase + hh * wld + col0);
-                                    float a = head[hh];
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const float4 ww = w[i];
-                                        a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
-                                    }
-                                    head[hh] = a;
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 b = bb[i];
+                            pk[4 * i + 0] = bias_act_bf16x2(v[8 * i + 0], v[8 * i + 1], b.x, relu);
+                            pk[4 * i + 1] = bias_act_bf16x2(v[8 * i + 2], v[8 * i + 3], b.y, relu);
+                            pk[4 * i + 2] = bias_act_bf16x2(v[8 * i + 4], v[8 * i + 5], b.z, relu);
+                            pk[4 * i + 3] = bias_act_bf16x2(v[8 * i + 6], v[8 * i + 7], b.w, relu);
                         }
-                        if (writes_h && !(p.debug & 1)) {
-                            if (h == 0 && save && it > 0) mbar_wait(&bars->panel_stored[j], (it - 1) & 1);
-                            uint8_t* dst = smem + kOffH + j * kPanelBytes;
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                *reinterpret_cast<uint4*>(dst + swz_offset(row, h * 4 + c)) =
-                                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                        }
-                    }
-                    if (h == 1) {
-                        if (jj < n_own && writes_h && !(p.debug & 1)) fence_async_smem();
-                        tc_fence_before();
-                        mbar_arrive(&bars->panel_ready[j]);
-                        if (tr) p.trace[256 + s * 16 + 5 + j] = clock64();         // panel j handed over
-                    }
-                }
-                if (has_head) {
-                    // combine the two panel sets: the odd-panel warp hands its partial sums to the even-panel warp
-                    if (w2 == 1) {
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) s_part[row * 4 + h] = head[h];
-                    }
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-                    if (w2 == 0 && valid) {
-                        const float4 o = *reinterpret_cast<const float4*>(s_part + row * 4);
-                        const int mb = kind == EPI_VIEW ? 4 : 0;
-                        head[0] += o.x + s_misc[mb + 0]; head[1] += o.y + s_misc[mb + 1];
-                        head[2] += o.z + s_misc[mb + 2]; head[3] += o.w + s_misc[mb + 3];
+                    } else {
                         if (kind == EPI_VIEW) {
+                            const float4* vb = reinterpret_cast<const float4*>(p.view_bias + (size_t)ray * 128 + col0);
 #pragma unroll
-                            for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h]);             // :704-707
-                        } else {
-                            const float nz = p.noise ? p.noise[pt] : 0.f;
-                            p.sigma[pt] = fmaxf(head[0] + nz, 0.f);                                        // :668-672
-                            if (kind == EPI_RELU_HEAD4) {
-#pragma unroll
-                                for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b = __ldg(vb + i);
+                                v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
+                                v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
+                                v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
+                                v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
                             }
+                        } else {
+                            const float4* bb = reinterpret_cast<const float4*>(s_bias32 + col0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b = bb[i];
+                                v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
+                                v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
+                                v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
+                                v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
+                            }
+                        }
+                        // fp32 heads on the un-rounded activations
+                        const float* wbase = kind == EPI_VIEW ? s_wrgb : s_whead;
+                        const int wld = kind == EPI_VIEW ? 128 : 256;
+                        const int nh = kind == EPI_RELU_HEAD1 ? 1 : (kind == EPI_VIEW ? 3 : 4);
+#pragma unroll
+                        for (int hh = 0; hh < 4; ++hh) {
+                            if (hh < nh) {
+                                const float4* w = reinterpret_cast<const float4*>(wbase + hh * wld + col0);
+                                float a = head[hh];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 ww = w[i];
+                                    a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
+                                }
+                                head[hh] = a;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+                    }
+                    if (writes_h) {
+                        uint8_t* dst = hbase + j * kPanelBytes;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4*>(dst + swz_offset(row, h * 4 + c)) =
+                                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    }
+                    if (tr) p.trace[512 + (x * 16 + s) * 8 + 1 + u] = clock64();
+                }
+            }
+            // hand-over: generic-proxy stores -> async proxy (MMA operand fetch, bulk store), TMEM reads ordered before the
+            // next MMA into this accumulator; then one arrival per warp
+            if (n_own > 0 && writes_h) fence_async_smem();
+            tc_fence_before();
+            if (tr) p.trace[512 + (x * 16 + s) * 8 + 5] = clock64();
+            __syncwarp();
+            if (lane == 0) {
+                if (save) mbar_arrive(&bars->stash_ready[x]);
+                mbar_arrive_cluster(x ? ready1 : ready0);
+                if (tr) p.trace[(x * 16 + s) * 16 + 3] = clock64();
+            }
+            if (has_head) {
+                // combine the two panel sets: the odd-panel warp hands its partial sums to the even-panel warp
+                float* part = s_part + x * 512;
+                if (w2 == 1) {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) part[row * 4 + h] = head[h];
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                if (w2 == 0 && valid) {
+                    const float4 o = *reinterpret_cast<const float4*>(part + row * 4);
+                    const int mb = kind == EPI_VIEW ? 4 : 0;
+                    head[0] += o.x + s_misc[mb + 0]; head[1] += o.y + s_misc[mb + 1];
+                    head[2] += o.z + s_misc[mb + 2]; head[3] += o.w + s_misc[mb + 3];
+                    if (kind == EPI_VIEW) {
+#pragma unroll
+                        for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h]);             // :704-707
+                    } else {
+                        const float nz = p.noise ? p.noise[pt] : 0.f;
+                        p.sigma[pt] = fmaxf(head[0] + nz, 0.f);                                        // :668-672
+                        if (kind == EPI_RELU_HEAD4) {
+#pragma unroll
+                            for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
                         }
                     }
                 }
@@ -400,53 +475,68 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
         }
     } else if (warp < 4) {
         // ======================= encoder =======================
+        // The encodings of the group's two tiles are computed once and kept in registers (packed bf16); the single
+        // encoding panel is rewritten before each use (layer 0, skip layer, view layer of the points-augmented model) in
+        // the issuer's order, as soon as the MMAs of the previous use have completed.
         const int row = warp * 32 + lane;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            const int tile = blockIdx.x + ti * gridDim.x;
-            const int ebuf = ti & 1;
-            const long long pt = (long long)tile * kTileRows + row;
-            float x[3] = {0.f, 0.f, 0.f};
-            if (pt < p.n_points) {
-                const int ray = (int)(pt / p.n_samples);
-                const float zz = p.z[pt];
+        const uint32_t enc_addr = cluster_addr(&bars->enc_ready, 0);
+        uint32_t e_steps = 0;                       // bit s: step s reads the encoding panel
+        for (int s = 0; s < p.n_steps; ++s)
+            for (int c = 0; c < p.steps[s].n_chunks; ++c)
+                if (p.steps[s].panel[c] == kPanelE) e_steps |= 1u << s;
+        uint32_t eu = 0;
+        for (int g = 0; 2 * g < my_super; ++g) {
+            const bool two = 2 * g + 1 < my_super;
+            uint32_t pk[2][32];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) x[c] = fmaf(p.rays_d[ray * 3 + c], zz, p.rays_o[ray * 3 + c]);   // :140/:142
+            for (int x = 0; x < 2; ++x) {
+                const long long pt = (long long)tile_of(2 * g + x) * kTileRows + row;
+                float xx[3] = {0.f, 0.f, 0.f};
+                if ((x == 0 || two) && pt < p.n_points) {
+                    const int ray = (int)((unsigned)pt / (unsigned)p.n_samples);
+                    const float zz = p.z[pt];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) xx[c] = fmaf(p.rays_d[ray * 3 + c], zz, p.rays_o[ray * 3 + c]);   // :140/:142
+                }
+                float enc[64];
+#pragma unroll
+                for (int k = 0; k < 64; ++k) enc[k] = 0.f;
+                encode_point(xx, p.pts_degree, enc);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) pk[x][k] = pack_bf16(enc[2 * k], enc[2 * k + 1]);
             }
-            float enc[64];
+            for (int s = 0; s < p.n_steps; ++s) {
+                if (!((e_steps >> s) & 1u)) continue;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) enc[i] = 0.f;
-            encode_point(x, p.pts_degree, enc);
-            if (ti >= 2) mbar_wait_sleep(&bars->enc_free[ebuf], ((ti >> 1) - 1) & 1, 256);
-            uint8_t* dst = smem + kOffE + ebuf * kPanelBytes;
+                for (int x = 0; x < 2; ++x) {
+                    if (x == 1 && !two) continue;
+                    if (eu > 0) mbar_wait(&bars->enc_free, (eu - 1) & 1);
+                    uint8_t* dst = smem + kOffE;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 u = make_uint4(pack_bf16(enc[8 * c], enc[8 * c + 1]), pack_bf16(enc[8 * c + 2], enc[8 * c + 3]),
-                                           pack_bf16(enc[8 * c + 4], enc[8 * c + 5]), pack_bf16(enc[8 * c + 6], enc[8 * c + 7]));
-                *reinterpret_cast<uint4*>(dst + swz_offset(row, c)) = u;
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4*>(dst + swz_offset(row, c)) = make_uint4(pk[x][4 * c], pk[x][4 * c + 1], pk[x][4 * c + 2], pk[x][4 * c + 3]);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(enc_addr);
+                    ++eu;
+                }
             }
-            fence_async_smem();
-            mbar_arrive(&bars->enc_ready[ebuf]);
         }
     } else if (warp == kWarpStash) {
         // ======================= stash writer (training) =======================
         if (save && lane == 0) {
-            uint32_t it = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int tile = blockIdx.x + ti * gridDim.x;
-                uint8_t* base = p.stash + (size_t)tile * p.tile_stash_bytes;
-                for (int s = 0; s < p.n_steps; ++s, ++it) {
-                    const TcStep& st = p.steps[s];
-                    const int n_pan = st.n_rows / 64;
-                    for (int j = 0; j < 4; ++j) {
-                        mbar_wait_sleep(&bars->panel_ready[j], it & 1, 64);
-                        if (j < n_pan && tile < p.n_tiles) {
-                            bulk_s2g(base + (size_t)st.slot * 65536 + j * kPanelBytes, smem + kOffH + j * kPanelBytes, kPanelBytes);
-                            bulk_commit();
-                        }
-                    }
+            SNERF_FOR_EACH_JOB(my_super, p.n_steps) {
+                const TcStep& st = p.steps[s];
+                const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+                const int tile = tile_of(2 * g + x);
+                mbar_wait_sleep(&bars->stash_ready[x], jx & 1, 64);
+                if (tile < p.n_tiles) {
+                    bulk_s2g(p.stash + (size_t)tile * p.tile_stash_bytes + (size_t)st.slot * 65536, smem + kOffH + x * 65536,
+                             (uint32_t)(st.n_rows / 64) * kPanelBytes);
+                    bulk_commit();
                     bulk_wait_read<0>();
-                    for (int j = 0; j < 4; ++j) mbar_arrive(&bars->panel_stored[j]);
                 }
+                mbar_arrive(&bars->stash_done[x]);
             }
             bulk_wait_all<0>();
         }
@@ -454,8 +544,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();   // no CTA leaves while a peer may still multicast into its ring or signal its barriers
-    if (warp == kWarpMma) tmem_dealloc<512>(tmem);
+    cluster_sync_all();   // no CTA leaves while the pair may still read its smem, signal its barriers or use its TMEM
+    if (warp == kWarpMma) tmem_dealloc2<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -496,12 +586,15 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     p.n_samples = n_samples; p.n_tiles = w.n_tiles; p.n_steps = pl.n_fwd; p.pts_degree = d.pts_degree; p.head_out = m.head_out;
     p.tile_stash_bytes = pl.tile_stash_bytes;
     for (int s = 0; s < pl.n_fwd; ++s) p.steps[s] = pl.fwd[s];
+    SNERF_REQUIRE(p.n_points < (1LL << 31), "mlp_forward: more than 2^31 points in one call");
     static bool attr = false;
     if (!attr) {
-        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
         attr = true;
     }
-    SNERF_CUDA_OK(launch_clustered(tc_forward_kernel, chain_grid(w.n_tiles), kFwdThreads, kFwdSmem, st, p));
+    if (p.trace) SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<true>, pair_grid(w.n_tiles), kFwdThreads, kFwdSmem, st, p));
+    else SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<false>, pair_grid(w.n_tiles), kFwdThreads, kFwdSmem, st, p));
     return SNERF_OK;
 }
 

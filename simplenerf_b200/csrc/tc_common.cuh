@@ -42,10 +42,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: stay suspended instead of spinning
         : "memory");
     return ok != 0;
 }
@@ -74,20 +74,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// Polite wait for warps that are off the critical path (producers running ahead, stash writers): the issue arbiter of an
-// SM sub-partition favours the highest warp id among eligible warps, so a tight polling loop in a helper warp steals issue
-// slots from the epilogue warps.  Sleeping between probes keeps the helper ineligible.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
-    if (mbar_test_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(ns);
-        if (clock64() - t0 > 4000000000LL) {
-            printf("simplenerf_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-                   threadIdx.x, smem_u32(bar), parity);
-            __trap();
-        }
-    }
+// Wait used by helper warps (loaders, stash writers, encoders).  mbarrier.try_wait is a hardware-suspended wait (the
+// thread does not burn issue slots while the phase is pending), so no software back-off is wanted: a __nanosleep
+// between probes was measured to add ~1 us (~2000 cycles) to every ring refill -- the sleep granularity is far coarser
+// than the requested 32 ns -- which throttled the weight ring of the chain kernels.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned) { mbar_wait(bar, parity); }
+
+// one lane of a converged warp (the pattern the compiler recognises for single-thread tcgen05 issue)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- proxies / fences ------------------------------------------------------------------------------
@@ -233,6 +230,95 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t 
 // arrives (count 1) on the mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- CTA pairs (cta_group::2): one MMA over two SMs ---------------------------------------------------
+// M = 256: each CTA of the pair supplies 128 rows of A and N/2 rows of B at the SAME shared-memory offsets and
+// receives its 128 rows of D (all N columns) at the same TMEM address.  Only the leader (cluster rank 0) issues.
+__device__ __forceinline__ uint32_t cluster_addr(const void* local_smem, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem)), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier of any CTA of the cluster (address from cluster_addr).  Default semantics on purpose: a
+// release at cluster scope compiles to MEMBAR.ALL.GPU + ERRBAR and was measured at ~20 % of the epilogue's time.  The
+// data the arrival publishes is this CTA's own shared memory, already made visible to the async proxy (tensor core,
+// bulk copies) by fence.proxy.async; only the count has to travel.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait_cl(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait, acquire at cluster scope (the arrivals may come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cl(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cl(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("simplenerf_b200: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                   threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result) {   // same warp id and same smem offset in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// Issue-cost note (tools/pair_probe.py): the single issuing thread is latency-bound on its OWN scalar code -- building
+// two 64-bit descriptors from scratch costs more cycles than the 129-cycle M256 N256 K16 MMA it feeds.  The K-major
+// 128-byte-swizzle descriptor of a panel is therefore kept as a 32-bit low word (start address >> 4 | LBO field), the
+// constant high word is shared, and a K step is "+2" on the low word.
+constexpr uint32_t kDescHiKmajor = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, 128-byte swizzle
+__device__ __forceinline__ uint32_t desc_lo_kmajor(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void umma2_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiKmajor)
+        : "memory");
+}
+// arrives (count 1) on the same-offset mbarrier of every CTA in cta_mask once every pair MMA issued so far has completed
+__device__ __forceinline__ void umma_commit2(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
 }
 
 // fp32 reductions into global memory (no return value): scalar and 16-byte vector forms

@@ -225,6 +225,12 @@ static inline int chain_grid(int n_tiles) {
     return g < kCluster ? kCluster : g;
 }
 
+// pair kernels: one CTA pair per two SMs; a pair works on 256-point super tiles
+static inline int pair_grid(int n_tiles) {
+    const int n_super = (n_tiles + 1) / 2, pairs = num_sms() / 2;
+    return 2 * (n_super < pairs ? n_super : pairs);
+}
+
 template <typename Kernel, typename Params>
 static inline cudaError_t launch_clustered(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t st, const Params& p) {
     cudaLaunchConfig_t cfg{};

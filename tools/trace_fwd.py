@@ -37,19 +37,19 @@ e0.record()
 for _ in range(5):
     ops.mlp_forward(block.desc, table, packed, o, d, vd, z, None, ws, flags)
 e1.record(); torch.cuda.synchronize()
-print(f'forward kernel (4096 rays x 64): {e0.elapsed_time(e1) / 5 * 1e3:.1f} us')
+print(f'forward kernel (4096 rays x 64, save={save}): {e0.elapsed_time(e1) / 5 * 1e3:.1f} us')
 t = trace.cpu().numpy()
-t0 = t[256]   # epilogue: accumulator of step 0 complete
+t0 = t[0]   # issuer: slot 0, step 0 of the pair's third tile: operands ready
 rel = lambda v: int(v - t0) if v else None
-print('EPI  step | acc done | tmem-ld done p0..p3 | handed p0..p3 | panel1: math done, stores issued, fence done')
+print('slot step | issuer: operands ready, all MMAs issued | epilogue warp 6: accumulator complete, handed over')
 for s_ in range(10):
-    e = t[256 + s_ * 16: 256 + s_ * 16 + 16]
-    print(f'{s_:2d} | {rel(e[0])} | {[rel(x) for x in e[1:5]]} | {[rel(x) for x in e[5:9]]} | {[rel(x) for x in e[9:12]]}')
-print('MMA  step | A panel available c0..c4 | weight chunk landed c0..c4 | chunk issued c0..c4')
+    for x in range(2):
+        e = t[(x * 16 + s_) * 16: (x * 16 + s_) * 16 + 16]
+        print(f'{x} {s_:2d} | {rel(e[0])} {rel(e[1])} | {rel(e[2])} {rel(e[3])} | weights seen {[rel(v) for v in e[4:9]]} chunk issued {[rel(v) for v in e[9:14]]}')
+print('epilogue warp 6 detail: slot step | after acc wait | unit 0..3 stored | fenced | arrived   (relative to the acc wait)')
 for s_ in range(10):
-    m = t[s_ * 16: s_ * 16 + 16]
-    print(f'{s_:2d} | {[rel(x) for x in m[0:5]]} | {[rel(x) for x in m[5:10]]} | {[rel(x) for x in m[10:15]]}')
-print('all epilogue warps (warp, q, hf): handed p0..p3 of steps 1 and 2')
-for w in range(8):
-    v = t[512 + w * 8: 512 + w * 8 + 8]
-    print(f'warp {w + 2} q={(w + 2) & 3} hf={w >> 2}: {[rel(x) for x in v]}')
+    for x in range(2):
+        e = t[(x * 16 + s_) * 16: (x * 16 + s_) * 16 + 16]
+        d = t[512 + (x * 16 + s_) * 8: 512 + (x * 16 + s_) * 8 + 8]
+        r2 = lambda v: int(v - e[2]) if v else None
+        print(f'{x} {s_:2d} | 0 | {[r2(v) for v in d[1:5]]} | {r2(d[5])} | {r2(e[3])}')
