@@ -154,14 +154,6 @@ __device__ __forceinline__ uint32_t bias_act_bf16x2(float lo, float hi, uint32_t
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
-// Every role walks the same job list: tiles 2g and 2g+1 of this pair occupy slots 0 and 1 and their steps interleave.
-// jx = g * n_steps + s is the job's index within its slot (barrier phases count per slot).
-#define SNERF_FOR_EACH_JOB(my_super, n_steps)                   \
-    for (int g = 0; 2 * g < (my_super); ++g)                    \
-        for (int s = 0; s < (n_steps); ++s)                     \
-            for (int x = 0; x < 2; ++x)                         \
-                if (2 * g + x < (my_super))
-
 template <bool kTrace>
 __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];

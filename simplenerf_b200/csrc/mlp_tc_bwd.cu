@@ -22,16 +22,24 @@ namespace snerf {
 using namespace tc;
 
 // =================================================================================================
-// dgrad chain kernel
+// dgrad chain kernel (CTA pairs, two tiles in flight -- the machine of the forward kernel run backwards)
 // =================================================================================================
-constexpr int kBwdThreads = 480;   // loader, MMA, 8 epilogue, 4 prologue, stash writer
+// roles by warp id: 0-3 prologue | 4 stash writer | 5 weight loader | 6-13 epilogue | 14 MMA issuer (leader) / relay (peer)
+// Per pair and group: two 256-point super tiles occupy slots 0/1; the issuer alternates between them step by step and
+// both tiles share the weight chunks of a step (mlp_tc.cu describes the protocol).  The prologue writes dY_v straight
+// into panels 0-1 of the slot (they are free until the first epilogue of the tile) and the 16-column head-pre panel
+// into one small buffer that is rewritten before each use.
+constexpr int kBwdThreads = 480;
 constexpr int kBwdEpiWarps = 8;
-constexpr uint32_t kBOffH = 0;
-constexpr uint32_t kBOffP = 65536;                                  // 3 panels: dY_v (2) + head-pre (1)
-constexpr uint32_t kBOffRing = kBOffP + 3 * kPanelBytes;             // 114688
-constexpr uint32_t kBOffConst = kBOffRing + kStages * kStageBytes;   // 212992
+constexpr int kBStages = 4;
+constexpr uint32_t kBStageBytes = 16384;
+constexpr uint32_t kBOffH = 0;                                          // [2 slots][4 panels]
+constexpr uint32_t kBOffHP = 2 * 65536;                                 // head-pre panel
+constexpr uint32_t kBOffRing = kBOffHP + kPanelBytes;                   // 147456
+constexpr uint32_t kBOffConst = kBOffRing + kBStages * kBStageBytes;    // 212992: w_rgb [3][128] fp32
 constexpr uint32_t kBOffBars = kBOffConst + 2048;
 constexpr uint32_t kBwdSmem = kBOffBars + 512 + 1024;
+static_assert(kBwdSmem <= 232448, "shared memory budget");
 
 struct BwdParams {
     const uint8_t* packed;
@@ -45,7 +53,17 @@ struct BwdParams {
 };
 
 struct BwdBars {
-    uint64_t w_full[kStages], w_empty[kStages], acc_full[2], panel_ready[4], panel_stored[4], pro_ready, pro_free, pro_stored;
+    uint64_t w_full[kBStages];     // leader: own bytes + the peer's relay (2 arrivals); peer: own bytes (1)
+    uint64_t w_empty[kBStages];    // MMA commit, multicast
+    uint64_t acc_full[2];          // per slot: MMA commit, multicast
+    uint64_t tile_ready[2];        // leader only: 2 x 8 epilogue warps
+    uint64_t stash_ready[2];       // local: 8 epilogue warps (one phase per job)
+    uint64_t stash_done[2];        // local: stash writer (one phase per stash event: dY_v of a tile, then every job)
+    uint64_t pro_ready[2];         // leader only: 2 x 4 prologue warps, dY_v of the slot's tile is in panels 0-1
+    uint64_t pro_local[2];         // local: 4 prologue warps -> stash writer
+    uint64_t slot_free[2];         // local: stash writer -> prologue, one phase per tile: the tile's last gradient panel has been copied out
+    uint64_t hp_ready;             // leader only: 2 x 4 prologue warps, one phase per use of the head-pre panel
+    uint64_t hp_free;              // MMA commit, multicast
     uint32_t tmem_base;
 };
 
@@ -55,220 +73,303 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     BwdBars* bars = (BwdBars*)(smem + kBOffBars);
     float* s_wrgb = (float*)(smem + kBOffConst);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    // roles by warp id (highest id = highest issue priority): 0-3 prologue | 4 stash writer | 5 weight loader | 6-13 epilogue | 14 MMA issuer (single thread, must never starve)
+    const uint32_t rank = cluster_rank();
     constexpr int kWarpStash = 4, kWarpLoader = 5, kWarpEpi0 = 6, kWarpMma = 14;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], kCluster); }
-        for (int i = 0; i < 2; ++i) mbar_init(&bars->acc_full[i], 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&bars->panel_ready[i], kBwdEpiWarps * 32); mbar_init(&bars->panel_stored[i], 1); }
-        mbar_init(&bars->pro_ready, 128);
-        mbar_init(&bars->pro_free, 1);
-        mbar_init(&bars->pro_stored, 1);
+        for (int i = 0; i < kBStages; ++i) { mbar_init(&bars->w_full[i], rank == 0 ? 2 : 1); mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->acc_full[i], 1);
+            mbar_init(&bars->tile_ready[i], 2 * kBwdEpiWarps);
+            mbar_init(&bars->stash_ready[i], kBwdEpiWarps);
+            mbar_init(&bars->stash_done[i], 1);
+            mbar_init(&bars->pro_ready[i], 2 * 4);
+            mbar_init(&bars->pro_local[i], 4);
+            mbar_init(&bars->slot_free[i], 1);
+        }
+        mbar_init(&bars->hp_ready, 2 * 4);
+        mbar_init(&bars->hp_free, 1);
         mbar_fence_init();
     }
-    if (warp == kWarpMma) tmem_alloc<512>(&bars->tmem_base);
+    if (warp == kWarpMma) tmem_alloc2<512>(&bars->tmem_base);
     if (p.w_rgb) for (int i = threadIdx.x; i < 3 * 128; i += kBwdThreads) s_wrgb[i] = p.w_rgb[i];
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;   // uniform per cluster; tiles >= n_tiles are dummies
-    constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1);
+    const int n_pairs = (int)gridDim.x / 2, pi = (int)blockIdx.x / 2;
+    const int n_super = (p.n_tiles + 1) / 2;
+    const int my_super = (n_super + n_pairs - 1) / n_pairs;     // uniform over pairs; tiles >= n_tiles are dummies
+    auto tile_of = [&](int i) { return 2 * (pi + i * n_pairs) + (int)rank; };
+    const int pv = p.has_view ? 1 : 0;
+    const int n_events = p.n_steps + pv;                        // stash events per tile and slot
 
     if (warp == kWarpLoader) {
-        // ======================= weight loader (1/kCluster of every chunk, multicast to the cluster) =======================
+        // ======================= weight loader: this CTA's N/2 rows of every chunk, once per step when both tiles can share =======================
         if (lane == 0) {
-            const uint32_t rank = cluster_rank();
             uint32_t cnt = 0;
-            for (int ti = 0; ti < my_tiles; ++ti)
+            for (int g = 0; 2 * g < my_super; ++g) {
+                const bool two = 2 * g + 1 < my_super;
                 for (int s = 0; s < p.n_steps; ++s) {
                     const TcStep& st = p.steps[s];
-                    const uint32_t bytes = (uint32_t)st.n_rows * kRowBytes;
-                    const uint32_t slice = bytes / kCluster;
-                    for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
-                        const uint32_t stage = cnt % kStages, round = cnt / kStages;
-                        if (round > 0) mbar_wait_sleep(&bars->w_empty[stage], (round - 1) & 1, 32);
-                        mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
-                        bulk_g2s_multicast(smem + kBOffRing + stage * kStageBytes + rank * slice,
-                                           p.packed + st.w_off + (uint32_t)c * bytes + rank * slice, slice,
-                                           &bars->w_full[stage], kClusterMask);
-                    }
-                }
-        }
-    } else if (warp == kWarpMma) {
-        // ======================= MMA issuer =======================
-        if (lane == 0) {
-            uint32_t cnt = 0, it = 0;
-            const uint32_t idesc = umma_idesc(128, 256, false, false);
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                bool pro_waited = false;
-                for (int s = 0; s < p.n_steps; ++s, ++it) {
-                    const TcStep& st = p.steps[s];
-                    const uint32_t d_tmem = tmem + (it & 1) * 256;
-                    uint32_t waited = 0;
-                    for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
-                        const int pn = st.panel[c];
-                        const uint32_t stage = cnt % kStages;
-                        mbar_wait(&bars->w_full[stage], (cnt / kStages) & 1);     // usually long landed: checked off the critical path
-                        uint32_t a_addr;
-                        if (pn >= kPanelP) {
-                            if (!pro_waited) { mbar_wait(&bars->pro_ready, ti & 1); pro_waited = true; }
-                            a_addr = smem_u32(smem + kBOffP + (pn - kPanelP) * kPanelBytes);
-                        } else {
-                            if (it > 0 && !(waited & (1u << pn))) { mbar_wait(&bars->panel_ready[pn], (it - 1) & 1); waited |= 1u << pn; }
-                            a_addr = smem_u32(smem + kBOffH + pn * kPanelBytes);
+                    const uint32_t bytes = (uint32_t)st.n_rows * kRowBytes, half = bytes / 2;
+                    const int reps = (two && st.n_chunks > kBStages) ? 2 : 1;
+                    for (int r = 0; r < reps; ++r)
+                        for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
+                            const uint32_t stage = cnt % kBStages, round = cnt / kBStages;
+                            if (round > 0) mbar_wait(&bars->w_empty[stage], (round - 1) & 1);
+                            mbar_arrive_expect_tx(&bars->w_full[stage], half);
+                            bulk_g2s(smem + kBOffRing + stage * kBStageBytes, p.packed + st.w_off + (uint32_t)c * bytes + rank * half, half,
+                                     &bars->w_full[stage]);
                         }
-                        tc_fence_after();
-                        const uint32_t b_addr = smem_u32(smem + kBOffRing + stage * kStageBytes);
-                        for (int k = 0; k < st.ksteps[c]; ++k)
-                            umma(d_tmem, umma_desc_kmajor(a_addr, k), umma_desc_kmajor(b_addr, k), idesc, (c | k) != 0);
-                        umma_commit_multicast(&bars->w_empty[stage], kClusterMask);
-                    }
-                    umma_commit(&bars->acc_full[it & 1]);
-                    if (st.last_e_use) umma_commit(&bars->pro_free);
-                    if (it > 0 && !(waited & 8u)) mbar_wait(&bars->panel_ready[3], (it - 1) & 1);
                 }
             }
         }
-    } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 8) {
+    } else if (warp == kWarpMma && rank != 0) {
+        // ======================= peer: relay "my half of the chunk has landed" to the leader =======================
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int g = 0; 2 * g < my_super; ++g) {
+                const bool two = 2 * g + 1 < my_super;
+                for (int s = 0; s < p.n_steps; ++s) {
+                    const TcStep& st = p.steps[s];
+                    const int n = ((two && st.n_chunks > kBStages) ? 2 : 1) * st.n_chunks;
+                    for (int c = 0; c < n; ++c, ++cnt) {
+                        const uint32_t stage = cnt % kBStages;
+                        mbar_wait(&bars->w_full[stage], (cnt / kBStages) & 1);
+                        mbar_arrive_cluster(cluster_addr(&bars->w_full[stage], 0));
+                    }
+                }
+            }
+        }
+    } else if (warp == kWarpMma) {
+        // ======================= MMA issuer (leader CTA; converged warp, one elected lane) =======================
+        uint32_t stage = 0, wpar = 0, hu = 0;
+        const uint32_t ring_lo = desc_lo_kmajor(smem_u32(smem + kBOffRing));
+        const uint32_t h_lo = desc_lo_kmajor(smem_u32(smem + kBOffH)), hp_lo = desc_lo_kmajor(smem_u32(smem + kBOffHP));
+        const uint32_t idesc = umma_idesc(256, 256, false, false);
+        bool w_ok = false, t_ok = false;
+        auto issue_job = [&](const int x, const int g, const int s, const bool release, const bool landed) {
+            const TcStep& st = p.steps[s];
+            const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+            const uint32_t d_tmem = tmem + x * 256;
+            if (jx > 0 && !t_ok) mbar_wait(&bars->tile_ready[x], (jx - 1) & 1);
+            if (s == 0 && pv) mbar_wait(&bars->pro_ready[x], g & 1);
+            const int nc = st.n_chunks;
+            for (int c = 0; c < nc; ++c) {
+                const int pn = st.panel[c], nk = st.ksteps[c];
+                const bool is_hp = pn == kPanelP + 2;
+                if (!landed && !w_ok) mbar_wait(&bars->w_full[stage], wpar);
+                if (is_hp) mbar_wait(&bars->hp_ready, hu & 1);
+                tc_fence_after();
+                const uint32_t a_lo = is_hp ? hp_lo : h_lo + x * (65536 >> 4) + (pn >= kPanelP ? pn - kPanelP : pn) * (kPanelBytes >> 4);
+                const uint32_t b_lo = ring_lo + stage * (kBStageBytes >> 4);
+                uint64_t* done = &bars->w_empty[stage];
+                if (elect_one()) {
+                    umma2_lo(d_tmem, a_lo, b_lo, idesc, c != 0);
+                    if (nk == 4) {
+                        umma2_lo(d_tmem, a_lo + 2, b_lo + 2, idesc, 1);
+                        umma2_lo(d_tmem, a_lo + 4, b_lo + 4, idesc, 1);
+                        umma2_lo(d_tmem, a_lo + 6, b_lo + 6, idesc, 1);
+                    } else {
+                        for (int k = 1; k < nk; ++k) umma2_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, 1);
+                    }
+                    if (release) umma_commit2(done, 3);
+                    if (is_hp) umma_commit2(&bars->hp_free, 3);
+                }
+                __syncwarp();
+                if (is_hp) ++hu;
+                if (++stage == kBStages) { stage = 0; wpar ^= 1; }
+                if (!landed) w_ok = mbar_test_wait(&bars->w_full[stage], wpar);
+            }
+            if (elect_one()) umma_commit2(&bars->acc_full[x], 3);
+            __syncwarp();
+        };
+        for (int g = 0; 2 * g < my_super; ++g) {
+            const bool two = 2 * g + 1 < my_super;
+            for (int s = 0; s < p.n_steps; ++s) {
+                const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+                const bool shared = two && p.steps[s].n_chunks <= kBStages;
+                const uint32_t stage0 = stage, wpar0 = wpar;
+                issue_job(0, g, s, !shared, false);
+                if (two) {
+                    t_ok = jx > 0 && mbar_test_wait(&bars->tile_ready[1], (jx - 1) & 1);
+                    if (shared) { stage = stage0; wpar = wpar0; }
+                    issue_job(1, g, s, true, shared);
+                    if (shared) w_ok = mbar_test_wait(&bars->w_full[stage], wpar);
+                }
+                t_ok = mbar_test_wait(&bars->tile_ready[0], jx & 1);
+            }
+        }
+    } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + kBwdEpiWarps) {
         // ======================= epilogue: ReLU mask, bf16, next A operand =======================
-        // warp (q, hf): rows 32q..32q+31, columns [32 hf, 32 hf + 32) of every panel
-        const int q = warp & 3, hf = (warp - kWarpEpi0) >> 2;
+        // warp (q, w2): rows 32q..32q+31, whole panels w2 and w2 + 2.  The sign masks come from the stashed forward
+        // activations (64 bytes per 32-column unit and row, two full sectors); they are fetched two units ahead.
+        const int q = warp & 3, w2 = (warp - kWarpEpi0) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t it = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            const int tile = blockIdx.x + ti * gridDim.x;
-            const uint8_t* act_tile = p.act + (size_t)tile * p.tile_stash_bytes;
-            for (int s = 0; s < p.n_steps; ++s, ++it) {
-                const TcStep& st = p.steps[s];
-                const bool masked = st.kind == BWD_MASK && tile < p.n_tiles;   // dummy tiles carry zero gradients
-                const uint8_t* mrow = act_tile + (size_t)st.mask_slot * 65536;
-                bool acc_ready = false;
-                for (int j = 0; j < 4; ++j) {
-                    uint4 mk[4];
-                    if (masked) {
+        const uint32_t ready0 = cluster_addr(&bars->tile_ready[0], 0), ready1 = cluster_addr(&bars->tile_ready[1], 0);
+        SNERF_FOR_EACH_JOB(my_super, p.n_steps) {
+            const TcStep& st = p.steps[s];
+            const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+            const uint32_t ev = (uint32_t)(g * n_events + pv + s);          // this job's stash event within the slot
+            const int tile = tile_of(2 * g + x);
+            const bool masked = st.kind == BWD_MASK && tile < p.n_tiles;    // dummy tiles carry zero gradients
+            const uint8_t* mrow = p.act + (size_t)tile * p.tile_stash_bytes + (size_t)st.mask_slot * 65536;
+            uint4 mk[2][4];
+            auto fetch = [&](const int u, uint4 (&dst)[4]) {
+                const int j = w2 + 2 * (u >> 1), h = u & 1;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            mk[c] = __ldg(reinterpret_cast<const uint4*>(mrow + j * kPanelBytes + swz_offset(row, hf * 4 + c)));
+                for (int c = 0; c < 4; ++c)
+                    dst[c] = masked ? __ldg(reinterpret_cast<const uint4*>(mrow + j * kPanelBytes + swz_offset(row, h * 4 + c)))
+                                    : make_uint4(0u, 0u, 0u, 0u);
+            };
+            fetch(0, mk[0]);
+            fetch(1, mk[1]);
+            mbar_wait(&bars->acc_full[x], jx & 1);
+            tc_fence_after();
+            const uint32_t acc_addr = lane_addr + x * 256;
+            uint8_t* hbase = smem + kBOffH + x * 65536;
+            uint32_t rr[2][32];
+            tmem_ld32_issue(acc_addr + w2 * 64, rr[0]);
+            if (ev > 0) mbar_wait(&bars->stash_done[x], (ev - 1) & 1);     // the slot's panels have been copied out
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = w2 + 2 * (u >> 1), h = u & 1;
+                tmem_ld_wait(rr[u & 1]);
+                if (u + 1 < 4) tmem_ld32_issue(acc_addr + (w2 + 2 * ((u + 1) >> 1)) * 64 + ((u + 1) & 1) * 32, rr[(u + 1) & 1]);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(__uint_as_float(rr[u & 1][2 * i]), __uint_as_float(rr[u & 1][2 * i + 1]));
+                if (st.kind == BWD_MASK) {
+                    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t w[4] = {mk[u & 1][c].x, mk[u & 1][c].y, mk[u & 1][c].z, mk[u & 1][c].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)     // dY * [h > 0] on a bf16 pair: all-ones / zero per half
+                            pk[4 * c + e] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w[e]), zero);
                     }
-                    if (!acc_ready) {
-                        mbar_wait(&bars->acc_full[it & 1], (it >> 1) & 1);
-                        tc_fence_after();
-                        acc_ready = true;
-                    }
-                    float v[32];
-                    tmem_ld32(lane_addr + (it & 1) * 256 + j * 64 + hf * 32, v);
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-                    if (masked) {
-                        const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const uint32_t w[4] = {mk[c].x, mk[c].y, mk[c].z, mk[c].w};
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                // dY * [h > 0] on a bf16 pair: __hgt2 yields 1.0 / 0.0 per half
-                                const __nv_bfloat162 ind = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&w[h]), zero);
-                                const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&pk[4 * c + h]), ind);
-                                pk[4 * c + h] = *reinterpret_cast<const uint32_t*>(&r);
-                            }
-                        }
-                    }
-                    if (it > 0) mbar_wait(&bars->panel_stored[j], (it - 1) & 1);
-                    uint8_t* dst = smem + kBOffH + j * kPanelBytes;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        *reinterpret_cast<uint4*>(dst + swz_offset(row, hf * 4 + c)) =
-                            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                    fence_async_smem();
-                    tc_fence_before();
-                    mbar_arrive(&bars->panel_ready[j]);
                 }
+                if (u + 2 < 4) fetch(u + 2, mk[u & 1]);
+                uint8_t* dst = hbase + j * kPanelBytes;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(dst + swz_offset(row, h * 4 + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bars->stash_ready[x]);
+                mbar_arrive_cluster(x ? ready1 : ready0);
             }
         }
     } else if (warp < 4) {
-        // ======================= prologue: head gradients of the next tile =======================
+        // ======================= prologue: head gradients =======================
+        // d rgb_pre = d rgb * rgb (1-rgb), d sigma_pre = d sigma * [sigma>0], dY_v = (d rgb_pre W_rgb) * [hv>0]  (CUDA cores, fp32)
         const int row = warp * 32 + lane;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            const int tile = blockIdx.x + ti * gridDim.x;
-            const long long pt = (long long)tile * kTileRows + row;
-            float ds = 0.f, g[3] = {0.f, 0.f, 0.f};
-            if (pt < p.n_points) {
-                ds = p.sigma[pt] > 0.f ? p.d_sigma[pt] : 0.f;                          // relu'(sigma_pre + noise)
+        const uint32_t pro0 = cluster_addr(&bars->pro_ready[0], 0), pro1 = cluster_addr(&bars->pro_ready[1], 0);
+        const uint32_t hp_addr = cluster_addr(&bars->hp_ready, 0);
+        uint32_t hu = 0;
+        for (int g = 0; 2 * g < my_super; ++g) {
+            const bool two = 2 * g + 1 < my_super;
+            uint4 hp[2];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float r = p.rgb[pt * 3 + c];
-                    g[c] = p.d_rgb[pt * 3 + c] * r * (1.f - r);                        // sigmoid'
-                }
-            }
-            uint4 mk[16];
-            if (p.has_view) {
-                const uint8_t* hv = p.act + (size_t)tile * p.tile_stash_bytes + (size_t)9 * 65536;
+            for (int x = 0; x < 2; ++x) {
+                hp[x] = make_uint4(0u, 0u, 0u, 0u);
+                if (x == 1 && !two) continue;
+                const int tile = tile_of(2 * g + x);
+                const long long pt = (long long)tile * kTileRows + row;
+                float ds = 0.f, gr[3] = {0.f, 0.f, 0.f};
+                if (pt < p.n_points) {
+                    ds = p.sigma[pt] > 0.f ? p.d_sigma[pt] : 0.f;                          // relu'(sigma_pre + noise)
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    mk[i] = tile < p.n_tiles ? __ldg(reinterpret_cast<const uint4*>(hv + (i >> 3) * kPanelBytes + swz_offset(row, i & 7)))
-                                             : make_uint4(0u, 0u, 0u, 0u);
-            }
-            if (ti > 0) {
-                mbar_wait_sleep(&bars->pro_free, (ti - 1) & 1, 256);
-                mbar_wait_sleep(&bars->pro_stored, (ti - 1) & 1, 256);
-            }
-            uint8_t* pb = smem + kBOffP;
-            if (p.has_view) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {   // i = panel * 8 + chunk; columns 8i .. 8i+7 of hv
-                    const uint32_t w[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
-                    float dv[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int col = 8 * i + e;
-                        const float d = g[0] * s_wrgb[col] + g[1] * s_wrgb[128 + col] + g[2] * s_wrgb[256 + col];
-                        const uint32_t bits = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFFu);
-                        dv[e] = bits != 0u ? d : 0.f;
+                    for (int c = 0; c < 3; ++c) {
+                        const float r = p.rgb[pt * 3 + c];
+                        gr[c] = p.d_rgb[pt * 3 + c] * r * (1.f - r);                       // sigmoid'
                     }
-                    const uint4 u = make_uint4(pack_bf16(dv[0], dv[1]), pack_bf16(dv[2], dv[3]), pack_bf16(dv[4], dv[5]),
-                                               pack_bf16(dv[6], dv[7]));
-                    *reinterpret_cast<uint4*>(pb + (i >> 3) * kPanelBytes + swz_offset(row, i & 7)) = u;
+                }
+                // head-pre row: column 0 = d sigma_pre, columns 1..3 = d rgb_pre when the rgb comes from the same head
+                hp[x] = p.has_view ? make_uint4(pack_bf16(ds, 0.f), 0u, 0u, 0u) : make_uint4(pack_bf16(ds, gr[0]), pack_bf16(gr[1], gr[2]), 0u, 0u);
+                if (p.has_view) {
+                    uint4 mk[16];
+                    const uint8_t* hv = p.act + (size_t)tile * p.tile_stash_bytes + (size_t)9 * 65536;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        mk[i] = tile < p.n_tiles ? __ldg(reinterpret_cast<const uint4*>(hv + (i >> 3) * kPanelBytes + swz_offset(row, i & 7)))
+                                                 : make_uint4(0u, 0u, 0u, 0u);
+                    // panels 0-1 of the slot are free once the previous tile's last gradient panel has been copied out.  (A wait on
+                    // stash_done would alias: this warp runs many phases ahead of that barrier; slot_free has one phase per tile.)
+                    if (g > 0) mbar_wait(&bars->slot_free[x], (g - 1) & 1);
+                    uint8_t* pb = smem + kBOffH + x * 65536;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {   // i = panel * 8 + chunk; columns 8i .. 8i+7 of hv
+                        const uint32_t w[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+                        float dv[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int col = 8 * i + e;
+                            const float d = gr[0] * s_wrgb[col] + gr[1] * s_wrgb[128 + col] + gr[2] * s_wrgb[256 + col];
+                            const uint32_t bits = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFFu);
+                            dv[e] = bits != 0u ? d : 0.f;
+                        }
+                        *reinterpret_cast<uint4*>(pb + (i >> 3) * kPanelBytes + swz_offset(row, i & 7)) =
+                            make_uint4(pack_bf16(dv[0], dv[1]), pack_bf16(dv[2], dv[3]), pack_bf16(dv[4], dv[5]), pack_bf16(dv[6], dv[7]));
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&bars->pro_local[x]);
+                        mbar_arrive_cluster(x ? pro1 : pro0);
+                    }
                 }
             }
-            // head-pre panel: column 0 = d sigma_pre, columns 1..3 = d rgb_pre when the rgb comes from the same head
-            const uint4 h0 = p.has_view ? make_uint4(pack_bf16(ds, 0.f), 0u, 0u, 0u)
-                                        : make_uint4(pack_bf16(ds, g[0]), pack_bf16(g[1], g[2]), 0u, 0u);
-            *reinterpret_cast<uint4*>(pb + 2 * kPanelBytes + swz_offset(row, 0)) = h0;
-            *reinterpret_cast<uint4*>(pb + 2 * kPanelBytes + swz_offset(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
-            fence_async_smem();
-            mbar_arrive(&bars->pro_ready);
+            // the head-pre panel, rewritten before each use in the issuer's order (tile of slot 0, then slot 1)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                if (x == 1 && !two) continue;
+                if (hu > 0) mbar_wait(&bars->hp_free, (hu - 1) & 1);
+                uint8_t* pb = smem + kBOffHP;
+                *reinterpret_cast<uint4*>(pb + swz_offset(row, 0)) = hp[x];
+                *reinterpret_cast<uint4*>(pb + swz_offset(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(hp_addr);
+                ++hu;
+            }
         }
     } else if (warp == kWarpStash) {
-        // ======================= stash writer =======================
+        // ======================= stash writer: every gradient panel -> HBM for the wgrad kernel =======================
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int tile = blockIdx.x + ti * gridDim.x;
-                uint8_t* base = p.dy + (size_t)tile * p.tile_stash_bytes;
-                mbar_wait_sleep(&bars->pro_ready, ti & 1, 64);
-                if (p.has_view && tile < p.n_tiles) {
-                    bulk_s2g(base + (size_t)9 * 65536, smem + kBOffP, 2 * kPanelBytes);
-                    bulk_commit();
-                    bulk_wait_read<0>();
-                }
-                mbar_arrive(&bars->pro_stored);
-                for (int s = 0; s < p.n_steps; ++s, ++it) {
-                    const TcStep& st = p.steps[s];
-                    for (int j = 0; j < 4; ++j) {
-                        mbar_wait_sleep(&bars->panel_ready[j], it & 1, 64);
+            for (int g = 0; 2 * g < my_super; ++g) {
+                const bool two = 2 * g + 1 < my_super;
+                if (pv) {
+                    for (int x = 0; x < (two ? 2 : 1); ++x) {
+                        const int tile = tile_of(2 * g + x);
+                        mbar_wait(&bars->pro_local[x], g & 1);
                         if (tile < p.n_tiles) {
-                            bulk_s2g(base + (size_t)st.slot * 65536 + j * kPanelBytes, smem + kBOffH + j * kPanelBytes, kPanelBytes);
+                            bulk_s2g(p.dy + (size_t)tile * p.tile_stash_bytes + (size_t)9 * 65536, smem + kBOffH + x * 65536, 2 * kPanelBytes);
                             bulk_commit();
+                            bulk_wait_read<0>();
                         }
+                        mbar_arrive(&bars->stash_done[x]);
                     }
-                    bulk_wait_read<0>();
-                    for (int j = 0; j < 4; ++j) mbar_arrive(&bars->panel_stored[j]);
                 }
+                for (int s = 0; s < p.n_steps; ++s)
+                    for (int x = 0; x < (two ? 2 : 1); ++x) {
+                        const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+                        const int tile = tile_of(2 * g + x);
+                        mbar_wait(&bars->stash_ready[x], jx & 1);
+                        if (tile < p.n_tiles) {
+                            bulk_s2g(p.dy + (size_t)tile * p.tile_stash_bytes + (size_t)p.steps[s].slot * 65536, smem + kBOffH + x * 65536, 4 * kPanelBytes);
+                            bulk_commit();
+                            bulk_wait_read<0>();
+                        }
+                        mbar_arrive(&bars->stash_done[x]);
+                        if (s == p.n_steps - 1) mbar_arrive(&bars->slot_free[x]);
+                    }
             }
             bulk_wait_all<0>();
         }
@@ -277,7 +378,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == kWarpMma) tmem_dealloc<512>(tmem);
+    if (warp == kWarpMma) tmem_dealloc2<512>(tmem);
 }
 
 // =================================================================================================
@@ -689,7 +790,7 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         SNERF_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
         attr = true;
     }
-    SNERF_CUDA_OK(launch_clustered(tc_dgrad_kernel, chain_grid(w.n_tiles), kBwdThreads, kBwdSmem, st, bp));
+    SNERF_CUDA_OK(launch_clustered(tc_dgrad_kernel, pair_grid(w.n_tiles), kBwdThreads, kBwdSmem, st, bp));
 
     // ---- (2) wgrad ----
     WgParams wp{};

@@ -225,6 +225,14 @@ static inline int chain_grid(int n_tiles) {
     return g < kCluster ? kCluster : g;
 }
 
+// Every role walks the same job list: tiles 2g and 2g+1 of this pair occupy slots 0 and 1 and their steps interleave.
+// jx = g * n_steps + s is the job's index within its slot (barrier phases count per slot).
+#define SNERF_FOR_EACH_JOB(my_super, n_steps)                   \
+    for (int g = 0; 2 * g < (my_super); ++g)                    \
+        for (int s = 0; s < (n_steps); ++s)                     \
+            for (int x = 0; x < 2; ++x)                         \
+                if (2 * g + x < (my_super))
+
 // pair kernels: one CTA pair per two SMs; a pair works on 256-point super tiles
 static inline int pair_grid(int n_tiles) {
     const int n_super = (n_tiles + 1) / 2, pairs = num_sms() / 2;

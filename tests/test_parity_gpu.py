@@ -250,6 +250,28 @@ def test_mlp_backward_vs_autograd(precision):
             assert rel <= (2e-4 if precision == 'fp32' else 5e-2), (slot, name, rel)
 
 
+@pytest.mark.parametrize('n', [1, 127, 129, 257, 5 * 128, 128 * (2 * 148 + 3) + 17])
+def test_tensor_path_tile_edges(n):
+    """The tensor path works on 256-point super tiles shared by a CTA pair, two in flight per pair: odd tile counts,
+    a single tile, a ragged last tile and more super tiles than pairs must all give the precise path's values."""
+    if not __import__('simplenerf_b200._lib', fromlist=['x']).load().snerf_has_tensor_path():
+        pytest.skip('tensor path not built')
+    configs = synthetic.make_configs('simplenerf')
+    gen = torch.Generator().manual_seed(n)
+    pts = (torch.rand((n, 3), generator=gen) - .5) * 2.4
+    vd = torch.nn.functional.normalize(torch.randn((n, 3), generator=gen), dim=-1)
+    noise = torch.randn((n, 1), generator=gen)
+    for slot, mlp_cfg in orc.model_slots(configs).items():
+        if slot == 'fine_model':
+            continue     # same architecture as the coarse model
+        spec, state, block = _mlp_setup(slot, mlp_cfg, 'bf16')
+        want_s, want_r, *_ = _run_mlp(block, 'fp32', pts, vd, noise)
+        for save in (False, True):
+            got_s, got_r, *_ = _run_mlp(block, 'bf16', pts, vd, noise, save=save)
+            torch.testing.assert_close(got_s, want_s, rtol=3e-2, atol=1e-2, msg=lambda m: f'{slot} n={n} save={save} sigma {m}')
+            torch.testing.assert_close(got_r, want_r, rtol=3e-2, atol=1e-2, msg=lambda m: f'{slot} n={n} save={save} rgb {m}')
+
+
 # ------------------------------------------------------------------------------------------------
 # a1/a2/a13 the whole drop-in against outputs of the unmodified reference
 # ------------------------------------------------------------------------------------------------
