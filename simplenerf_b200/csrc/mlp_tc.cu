@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restri
 // epilogue of one tile (TMEM -> bias/ReLU -> bf16 -> smem) runs under the MMAs of the other.
 // Measured (tools/pair_probe.py, tools/mma_rate.py): 129 cycles per M256 N256 K16 pair MMA against 165 cycles per
 // M128 N256 K16 single-CTA MMA, i.e. 2.5x the issue rate per row, and half the weight bytes per SM.
-constexpr int kFwdThreads = 480;                                       // 15 warps, see the role table
-constexpr int kEpiWarps = 8;                                            // 2 per SM sub-partition
+constexpr int kFwdThreads = 736;                                       // 23 warps, see the role table
+constexpr int kEpiWarps = 16;                                           // 4 per SM sub-partition, one 64-column panel each
 constexpr int kPStages = 4;                                             // weight ring: this CTA's half chunks; 4 = one whole layer
 constexpr uint32_t kPStageBytes = 16384;
 constexpr uint32_t kOffH = 0;                                           // [2 slots][4 panels]
@@ -109,10 +109,11 @@ constexpr uint32_t kConstBias32 = 9 * 256 * 2;                          // [256]
 constexpr uint32_t kConstHeadW = kConstBias32 + 256 * 4;                // [4][256] fp32
 constexpr uint32_t kConstRgbW = kConstHeadW + 4 * 256 * 4;              // [3][128] fp32
 constexpr uint32_t kConstMisc = kConstRgbW + 3 * 128 * 4;               // head bias[4], rgb bias[4]
-constexpr uint32_t kConstPart = kConstMisc + 64;                        // [2 slots][128][4] fp32 partial head sums of the odd panels
-constexpr uint32_t kOffBars = kOffConst + 16384;
+constexpr uint32_t kConstPart = kConstMisc + 64;                        // [3][128][4] fp32 partial head sums of panels 1-3
+constexpr uint32_t kConstBytes = 17920;
+constexpr uint32_t kOffBars = kOffConst + kConstBytes;
 constexpr uint32_t kFwdSmem = kOffBars + 512 + 1024;                    // + alignment slack
-static_assert(kConstPart + 2 * 128 * 4 * 4 <= 16384, "constant area overflow");
+static_assert(kConstPart + 3 * 128 * 4 * 4 <= kConstBytes, "constant area overflow");
 static_assert(kFwdSmem <= 232448, "shared memory budget");
 
 struct FwdParams {
@@ -170,8 +171,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
     const uint32_t rank = cluster_rank();
     // roles by warp id -- the sub-partition arbiter issues the highest eligible warp id first, so the latency-critical
     // epilogue warps sit on top and the helpers below them:
-    //   0-3 encoders | 4 stash writer | 5 weight loader | 6-13 epilogue | 14 MMA issuer (leader) / weight relay (peer)
-    constexpr int kWarpStash = 4, kWarpLoader = 5, kWarpEpi0 = 6, kWarpMma = 14;
+    //   0-3 encoders | 4 stash writer | 5 weight loader | 6-21 epilogue | 22 MMA issuer (leader) / weight relay (peer)
+    constexpr int kWarpStash = 4, kWarpLoader = 5, kWarpEpi0 = 6, kWarpMma = 22;
 
     // ---- setup ----
     if (threadIdx.x == 0) {
@@ -323,146 +324,161 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
         }
     } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + kEpiWarps) {
         // ======================= epilogue =======================
-        // warp (q, w2): TMEM lanes / tile rows 32q..32q+31; it owns the whole 64-column panels w2 and w2 + 2 of every step.
-        // TMEM -> registers is software pipelined in 32-column units: the load of unit u+1 is in flight while unit u is
-        // converted and stored.  One elected lane per warp signals the stash writer and the leader's MMA thread.
-        const int q = warp & 3, w2 = (warp - kWarpEpi0) >> 2;
+        // warp (q, j): TMEM lanes / tile rows 32q..32q+31, the 64-column panel j of every step.  Four warps per SM
+        // sub-partition hide each other's TMEM / shared-memory latencies; each works in 16-column units with the next
+        // unit's TMEM load in flight (small register footprint: 23 warps fit the register file).  The epilogue is the
+        // pacing stage of the chain, so the hidden-layer path is kept to the bare instruction count: one F2FP + one
+        // HFMA2(.RELU) per value pair, store offsets precomputed, the step kind dispatched once per job.
+        const int q = warp & 3, j = (warp - kWarpEpi0) >> 2;
         const int row = q * 32 + lane;
-        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + j * 64;
         const uint32_t ready0 = cluster_addr(&bars->tile_ready[0], 0), ready1 = cluster_addr(&bars->tile_ready[1], 0);
-        SNERF_FOR_EACH_JOB(my_super, p.n_steps) {
+        uint32_t soff[8];      // byte offset of this row's 16-byte chunk c inside a panel
+#pragma unroll
+        for (int c = 0; c < 8; ++c) soff[c] = (uint32_t)row * kRowBytes + (((uint32_t)c ^ ((uint32_t)row & 7u)) << 4);
+        auto job = [&](const int x, const int g, const int s) {
             const TcStep& st = p.steps[s];
             const int kind = st.kind;
             const uint32_t jx = (uint32_t)(g * p.n_steps + s);
-            const int tile = tile_of(2 * g + x);
-            const long long pt = (long long)tile * kTileRows + row;
-            const bool valid = pt < p.n_points;
-            const int ray = (kind == EPI_VIEW && valid) ? (int)((unsigned)pt / (unsigned)p.n_samples) : 0;   // host guarantees n_points < 2^31
             mbar_wait(&bars->acc_full[x], jx & 1);
             tc_fence_after();
             const bool tr = kTrace && p.trace && blockIdx.x == 0 && g == 1 && warp == kWarpEpi0 && lane == 0;
             if (tr) p.trace[(x * 16 + s) * 16 + 2] = clock64();
-            const int n_pan = st.n_rows / 64;
-            const int n_own = (p.debug & 2) ? 0 : (n_pan > w2 + 2 ? 2 : (n_pan > w2 ? 1 : 0));     // panels with data owned by this warp
+            const bool own = j * 64 < st.n_rows && !(p.debug & 2);        // the step has this panel
             const bool writes_h = ((kind != EPI_VIEW) || save) && !(p.debug & 1);
-            const bool has_head = kind == EPI_RELU_HEAD1 || kind == EPI_RELU_HEAD4 || kind == EPI_VIEW;
-            float head[4] = {0.f, 0.f, 0.f, 0.f};
             const uint32_t acc_addr = lane_addr + x * 256;
-            uint8_t* hbase = smem + kOffH + x * 65536;
-            uint32_t rr[2][32];
-            if (n_own > 0) tmem_ld32_issue(acc_addr + w2 * 64, rr[0]);
-            // the stash writer has finished reading the panels of the slot's previous job
-            if (save && jx > 0 && n_own > 0) mbar_wait(&bars->stash_done[x], (jx - 1) & 1);
+            uint8_t* dst = smem + kOffH + x * 65536 + j * kPanelBytes;
+            if (kind == EPI_RELU || kind == EPI_LINEAR) {
+                // ---- hidden layers and the feature layer: bias (+ReLU) in packed bf16 ----
+                if (own) {
+                    uint32_t rr[2][16];
+                    tmem_ld16_issue(acc_addr, rr[0]);
+                    const uint4* bb = reinterpret_cast<const uint4*>(s_bias16 + st.bias_row * 256 + j * 64);
+                    const bool relu = kind == EPI_RELU;
+                    if (save && jx > 0) mbar_wait(&bars->stash_done[x], (jx - 1) & 1);   // the slot's panels have been copied out
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int jj = u >> 1, h = u & 1, j = w2 + 2 * jj;
-                if (jj < n_own) {
-                    const int col0 = j * 64 + h * 32;
-                    tmem_ld_wait(rr[u & 1]);
-                    if (u + 1 < 2 * n_own) tmem_ld32_issue(acc_addr + (w2 + 2 * ((u + 1) >> 1)) * 64 + ((u + 1) & 1) * 32, rr[(u + 1) & 1]);
-                    float v[32];
+                    for (int u = 0; u < 4; ++u) {
+                        tmem_ld_wait16(rr[u & 1]);
+                        if (u + 1 < 4) tmem_ld16_issue(acc_addr + (u + 1) * 16, rr[(u + 1) & 1]);
+                        uint32_t pk[8];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[u & 1][i]);
-                    uint32_t pk[16];
-                    if (kind == EPI_RELU || kind == EPI_LINEAR) {
-                        const uint4* bb = reinterpret_cast<const uint4*>(s_bias16 + st.bias_row * 256 + col0);
-                        const bool relu = kind == EPI_RELU;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 b = bb[i];
-                            pk[4 * i + 0] = bias_act_bf16x2(v[8 * i + 0], v[8 * i + 1], b.x, relu);
-                            pk[4 * i + 1] = bias_act_bf16x2(v[8 * i + 2], v[8 * i + 3], b.y, relu);
-                            pk[4 * i + 2] = bias_act_bf16x2(v[8 * i + 4], v[8 * i + 5], b.z, relu);
-                            pk[4 * i + 3] = bias_act_bf16x2(v[8 * i + 6], v[8 * i + 7], b.w, relu);
+                        for (int i = 0; i < 2; ++i) {
+                            const uint4 b = bb[2 * u + i];
+                            pk[4 * i + 0] = bias_act_bf16x2(__uint_as_float(rr[u & 1][8 * i + 0]), __uint_as_float(rr[u & 1][8 * i + 1]), b.x, relu);
+                            pk[4 * i + 1] = bias_act_bf16x2(__uint_as_float(rr[u & 1][8 * i + 2]), __uint_as_float(rr[u & 1][8 * i + 3]), b.y, relu);
+                            pk[4 * i + 2] = bias_act_bf16x2(__uint_as_float(rr[u & 1][8 * i + 4]), __uint_as_float(rr[u & 1][8 * i + 5]), b.z, relu);
+                            pk[4 * i + 3] = bias_act_bf16x2(__uint_as_float(rr[u & 1][8 * i + 6]), __uint_as_float(rr[u & 1][8 * i + 7]), b.w, relu);
                         }
-                    } else {
-                        if (kind == EPI_VIEW) {
-                            const float4* vb = reinterpret_cast<const float4*>(p.view_bias + (size_t)ray * 128 + col0);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 b = __ldg(vb + i);
-                                v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
-                                v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
-                                v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
-                                v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
-                            }
-                        } else {
-                            const float4* bb = reinterpret_cast<const float4*>(s_bias32 + col0);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 b = bb[i];
-                                v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.f);
-                                v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
-                                v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f);
-                                v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
-                            }
+                        if (writes_h) {
+                            *reinterpret_cast<uint4*>(dst + soff[2 * u]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            *reinterpret_cast<uint4*>(dst + soff[2 * u + 1]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         }
-                        // fp32 heads on the un-rounded activations
-                        const float* wbase = kind == EPI_VIEW ? s_wrgb : s_whead;
-                        const int wld = kind == EPI_VIEW ? 128 : 256;
-                        const int nh = kind == EPI_RELU_HEAD1 ? 1 : (kind == EPI_VIEW ? 3 : 4);
+                        if (tr) p.trace[512 + (x * 16 + s) * 8 + 1 + u] = clock64();
+                    }
+                    if (writes_h) fence_async_smem();   // generic-proxy stores -> async proxy (MMA operand fetch, bulk store)
+                }
+                tc_fence_before();     // TMEM reads ordered before the next MMA into this accumulator
+                if (tr) p.trace[512 + (x * 16 + s) * 8 + 5] = clock64();
+                __syncwarp();
+                if (lane == 0) {
+                    if (save) mbar_arrive(&bars->stash_ready[x]);
+                    mbar_arrive_cluster(x ? ready1 : ready0);
+                    if (tr) p.trace[(x * 16 + s) * 16 + 3] = clock64();
+                }
+                return;
+            }
+            // ---- last trunk layer (sigma / rgb head) and the view layer (rgb head): fp32 on the un-rounded activations ----
+            const long long pt = (long long)tile_of(2 * g + x) * kTileRows + row;
+            const bool valid = pt < p.n_points;
+            float head[4] = {0.f, 0.f, 0.f, 0.f};
+            if (own) {
+                uint32_t rr[2][16];
+                tmem_ld16_issue(acc_addr, rr[0]);
+                if (save && jx > 0) mbar_wait(&bars->stash_done[x], (jx - 1) & 1);
+                const float* vbias = nullptr;
+                if (kind == EPI_VIEW) {
+                    const int ray = valid ? (int)((unsigned)pt / (unsigned)p.n_samples) : 0;   // host guarantees n_points < 2^31
+                    vbias = p.view_bias + (size_t)ray * 128 + j * 64;
+                }
+                const float* wbase = kind == EPI_VIEW ? s_wrgb : s_whead;
+                const int wld = kind == EPI_VIEW ? 128 : 256;
+                const int nh = kind == EPI_RELU_HEAD1 ? 1 : (kind == EPI_VIEW ? 3 : 4);
 #pragma unroll
-                        for (int hh = 0; hh < 4; ++hh) {
-                            if (hh < nh) {
-                                const float4* w = reinterpret_cast<const float4*>(wbase + hh * wld + col0);
-                                float a = head[hh];
+                for (int u = 0; u < 4; ++u) {
+                    const int col0 = j * 64 + u * 16;
+                    tmem_ld_wait16(rr[u & 1]);
+                    if (u + 1 < 4) tmem_ld16_issue(acc_addr + (u + 1) * 16, rr[(u + 1) & 1]);
+                    float v[16];
+                    const float4* bb = kind == EPI_VIEW ? reinterpret_cast<const float4*>(vbias + u * 16)
+                                                        : reinterpret_cast<const float4*>(s_bias32 + col0);
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 ww = w[i];
-                                    a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
-                                }
-                                head[hh] = a;
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b = kind == EPI_VIEW ? __ldg(bb + i) : bb[i];
+                        v[4 * i + 0] = fmaxf(__uint_as_float(rr[u & 1][4 * i + 0]) + b.x, 0.f);
+                        v[4 * i + 1] = fmaxf(__uint_as_float(rr[u & 1][4 * i + 1]) + b.y, 0.f);
+                        v[4 * i + 2] = fmaxf(__uint_as_float(rr[u & 1][4 * i + 2]) + b.z, 0.f);
+                        v[4 * i + 3] = fmaxf(__uint_as_float(rr[u & 1][4 * i + 3]) + b.w, 0.f);
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < 4; ++hh) {
+                        if (hh < nh) {
+                            const float4* w = reinterpret_cast<const float4*>(wbase + hh * wld + col0);
+                            float a = head[hh];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 ww = w[i];
+                                a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
                             }
+                            head[hh] = a;
                         }
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
                     }
                     if (writes_h) {
-                        uint8_t* dst = hbase + j * kPanelBytes;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<uint4*>(dst + swz_offset(row, h * 4 + c)) =
-                                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(dst + soff[2 * u]) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                        *reinterpret_cast<uint4*>(dst + soff[2 * u + 1]) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
                     }
-                    if (tr) p.trace[512 + (x * 16 + s) * 8 + 1 + u] = clock64();
                 }
+                if (writes_h) fence_async_smem();
             }
-            // hand-over: generic-proxy stores -> async proxy (MMA operand fetch, bulk store), TMEM reads ordered before the
-            // next MMA into this accumulator; then one arrival per warp
-            if (n_own > 0 && writes_h) fence_async_smem();
             tc_fence_before();
-            if (tr) p.trace[512 + (x * 16 + s) * 8 + 5] = clock64();
             __syncwarp();
             if (lane == 0) {
                 if (save) mbar_arrive(&bars->stash_ready[x]);
                 mbar_arrive_cluster(x ? ready1 : ready0);
                 if (tr) p.trace[(x * 16 + s) * 16 + 3] = clock64();
             }
-            if (has_head) {
-                // combine the two panel sets: the odd-panel warp hands its partial sums to the even-panel warp
-                float* part = s_part + x * 512;
-                if (w2 == 1) {
+            // combine the panels: warps 1-3 of the row group hand their partial sums to warp 0
+            if (j > 0) {
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) part[row * 4 + h] = head[h];
+                for (int h = 0; h < 4; ++h) s_part[((j - 1) * 128 + row) * 4 + h] = head[h];
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+            if (j == 0 && valid) {
+                const int mb = kind == EPI_VIEW ? 4 : 0;
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj) {
+                    const float4 o = *reinterpret_cast<const float4*>(s_part + (jj * 128 + row) * 4);
+                    head[0] += o.x; head[1] += o.y; head[2] += o.z; head[3] += o.w;
                 }
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-                if (w2 == 0 && valid) {
-                    const float4 o = *reinterpret_cast<const float4*>(part + row * 4);
-                    const int mb = kind == EPI_VIEW ? 4 : 0;
-                    head[0] += o.x + s_misc[mb + 0]; head[1] += o.y + s_misc[mb + 1];
-                    head[2] += o.z + s_misc[mb + 2]; head[3] += o.w + s_misc[mb + 3];
-                    if (kind == EPI_VIEW) {
+                head[0] += s_misc[mb + 0]; head[1] += s_misc[mb + 1]; head[2] += s_misc[mb + 2]; head[3] += s_misc[mb + 3];
+                if (kind == EPI_VIEW) {
 #pragma unroll
-                        for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h]);             // :704-707
-                    } else {
-                        const float nz = p.noise ? p.noise[pt] : 0.f;
-                        p.sigma[pt] = fmaxf(head[0] + nz, 0.f);                                        // :668-672
-                        if (kind == EPI_RELU_HEAD4) {
+                    for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h]);             // :704-707
+                } else {
+                    const float nz = p.noise ? p.noise[pt] : 0.f;
+                    p.sigma[pt] = fmaxf(head[0] + nz, 0.f);                                        // :668-672
+                    if (kind == EPI_RELU_HEAD4) {
 #pragma unroll
-                            for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
-                        }
+                        for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
                     }
                 }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // the partial sums may be overwritten by the next head step
+        };
+        for (int g = 0; 2 * g < my_super; ++g) {
+            const bool two = 2 * g + 1 < my_super;
+            for (int s = 0; s < p.n_steps; ++s) {
+                job(0, g, s);
+                if (two) job(1, g, s);
             }
         }
     } else if (warp < 4) {
