@@ -863,12 +863,12 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
             const WgJob& jb = wp.jobs[j];
             // measured with tools/wgrad_balance.py (cycles of work per tile, relative): streaming dominates, the
             // recomputed encodings and the CUDA-core head matrices add their own latency
-            cost[j] = (jb.a_panels + jb.b_panels) * 12.5;
-            if (jb.kind == 0 && jb.b_panels == 0) cost[j] = 125.0;                    // dY x encoding only
-            if (jb.b_enc && jb.b_panels > 0) cost[j] += 70.0;                         // view job of the points-augmented model
-            if (jb.with_head) cost[j] += 68.0;
-            if (jb.kind == 1) cost[j] = 136.0;
-            if (jb.kind == 2) cost[j] = 109.0;
+            cost[j] = (jb.a_panels + jb.b_panels) * 12.5;                             // streaming job: 100 for 4 + 4 panels
+            if (jb.kind == 0 && jb.b_panels == 0) cost[j] = 142.0;                    // dY x encoding only (encoder-bound)
+            if (jb.kind == 0 && jb.a_panels == 2) cost[j] = jb.b_enc ? 195.0 : 128.0; // view job: recomputed view-dir (+ point) encoding
+            if (jb.with_head) cost[j] += 73.0;
+            if (jb.kind == 1) cost[j] = 149.0;
+            if (jb.kind == 2) cost[j] = 112.0;
             total += cost[j];
         }
         int n[kMaxJobs], used = 0;
