@@ -124,6 +124,7 @@ struct FwdParams {
     const float *rays_o, *rays_d, *z, *noise;
     float *sigma, *rgb;
     uint8_t* stash;                // null in eval
+    uint8_t* bits;                 // (training) ReLU sign bits of the trunk activations, kBitsTileBytes per tile
     long long* trace;              // debug: clock64 timestamps of pair 0 (tools/trace_fwd.py), normally null
     int debug;                     // debug (timing experiments, results become garbage): bit0 no panel stores, bit1 no TMEM loads / epilogue math, bit2 no weight copies
     long long n_points;
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 // ---- hidden layers and the feature layer: bias (+ReLU) in packed bf16 ----
                 if (own) {
                     uint32_t rr[2][16];
+                    uint32_t mw[2] = {0u, 0u};
                     tmem_ld16_issue(acc_addr, rr[0]);
                     const uint4* bb = reinterpret_cast<const uint4*>(s_bias16 + st.bias_row * 256 + j * 64);
                     const bool relu = kind == EPI_RELU;
@@ -373,9 +375,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                             *reinterpret_cast<uint4*>(dst + soff[2 * u]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             *reinterpret_cast<uint4*>(dst + soff[2 * u + 1]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         }
+                        if (save && relu) mw[u >> 1] |= relu_bits_unit(pk, u);
                         if (tr) p.trace[512 + (x * 16 + s) * 8 + 1 + u] = clock64();
                     }
                     if (writes_h) fence_async_smem();   // generic-proxy stores -> async proxy (MMA operand fetch, bulk store)
+                    if (save && relu) {
+                        const int tile = tile_of(2 * g + x);
+                        if (tile < p.n_tiles)
+                            *reinterpret_cast<uint2*>(p.bits + (size_t)tile * kBitsTileBytes + (size_t)st.slot * kBitsSlotBytes + row * 32 + j * 8) = make_uint2(mw[0], mw[1]);
+                    }
                 }
                 tc_fence_before();     // TMEM reads ordered before the next MMA into this accumulator
                 if (tr) p.trace[512 + (x * 16 + s) * 8 + 5] = clock64();
@@ -388,7 +396,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 return;
             }
             // ---- last trunk layer (sigma / rgb head) and the view layer (rgb head): fp32 on the un-rounded activations ----
-            const long long pt = (long long)tile_of(2 * g + x) * kTileRows + row;
+            const int tile = tile_of(2 * g + x);
+            const long long pt = (long long)tile * kTileRows + row;
             const bool valid = pt < p.n_points;
             float head[4] = {0.f, 0.f, 0.f, 0.f};
             if (own) {
@@ -403,6 +412,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 const float* wbase = kind == EPI_VIEW ? s_wrgb : s_whead;
                 const int wld = kind == EPI_VIEW ? 128 : 256;
                 const int nh = kind == EPI_RELU_HEAD1 ? 1 : (kind == EPI_VIEW ? 3 : 4);
+                uint32_t mw[2] = {0u, 0u};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int col0 = j * 64 + u * 16;
@@ -433,11 +443,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                         }
                     }
                     if (writes_h) {
-                        *reinterpret_cast<uint4*>(dst + soff[2 * u]) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                        *reinterpret_cast<uint4*>(dst + soff[2 * u + 1]) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+                        *reinterpret_cast<uint4*>(dst + soff[2 * u]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(dst + soff[2 * u + 1]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        if (save && kind != EPI_VIEW) mw[u >> 1] |= relu_bits_unit(pk, u);
                     }
                 }
                 if (writes_h) fence_async_smem();
+                if (save && kind != EPI_VIEW && tile < p.n_tiles)
+                    *reinterpret_cast<uint2*>(p.bits + (size_t)tile * kBitsTileBytes + (size_t)st.slot * kBitsSlotBytes + row * 32 + j * 8) = make_uint2(mw[0], mw[1]);
             }
             tc_fence_before();
             __syncwarp();
@@ -589,6 +605,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     p.view_bias = (const float*)(wsb + w.view_bias);
     p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.noise = noise; p.sigma = sigma; p.rgb = rgb;
     p.stash = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.act : nullptr;
+    p.bits = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.bits : nullptr;
     p.trace = g_trace; p.debug = g_fwd_debug;
     p.n_points = (long long)n_rays * n_samples;
     p.n_samples = n_samples; p.n_tiles = w.n_tiles; p.n_steps = pl.n_fwd; p.pts_degree = d.pts_degree; p.head_out = m.head_out;

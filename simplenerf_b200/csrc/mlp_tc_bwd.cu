@@ -24,13 +24,13 @@ using namespace tc;
 // =================================================================================================
 // dgrad chain kernel (CTA pairs, two tiles in flight -- the machine of the forward kernel run backwards)
 // =================================================================================================
-// roles by warp id: 0-3 prologue | 4 stash writer | 5 weight loader | 6-13 epilogue | 14 MMA issuer (leader) / relay (peer)
+// roles by warp id: 0-3 prologue | 4 stash writer | 5 weight loader | 6-21 epilogue | 22 MMA issuer (leader) / relay (peer)
 // Per pair and group: two 256-point super tiles occupy slots 0/1; the issuer alternates between them step by step and
 // both tiles share the weight chunks of a step (mlp_tc.cu describes the protocol).  The prologue writes dY_v straight
 // into panels 0-1 of the slot (they are free until the first epilogue of the tile) and the 16-column head-pre panel
 // into one small buffer that is rewritten before each use.
-constexpr int kBwdThreads = 480;
-constexpr int kBwdEpiWarps = 8;
+constexpr int kBwdThreads = 736;          // 23 warps
+constexpr int kBwdEpiWarps = 16;          // 4 per SM sub-partition, one 64-column panel each
 constexpr int kBStages = 4;
 constexpr uint32_t kBStageBytes = 16384;
 constexpr uint32_t kBOffH = 0;                                          // [2 slots][4 panels]
@@ -44,6 +44,7 @@ static_assert(kBwdSmem <= 232448, "shared memory budget");
 struct BwdParams {
     const uint8_t* packed;
     const uint8_t* act;
+    const uint8_t* bits;          // ReLU sign bits written by the forward kernel (kBitsTileBytes per tile)
     uint8_t* dy;
     const float *sigma, *rgb, *d_sigma, *d_rgb, *w_rgb;
     long long n_points;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     float* s_wrgb = (float*)(smem + kBOffConst);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t rank = cluster_rank();
-    constexpr int kWarpStash = 4, kWarpLoader = 5, kWarpEpi0 = 6, kWarpMma = 14;
+    constexpr int kWarpStash = 4, kWarpLoader = 5, kWarpEpi0 = 6, kWarpMma = 22;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kBStages; ++i) { mbar_init(&bars->w_full[i], rank == 0 ? 2 : 1); mbar_init(&bars->w_empty[i], 1); }
@@ -204,59 +205,43 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
         }
     } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + kBwdEpiWarps) {
         // ======================= epilogue: ReLU mask, bf16, next A operand =======================
-        // warp (q, w2): rows 32q..32q+31, whole panels w2 and w2 + 2.  The sign masks come from the stashed forward
-        // activations (64 bytes per 32-column unit and row, two full sectors); they are fetched two units ahead.
-        const int q = warp & 3, w2 = (warp - kWarpEpi0) >> 2;
+        // warp (q, j): rows 32q..32q+31, the 64-column panel j; 16-column TMEM units, the next one in flight.  The
+        // ReLU mask of the whole panel row is two words of sign bits written by the forward epilogue (tc_plan.cuh).
+        const int q = warp & 3, j = (warp - kWarpEpi0) >> 2;
         const int row = q * 32 + lane;
-        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + j * 64;
         const uint32_t ready0 = cluster_addr(&bars->tile_ready[0], 0), ready1 = cluster_addr(&bars->tile_ready[1], 0);
-        SNERF_FOR_EACH_JOB(my_super, p.n_steps) {
+        uint32_t soff[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) soff[c] = (uint32_t)row * kRowBytes + (((uint32_t)c ^ ((uint32_t)row & 7u)) << 4);
+        auto job = [&](const int x, const int g, const int s) {
             const TcStep& st = p.steps[s];
             const uint32_t jx = (uint32_t)(g * p.n_steps + s);
             const uint32_t ev = (uint32_t)(g * n_events + pv + s);          // this job's stash event within the slot
-            const int tile = tile_of(2 * g + x);
-            const bool masked = st.kind == BWD_MASK && tile < p.n_tiles;    // dummy tiles carry zero gradients
-            const uint8_t* mrow = p.act + (size_t)tile * p.tile_stash_bytes + (size_t)st.mask_slot * 65536;
-            uint4 mk[2][4];
-            auto fetch = [&](const int u, uint4 (&dst)[4]) {
-                const int j = w2 + 2 * (u >> 1), h = u & 1;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    dst[c] = masked ? __ldg(reinterpret_cast<const uint4*>(mrow + j * kPanelBytes + swz_offset(row, h * 4 + c)))
-                                    : make_uint4(0u, 0u, 0u, 0u);
-            };
-            fetch(0, mk[0]);
-            fetch(1, mk[1]);
+            const bool mask = st.kind == BWD_MASK;
+            uint2 mw = make_uint2(0u, 0u);                                  // dummy tiles carry zero gradients
+            if (mask) {
+                const int tile = tile_of(2 * g + x);
+                if (tile < p.n_tiles)
+                    mw = __ldg(reinterpret_cast<const uint2*>(p.bits + (size_t)tile * kBitsTileBytes + (size_t)st.mask_slot * kBitsSlotBytes + row * 32 + j * 8));
+            }
             mbar_wait(&bars->acc_full[x], jx & 1);
             tc_fence_after();
             const uint32_t acc_addr = lane_addr + x * 256;
-            uint8_t* hbase = smem + kBOffH + x * 65536;
-            uint32_t rr[2][32];
-            tmem_ld32_issue(acc_addr + w2 * 64, rr[0]);
+            uint8_t* dst = smem + kBOffH + x * 65536 + j * kPanelBytes;
+            uint32_t rr[2][16];
+            tmem_ld16_issue(acc_addr, rr[0]);
             if (ev > 0) mbar_wait(&bars->stash_done[x], (ev - 1) & 1);     // the slot's panels have been copied out
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int j = w2 + 2 * (u >> 1), h = u & 1;
-                tmem_ld_wait(rr[u & 1]);
-                if (u + 1 < 4) tmem_ld32_issue(acc_addr + (w2 + 2 * ((u + 1) >> 1)) * 64 + ((u + 1) & 1) * 32, rr[(u + 1) & 1]);
-                uint32_t pk[16];
+                tmem_ld_wait16(rr[u & 1]);
+                if (u + 1 < 4) tmem_ld16_issue(acc_addr + (u + 1) * 16, rr[(u + 1) & 1]);
+                uint32_t pk[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(__uint_as_float(rr[u & 1][2 * i]), __uint_as_float(rr[u & 1][2 * i + 1]));
-                if (st.kind == BWD_MASK) {
-                    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint32_t w[4] = {mk[u & 1][c].x, mk[u & 1][c].y, mk[u & 1][c].z, mk[u & 1][c].w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)     // dY * [h > 0] on a bf16 pair: all-ones / zero per half
-                            pk[4 * c + e] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w[e]), zero);
-                    }
-                }
-                if (u + 2 < 4) fetch(u + 2, mk[u & 1]);
-                uint8_t* dst = hbase + j * kPanelBytes;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4*>(dst + swz_offset(row, h * 4 + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(rr[u & 1][2 * i]), __uint_as_float(rr[u & 1][2 * i + 1]));
+                if (mask) relu_mask_unit((u >> 1) ? mw.y : mw.x, u, pk);
+                *reinterpret_cast<uint4*>(dst + soff[2 * u]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(dst + soff[2 * u + 1]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
             fence_async_smem();
             tc_fence_before();
@@ -264,6 +249,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
             if (lane == 0) {
                 mbar_arrive(&bars->stash_ready[x]);
                 mbar_arrive_cluster(x ? ready1 : ready0);
+            }
+        };
+        for (int g = 0; 2 * g < my_super; ++g) {
+            const bool two = 2 * g + 1 < my_super;
+            for (int s = 0; s < p.n_steps; ++s) {
+                job(0, g, s);
+                if (two) job(1, g, s);
             }
         }
     } else if (warp < 4) {
@@ -778,7 +770,7 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
 
     // ---- (1) dgrad chain ----
     BwdParams bp{};
-    bp.packed = (const uint8_t*)packed; bp.act = wsb + w.act; bp.dy = wsb + w.dy;
+    bp.packed = (const uint8_t*)packed; bp.act = wsb + w.act; bp.dy = wsb + w.dy; bp.bits = wsb + w.bits;
     bp.sigma = sigma; bp.rgb = rgb; bp.d_sigma = d_sigma; bp.d_rgb = d_rgb;
     bp.w_rgb = m.has_view ? prm[SNERF_P_RGB_W] : nullptr;
     bp.n_points = P; bp.n_tiles = w.n_tiles; bp.n_steps = pl.n_bwd; bp.has_view = m.has_view ? 1 : 0;

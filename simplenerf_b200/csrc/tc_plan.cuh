@@ -184,10 +184,42 @@ __device__ __forceinline__ void encode_point_accurate(const float x[3], int degr
     }
 }
 
+constexpr uint32_t kBitsSlotBytes = 4096;                 // sign bits of one 128 x 256 activation tile: [row][panel][2 words]
+constexpr uint32_t kBitsTileBytes = 8 * kBitsSlotBytes;   // trunk layers 0..7
+
 struct TcWorkspace {
-    size_t view_bias, act, dy, total;
+    size_t view_bias, act, dy, bits, total;
     int n_tiles;
 };
+
+// Sign bits of post-ReLU bf16 activations (the ReLU masks of the backward pass).  A 16-column unit is 8 packed pairs;
+// pair p.lo / p.hi nonzero is bit 15 / 31 of (pair + 0x7FFF7FFF) -- the values are non-negative, so no carry crosses the
+// halves.  Byte permutes gather the four flag bytes of two pairs and a shift files them at bit (8 * byte + kk) of the
+// word, kk = 4 * (unit & 1) + pair / 2: 32 flags per word, two words per row and 64-column panel.
+// generic-mode byte permute; bit 3 of a selector nibble replicates the msb of the selected byte (the __byte_perm intrinsic masks it off)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t relu_bits_unit(const uint32_t (&pk)[8], int unit) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t z = prmt(pk[2 * k] + 0x7FFF7FFFu, pk[2 * k + 1] + 0x7FFF7FFFu, 0x7531u);
+        w |= (z & 0x80808080u) >> (7 - (4 * (unit & 1) + k));
+    }
+    return w;
+}
+// inverse: all-ones / zero half-word masks for the 8 pairs of a unit
+__device__ __forceinline__ void relu_mask_unit(uint32_t word, int unit, uint32_t (&pk)[8]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t t = word << (7 - (4 * (unit & 1) + k));
+        pk[2 * k] &= prmt(t, 0u, 0x9988u);        // sign-replicate bytes 0 / 1
+        pk[2 * k + 1] &= prmt(t, 0u, 0xBBAAu);    // sign-replicate bytes 2 / 3
+    }
+}
 
 static inline TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n_rays, int n_samples, uint32_t flags) {
     TcWorkspace w{};
@@ -201,6 +233,8 @@ static inline TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n
         off += (size_t)w.n_tiles * pl.tile_stash_bytes;
         w.dy = off;
         off += (size_t)w.n_tiles * pl.tile_stash_bytes;
+        w.bits = off;
+        off += (size_t)w.n_tiles * kBitsTileBytes;
     }
     w.total = off + 1024;
     return w;
