@@ -29,6 +29,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RAYS_PER_GPU = 4096
+# DRAM bytes of the three MLP kernels per 4096-ray step (dram__bytes_read.sum + dram__bytes_write.sum, summed over the 12
+# launches of one step): profiles/r1_final_ncu_full_summary.md.  Algorithmic figure: forward
+# 5.0 + dgrad 5.25 + wgrad 10.8 KB/point x 1 572 864 points = 33.1 GB.
+MLP_DRAM_BYTES_PER_STEP = 31.47e9
 TRAIN_FLOP_PER_RAY = 2 * 648_585_216          # fwd+bwd MACs per ray (4 MLPs) x 2
 RENDER_FLOP_PER_RAY = 2 * 256 * 593_408       # vanilla coarse+fine eval
 STREAMS = (('rgb_coarse', 'depth_coarse'), ('rgb_fine', 'depth_fine'),
@@ -317,7 +321,11 @@ def run_ours(args):
             'clocks': clocks.summary(),
             'roofline': {'bound': 'tensor', 'kernel': 'tc_forward_kernel + tc_dgrad_kernel + tc_wgrad_kernel (all 4 MLPs)',
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
-                         'traffic': None, 'peak_source': pk['source'],
+                         'traffic': MLP_DRAM_BYTES_PER_STEP, 'peak_source': pk['source'],
+                         'traffic_note': 'DRAM bytes per step of the same three kernels (12 launches), ncu --set full, profiles/r1_final_ncu_full_summary.md',
+                         # the training step moves 31.5 GB through HBM for 5.3 TFLOP: it sits between the two roofs
+                         'hbm': {'achieved': MLP_DRAM_BYTES_PER_STEP / (mlp_total * 1e-3) / 1e9, 'peak': pk['hbm'], 'unit': 'GB/s',
+                                 'frac': MLP_DRAM_BYTES_PER_STEP / (mlp_total * 1e-3) / 1e9 / pk['hbm']},
                          'ms_per_step': {'mlp_forward': mlp_ms['mlp_forward'], 'mlp_backward': mlp_ms['mlp_backward'],
                                          'other': ms_step - mlp_total},
                          'frac_forward': n * 2 * 220_348_416 / (mlp_ms['mlp_forward'] * 1e-3) / 1e12 / pk['tflops'],
