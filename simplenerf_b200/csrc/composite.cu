@@ -167,14 +167,15 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_fwd_kernel(const 
     const int ray = blockIdx.x * kCompWarps + warp;
     if (ray >= a.n_rays) return;
     const int s = a.s;
+    // the colour row is requested before the depth / density rows are consumed: one memory round trip per ray, not two
+    const float* rgb = a.rgb + (size_t)ray * s * 3;
+    float c[CONTIG ? 3 * C : 1];
+    if constexpr (CONTIG) load_vec<3 * C>(rgb + lane * 3 * C, c);
     RayState<C, CONTIG> r;
     r.load_and_scan(a, ray, lane);
 
-    const float* rgb = a.rgb + (size_t)ray * s * 3;
     float cr = 0.f, cg = 0.f, cb = 0.f;
     if constexpr (CONTIG) {
-        float c[3 * C];
-        load_vec<3 * C>(rgb + lane * 3 * C, c);
 #pragma unroll
         for (int i = 0; i < C; ++i) {
             cr += r.w[i] * c[3 * i];                                                                // :449
@@ -241,6 +242,9 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const 
     const int ray = blockIdx.x * kCompWarps + warp;
     if (ray >= a.n_rays) return;
     const int s = a.s;
+    const float* rgb = a.rgb + (size_t)ray * s * 3;
+    float c[CONTIG ? 3 * C : 1];
+    if constexpr (CONTIG) load_vec<3 * C>(rgb + lane * 3 * C, c);     // in flight during the scan
     RayState<C, CONTIG> r;
     r.load_and_scan(a, ray, lane);
 
@@ -262,10 +266,7 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const 
     const float resid = r.dsum - depth * r.acc, resid_ndc = r.dsum_ndc - depth_ndc * r.acc;
     const bool per_sample_grads = a.g_weights || a.g_vis || a.g_alpha;
 
-    const float* rgb = a.rgb + (size_t)ray * s * 3;
     float g[C], gt[C];
-    float c[CONTIG ? 3 * C : 1];
-    if constexpr (CONTIG) load_vec<3 * C>(rgb + lane * 3 * C, c);
     float lane_gt = 0.f;
 #pragma unroll
     for (int i = 0; i < C; ++i) {

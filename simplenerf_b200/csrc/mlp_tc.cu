@@ -68,22 +68,40 @@ int tc_pack(const snerf_mlp_desc& d, const float* const* prm, void* packed, cuda
 }
 
 // per-ray part of the view layer: vb[ray][o] = b_view[o] + sum_c W_view[o][col0 + c] * PE(view_dir)[c]   (:640, :695)
+// One block per kRaysPerBlock rays: the encodings are computed element-parallel (accurate sin/cos: fp32 consumers), then
+// thread o keeps its weight row in registers and forms the output of every ray of the block.
+constexpr int kVbRays = 16;
 __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restrict__ view_dirs, const float* __restrict__ w_view,
                                                            const float* __restrict__ b_view, float* __restrict__ vb, int n_rays,
                                                            int view_degree, int view_in, int col0, int venc) {
-    const int ray = blockIdx.x;
-    __shared__ float ve[32];
-    if (threadIdx.x == 0) {
-        float v[3] = {view_dirs[ray * 3], view_dirs[ray * 3 + 1], view_dirs[ray * 3 + 2]};
-        float e[64];
-        encode_point_accurate(v, view_degree, e);
-        for (int c = 0; c < venc; ++c) ve[c] = e[c];
+    const int ray0 = blockIdx.x * kVbRays;
+    __shared__ float ve[kVbRays][32];
+    for (int e = threadIdx.x; e < kVbRays * 32; e += blockDim.x) {
+        const int r = e >> 5, idx = e & 31, ray = ray0 + r;
+        float val = 0.f;                                                   // columns >= venc and rays past the end stay zero
+        if (ray < n_rays && idx < venc) {
+            if (idx < 3) {
+                val = view_dirs[ray * 3 + idx];
+            } else {
+                const int j = idx - 3, k = j / 6, rem = j - 6 * k, c = rem >= 3 ? rem - 3 : rem;
+                const float x = view_dirs[ray * 3 + c] * (float)(1 << k);          // same arithmetic as encode_point_accurate
+                val = rem >= 3 ? cosf(x) : sinf(x);
+            }
+        }
+        ve[r][idx] = val;
     }
     __syncthreads();
     const int o = threadIdx.x;
-    float acc = b_view[o];
-    for (int c = 0; c < venc; ++c) acc = fmaf(w_view[(size_t)o * view_in + col0 + c], ve[c], acc);
-    vb[(size_t)ray * 128 + o] = acc;
+    float w[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) w[c] = c < venc ? w_view[(size_t)o * view_in + col0 + c] : 0.f;
+    const float bias = b_view[o];
+    for (int r = 0; r < kVbRays && ray0 + r < n_rays; ++r) {
+        float acc = bias;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc = fmaf(w[c], ve[r][c], acc);
+        vb[(size_t)(ray0 + r) * 128 + o] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -592,7 +610,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     SNERF_REQUIRE(((uintptr_t)packed & 15) == 0 && ((uintptr_t)ws & 15) == 0, "mlp_forward: packed/workspace must be 16-byte aligned");
     uint8_t* wsb = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     if (m.has_view) {
-        tc_view_bias_kernel<<<n_rays, 128, 0, st>>>(view_dirs, prm[SNERF_P_VIEW_W], prm[SNERF_P_VIEW_B], (float*)(wsb + w.view_bias),
+        tc_view_bias_kernel<<<(n_rays + kVbRays - 1) / kVbRays, 128, 0, st>>>(view_dirs, prm[SNERF_P_VIEW_W], prm[SNERF_P_VIEW_B], (float*)(wsb + w.view_bias),
                                                     n_rays, d.view_degree, m.view_in, m.width + m.enc_hi, m.venc);
         SNERF_LAUNCH_OK("tc_view_bias_kernel");
     }
