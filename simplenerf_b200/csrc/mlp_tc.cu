@@ -4,17 +4,18 @@
 // Reference behaviour: src/models/SimpleNeRF01.py  run_network :363-392, PositionalEncoder :525-557,
 // MLP.forward :626-654, get_view_independent_outputs :656-685, get_view_dependent_outputs :687-715.
 //
-// Forward kernel (one CTA per SM, 128-point tiles, 480 threads):
-//   warp 0     weight loader   packed bf16 weight chunks [N x 64] stream L2 -> smem ring by bulk async copy (TMA)
-//   warp 1     MMA issuer      tcgen05.mma M=128, N=256|128, K=16; accumulators ping-pong in TMEM (2 x 256 cols)
-//   warps 2-9  epilogue        TMEM -> regs -> bias/ReLU -> bf16 -> swizzled smem panel (the next layer's A operand);
-//                              two warps per SM sub-partition, each owning 32 of a panel's 64 columns; hidden layers
-//                              use one packed HFMA2.BF16.RELU per value pair, the sigma / rgb heads are fp32 dot
-//                              products on the un-rounded activations
-//   warps 10-13 encoder        rays + depth -> point -> positional encoding -> bf16 panel E of the NEXT tile
-//   warp 14    stash writer    (training) bulk-copies every activation panel to HBM for the backward pass
-// The epilogue hands activations to the MMA issuer panel by panel (64 columns), so layer l+1's MMAs start while
-// layer l's epilogue is still running; activations never leave the SM in eval mode.
+// Forward kernel: 74 clusters of two CTAs (one CTA per SM, 736 threads); a pair works on 256-point super tiles with
+// tcgen05.mma.cta_group::2 and keeps two of them in flight (see the comment above the kernel):
+//   warps 0-3   encoder        rays + depth -> point -> positional encoding (kept in registers, the single encoding
+//                              panel is rewritten before each use)
+//   warp 4      stash writer   (training) one 64 KB bulk copy of the slot's activation panels per job -> HBM
+//   warp 5      weight loader  this CTA's half of every packed bf16 weight chunk, L2 -> smem ring by bulk async copy
+//   warps 6-21  epilogue       TMEM -> regs -> bias/ReLU -> bf16 -> swizzled smem panel (the next layer's A operand);
+//                              four warps per SM sub-partition, one 64-column panel each; hidden layers use one packed
+//                              HFMA2.BF16.RELU per value pair, the sigma / rgb heads are fp32 dot products on the
+//                              un-rounded activations; in training also the ReLU sign bits for the backward pass
+//   warp 22     MMA issuer (leader CTA: converged warp, one elected lane) / weight relay (peer CTA)
+// Activations never leave the SM in eval mode.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_plan.cuh"

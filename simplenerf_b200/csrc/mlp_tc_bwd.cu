@@ -3,12 +3,12 @@
 // The forward kernel (mlp_tc.cu) left the bf16 activation panels of every layer in the HBM stash as raw
 // swizzled smem images.  Backward of the reference MLP (src/models/SimpleNeRF01.py :626-715 under autograd):
 //
-//  dgrad kernel  -- same warp-specialised chain as the forward: per 128-point tile
+//  dgrad kernel  -- the CTA-pair machine of the forward kernel run backwards (two 256-point super tiles in flight):
 //      prologue warps : d rgb_pre = d rgb * rgb (1-rgb), d sigma_pre = d sigma * [sigma>0],
 //                       dY_v = (d rgb_pre W_rgb) * [hv>0]            (CUDA cores, fp32)
 //      MMA chain      : d feature = dY_v W_view[:, :256];  d h8 = d feature W_feat + d head_pre W_head;
-//                       d h_l = dY_l W_l[:, hidden]  for l = 7..1    (tcgen05, B = packed W^T chunks)
-//      epilogue warps : ReLU mask from the stashed activation, bf16, back to smem as the next A operand
+//                       d h_l = dY_l W_l[:, hidden]  for l = 7..1    (tcgen05 cta_group::2, B = packed W^T chunks)
+//      epilogue warps : ReLU mask from the sign bits the forward epilogue filed, bf16, back to smem as the next A operand
 //      stash writer   : every dY panel -> HBM (raw panel image) for the wgrad kernel
 //  wgrad kernel  -- per parameter matrix dW = dY^T X over all points: both operands are read MN-major from the
 //      stashed panels (no transposes), accumulated in TMEM across all tiles of the CTA, flushed once with fp32
