@@ -5,7 +5,7 @@ gradients per optimizer step (NCCL on GPUs; the same code runs over gloo in the 
 needs no collective."""
 from __future__ import annotations
 
-from typing import Dict, Iterable, Tuple
+from typing import Dict, Iterable, List, Tuple
 
 import torch
 import torch.distributed as dist
@@ -23,19 +23,56 @@ def shard_rays(batch: Dict, rank: int, world: int) -> Dict:
     return {k: (v[lo:hi] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == n else v) for k, v in batch.items()}
 
 
+def _grad_buckets(params: List[torch.nn.Parameter]):
+    """Gradients that are views of one flat bucket (the drop-in's backward hands out one zero-padded fp32 bucket per MLP)
+    are exchanged in place; anything else goes through a temporary flat copy.  Returns (flat tensors, loose params)."""
+    by_storage: Dict[int, list] = {}
+    for p in params:
+        by_storage.setdefault(p.grad.untyped_storage().data_ptr(), []).append(p)
+    flats, loose = [], []
+    for ps in by_storage.values():
+        g0 = ps[0].grad
+        storage = g0.untyped_storage()
+        n_el = storage.nbytes() // 4
+        spans = sorted((p.grad.storage_offset(), p.grad.numel()) for p in ps)
+        tiled = len(ps) > 1 and all(p.grad.dtype == torch.float32 and p.grad.is_contiguous() for p in ps)
+        end = 0
+        for off, n in spans:                 # every span starts where the previous one ended, up to 3 floats of padding
+            tiled = tiled and end <= off <= end + 3
+            end = off + n
+        tiled = tiled and end <= n_el <= end + 3
+        if tiled:
+            flats.append(torch.empty(0, dtype=torch.float32, device=g0.device).set_(storage, 0, (n_el,)))
+        else:
+            loose.extend(ps)
+    return flats, loose
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], weight: float = 1.0, group=None) -> None:
-    """Sum the gradients of all ranks in one flat bucket.  Each rank first scales its gradient by ``weight`` =
+    """Sum the gradients of all ranks.  Each rank first scales its gradient by ``weight`` =
     (rays of this rank that enter the mean) / (such rays over all ranks), so that per-rank *mean* losses add up to the
-    gradient of the global mean loss; for equal shards weight = 1/world."""
+    gradient of the global mean loss; for equal shards weight = 1/world.
+    Bucketed gradients (one flat buffer per MLP) are all-reduced in place, one collective each, launched back to back."""
     params = [p for p in params if p.grad is not None]
     if not params:
         return
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
-    if weight != 1.0:
-        flat *= weight
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, group=group)
-    off = 0
-    for p in params:
-        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-        off += p.numel()
+    flats, loose = _grad_buckets(params)
+    packed = torch.cat([p.grad.reshape(-1) for p in loose]) if loose else None
+    bufs = flats + ([packed] if packed is not None else [])
+    active = dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if active else 1
+    # NCCL averages in the collective itself when every rank carries the same weight
+    use_avg = active and dist.get_backend(group) == 'nccl' and abs(weight * world - 1.0) < 1e-12
+    handles = []
+    for b in bufs:
+        if weight != 1.0 and not use_avg:
+            b *= weight
+        if active:
+            handles.append(dist.all_reduce(b, op=dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM, group=group, async_op=True))
+    for h in handles:
+        h.wait()
+    if packed is not None:
+        off = 0
+        for p in loose:
+            p.grad.copy_(packed[off:off + p.numel()].view_as(p))
+            off += p.numel()

@@ -46,6 +46,42 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _bucket_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    # gradients laid out the way the drop-in's backward hands them out: views of one zero-padded flat bucket per MLP
+    shapes = [(5, 3), (7,), (2, 2), (1,)]
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    total = sum((p.numel() + 3) // 4 * 4 for p in params)
+    flat = torch.zeros(total)
+    off = 0
+    for i, p in enumerate(params):
+        view = flat[off:off + p.numel()].view_as(p)
+        view.fill_(float(10 * rank + i + 1))
+        p.grad = view
+        off += (p.numel() + 3) // 4 * 4
+    loose = torch.nn.Parameter(torch.zeros(3))
+    loose.grad = torch.full((3,), float(rank + 1))
+    allreduce_gradients(params + [loose], weight=0.5)
+    if rank == 0:
+        ret['bucket'] = [p.grad.clone() for p in params] + [loose.grad.clone()]
+        ret['same_storage'] = all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for p in params)
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradients_are_reduced_in_place():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_bucket_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret['same_storage']
+    for i, g in enumerate(ret['bucket'][:4]):       # 0.5 * ((i + 1) + (10 + i + 1))
+        torch.testing.assert_close(g, torch.full_like(g, 0.5 * (2 * i + 12)))
+    torch.testing.assert_close(ret['bucket'][4], torch.full((3,), 1.5))
+
+
 def test_shard_bounds_cover_everything():
     for n in (0, 1, 7, 4096, 762048):
         for world in (1, 2, 4, 8):
