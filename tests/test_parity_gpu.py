@@ -272,6 +272,41 @@ def test_tensor_path_tile_edges(n):
             torch.testing.assert_close(got_r, want_r, rtol=3e-2, atol=1e-2, msg=lambda m: f'{slot} n={n} save={save} rgb {m}')
 
 
+def test_tensor_path_reproducible():
+    """The chain kernels hand work between warps and CTAs through ~20 mbarriers; a protocol race would show up as a run
+    that differs from the previous one.  Forward must be bit-identical, gradients equal up to fp32-atomics ordering."""
+    if not __import__('simplenerf_b200._lib', fromlist=['x']).load().snerf_has_tensor_path():
+        pytest.skip('tensor path not built')
+    from simplenerf_b200._lib import FLAG_SAVE_FOR_BWD
+    from simplenerf_b200.models.FusedSimpleNeRF01 import MlpBlock
+    model_cfg = synthetic.make_configs('simplenerf')['model']
+    for cfg, n_rays, s in ((model_cfg['coarse_mlp'], 2500, 64), (model_cfg['views_augmentation']['coarse_mlp'], 700, 192)):
+        torch.manual_seed(0)
+        block = MlpBlock(cfg).to(DEV)
+        table = [None if p is None else p.detach() for p in block.param_table()]
+        packed = block.packed(table)
+        b = synthetic.make_ray_batch('llff', n_rays, 3)
+        o, d, vd = cuda(b['rays_o_ndc']), cuda(b['rays_d_ndc']), cuda(b['view_dirs'])
+        z = torch.sort(torch.rand(n_rays, s, device=DEV), -1)[0].contiguous()
+        noise = torch.randn(n_rays * s, device=DEV)
+        ws = torch.empty(ops.mlp_workspace_bytes(block.desc, n_rays, s, FLAG_SAVE_FOR_BWD), dtype=torch.uint8, device=DEV)
+        ds, dr = torch.randn(n_rays, s, device=DEV), torch.randn(n_rays, s, 3, device=DEV)
+        ref = None
+        for _ in range(6):
+            sigma, rgb = ops.mlp_forward(block.desc, table, packed, o, d, vd, z, noise, ws, FLAG_SAVE_FOR_BWD)
+            grads = [None if p is None else torch.zeros_like(p) for p in table]
+            ops.mlp_backward(block.desc, table, packed, o, d, vd if block.view_degree else None, z, sigma, rgb, ds, dr, grads, ws,
+                             FLAG_SAVE_FOR_BWD)
+            cur = (sigma.clone(), rgb.clone(), [None if g is None else g.clone() for g in grads])
+            if ref is None:
+                ref = cur
+                continue
+            assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1])
+            for ga, gb in zip(cur[2], ref[2]):
+                if ga is not None:
+                    assert float((ga - gb).norm() / (gb.norm() + 1e-20)) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------
 # a1/a2/a13 the whole drop-in against outputs of the unmodified reference
 # ------------------------------------------------------------------------------------------------
