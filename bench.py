@@ -201,7 +201,9 @@ def run_ours(args):
     model = get_model(configs, None)
     model.load_state_dict(make_state(model))
     model = model.to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4, betas=(0.9, 0.999), fused=True)
+    from simplenerf_b200.optim import FusedAdam
+    opt = (torch.optim.Adam(model.parameters(), lr=5e-4, betas=(0.9, 0.999), fused=True) if args.torch_adam
+           else FusedAdam(model.parameters(), lr=5e-4, betas=(0.9, 0.999)))    # Trainer01.py:516, one launch
     params = [p for p in model.parameters()]
     n = RAYS_PER_GPU
     host = synthetic.make_ray_batch('llff', n, 1021 + rank)
@@ -240,7 +242,10 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(max(args.warmup, 3)):
+    # warm-up: the W requested steps, and at least 25 in total -- a fresh box needs a few hundred ms of load before clocks,
+    # allocator pools and the NCCL channels settle (the first timed steps of a cold process measured 3-5 % slow)
+    n_warm = max(args.warmup, 25)
+    for _ in range(n_warm):
         step(resident)
 
     # ---- value: inputs resident in HBM; MLP kernels timed with CUDA events inside the timed region ----
@@ -322,7 +327,7 @@ def run_ours(args):
         achieved = n * TRAIN_FLOP_PER_RAY / (mlp_total * 1e-3) / 1e12
         line = {
             'metric': 'train rays/s (64+128 samples, fwd+bwd)', 'value': value, 'unit': 'rays/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+            'steps': args.steps, 'warmup': n_warm, 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': workload_config(world),
             'e2e': {'value': e2e_value, 'unit': 'rays/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d_bytes,
@@ -359,6 +364,7 @@ def main():
     ap.add_argument('--no-render', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--quick-cpu', action='store_true')
+    ap.add_argument('--torch-adam', action='store_true', help='torch.optim.Adam(fused=True) instead of simplenerf_b200.optim.FusedAdam')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

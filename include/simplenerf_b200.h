@@ -132,6 +132,17 @@ int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const* host_para
                        float* const* host_grads, void* workspace, size_t workspace_bytes, int n_rays,
                        int n_samples, uint32_t flags, void* stream);
 
+/* ---- (f) N2, optimizer step of the process-per-GPU trainer ------------------------------------
+ * Adam update of n_tensors (<= SNERF_ADAM_MAX_TENSORS) fp32 tensors in ONE launch; replaces the per-tensor work of
+ * torch.optim.Adam as the reference uses it (src/Trainer01.py:516; no weight decay, no amsgrad):
+ *   m = m + (g - m)(1 - beta1);  v = beta2 v + (1 - beta2) g^2;
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * params / grads / exp_avg / exp_avg_sq are HOST arrays of device pointers (16-byte aligned), numel a host array.   */
+#define SNERF_ADAM_MAX_TENSORS 64
+int snerf_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                    const long long* numel, int n_tensors, float lr, float beta1, float beta2, float eps, int step,
+                    void* stream);
+
 /* Self-test of the tcgen05 GEMM building blocks against a CUDA-core GEMM (used by tests).
  * Returns SNERF_OK and writes the max abs error of each mode to host_max_err[4].               */
 int snerf_tensor_selftest(float* host_max_err, void* stream);

@@ -307,6 +307,33 @@ def test_tensor_path_reproducible():
                     assert float((ga - gb).norm() / (gb.norm() + 1e-20)) < 1e-4
 
 
+def test_fused_adam_matches_torch_adam():
+    """(f) N2: the one-launch Adam against torch.optim.Adam as the reference configures it (Trainer01.py:516)."""
+    from simplenerf_b200.optim import FusedAdam
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(256, 63), (256,), (256, 319), (1, 256), (1,), (3, 128), (128, 283), (70001,)]
+    ours = [torch.nn.Parameter(cuda(torch.randn(s, generator=gen))) for s in shapes]
+    theirs = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    a = FusedAdam(ours, lr=5e-4, betas=(0.9, 0.999), eps=1e-8)
+    b = torch.optim.Adam(theirs, lr=5e-4, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(6):
+        total = sum((p.numel() + 3) // 4 * 4 for p in ours)
+        flat = cuda(torch.randn(total, generator=gen)) * (10.0 ** (step - 3))        # the backward's bucket layout
+        off = 0
+        for p, q in zip(ours, theirs):
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            q.grad = p.grad.clone()
+            off += (p.numel() + 3) // 4 * 4
+        if step == 4:
+            a.param_groups[0]['lr'] = b.param_groups[0]['lr'] = 1e-3                   # LR schedule touches param_groups
+        a.step()
+        b.step()
+        for p, q in zip(ours, theirs):
+            torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-6, atol=1e-7)
+    state = a.state_dict()
+    assert state['step'] == 6 and len(state['exp_avg']) == len(shapes)
+
+
 # ------------------------------------------------------------------------------------------------
 # a1/a2/a13 the whole drop-in against outputs of the unmodified reference
 # ------------------------------------------------------------------------------------------------
