@@ -307,9 +307,22 @@ def run_ours(args):
         with torch.no_grad():
             vmodel(frame)
             ms_frame = timed(lambda: vmodel(frame), 2) / 2
+        # the same frame through the one-call renderer: pose on the host -> device ray generation -> render ->
+        # device post-processing -> uint8 image and depth maps in pinned host memory, all inside the timed region
+        from simplenerf_b200.render import FrameRenderer
+        cam = synthetic.CAMERAS['llff']
+        intrinsic = [[cam['focal'], 0, cam['centre'][0]], [0, cam['focal'], cam['centre'][1]], [0, 0, 1]]
+        fr = FrameRenderer(vmodel, (h, w), intrinsic, cam['near'], cam['far'], rows=(r0, r1))
+        import numpy as np
+        pose = np.eye(4, dtype=np.float32)
+        fr.render(pose)
+        ms_frame_e2e = timed(lambda: fr.render(pose), 2) / 2
+        d2h = (r1 - r0) * w * (3 + 4 * 4)
         render = {'ms_per_frame': ms_frame, 'rays_per_s': h * w / (ms_frame * 1e-3), 'resolution': [h, w],
                   'tensor_frac_of_peak': h * w * RENDER_FLOP_PER_RAY / (ms_frame * 1e-3) / (peaks()['tflops'] * 1e12 * world),
-                  'sharding': f'{world} row bands, no collective'}
+                  'sharding': f'{world} row bands, no collective',
+                  'e2e': {'ms_per_frame': ms_frame_e2e, 'h2d_bytes_per_frame': 48 + 36, 'd2h_bytes_per_frame': d2h,
+                          'note': 'FrameRenderer.render(pose): rays generated on the device, uint8 image + 4 depth maps copied to pinned host memory'}}
 
     # ---- cpu baseline (rank 0, N=1 only): the oracle on the host cores, one full C2 step ----
     cpu = None

@@ -132,6 +132,20 @@ int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const* host_para
                        float* const* host_grads, void* workspace, size_t workspace_bytes, int n_rays,
                        int n_samples, uint32_t flags, void* stream);
 
+/* ---- (f) N1, one frame per call: rays of a camera pose and output post-processing -------------------
+ * (DataPreprocessor01.py get_rays :351-368, get_ndc_rays :371-389, get_view_dirs :392-394, post_process_image
+ * :1106-1109, post_process_depth :1112-1114; replaces the host numpy pass of create_test_data :807-895).
+ * pose34 (rows of [R|t]) and kinv33 (inverse intrinsic) are HOST arrays; s_w = -1/(W/(2 fx)), s_h = -1/(H/(2 fy)),
+ * two_near = 2 near, all computed by the caller in fp32 like the reference.  Rays of image rows [row0, row0+n_rows)
+ * are written row-major to the [n_rows*W, 3] device outputs (the *_ndc pair only if ndc != 0).                     */
+int snerf_generate_rays(const float* pose34, const float* kinv33, float s_w, float s_h, float near, float two_near,
+                        int h, int w, int row0, int n_rows, int ndc, float* rays_o, float* rays_d, float* view_dirs,
+                        float* rays_o_ndc, float* rays_d_ndc, void* stream);
+/* image[n_pixels,3] = uint8(round_half_even(clip(rgb,0,1)*255)); every depth map (<= 4, host array of device pointers)
+ * is clipped to >= 0 in place.                                                                                       */
+int snerf_postprocess_frame(const float* rgb, uint8_t* image, float* const* depth_maps, int n_maps, long long n_pixels,
+                            void* stream);
+
 /* ---- (f) N2, optimizer step of the process-per-GPU trainer ------------------------------------
  * Adam update of n_tensors (<= SNERF_ADAM_MAX_TENSORS) fp32 tensors in ONE launch; replaces the per-tensor work of
  * torch.optim.Adam as the reference uses it (src/Trainer01.py:516; no weight decay, no amsgrad):

@@ -34,6 +34,9 @@ _SIGNATURES = {
                                     C.c_size_t, C.c_int, C.c_int, C.c_uint32, _fp]),
     'snerf_mlp_backward': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                      C.POINTER(_fp), _fp, C.c_size_t, C.c_int, C.c_int, C.c_uint32, _fp]),
+    'snerf_generate_rays': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp]),
+    'snerf_postprocess_frame': (C.c_int, [_fp, _fp, C.POINTER(_fp), C.c_int, C.c_longlong, _fp]),
     'snerf_adam_step': (C.c_int, [C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_fp), C.POINTER(C.c_longlong), C.c_int,
                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _fp]),
     'snerf_tensor_selftest': (C.c_int, [C.POINTER(C.c_float), _fp]),

@@ -97,3 +97,20 @@ def test_render_matches_reference(name):
         scale = float(g[f'gnorm__{pname}'][0]) / max(1.0, prm.numel() ** 0.5)
         torch.testing.assert_close(gv, ref, rtol=1e-3, atol=1e-4 * scale + 1e-9, msg=lambda m, p=pname: f'{p}: {m}')
         np.testing.assert_allclose(float(prm.grad.double().norm()), float(g[f'gnorm__{pname}'][0]), rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# next row N1: per-frame ray construction and output post-processing (DataPreprocessor01.py)
+# ------------------------------------------------------------------------------------------------
+def test_rays_oracle_matches_reference_golden():
+    import os
+    from oracle import rays_oracle as ro
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rays.npz'))
+    for cam_name in ('llff', 're10k'):
+        cam = synthetic.CAMERAS[cam_name]
+        rays = ro.frame_rays(cam['resolution'], g[f'{cam_name}_intrinsic'], g[f'{cam_name}_pose'], cam['near'])
+        pick = g[f'{cam_name}_pick']
+        for key in ('rays_o', 'rays_d', 'view_dirs', 'rays_o_ndc', 'rays_d_ndc'):
+            np.testing.assert_array_equal(rays[key][pick], g[f'{cam_name}_{key}'], err_msg=f'{cam_name} {key}')
+    np.testing.assert_array_equal(ro.post_process_image(g['post_rgb']), g['post_image'])
+    np.testing.assert_array_equal(ro.post_process_depth(g['post_depth_in']), g['post_depth'])

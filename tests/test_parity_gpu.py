@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): composited rgb/depth <= 1e-3 abs; sample_
 identical uniforms and cdf; gradients <= 1e-2 relative.  The fp32 "precise" MLP path is held to much
 tighter bounds (1e-4) because it shares the reference's arithmetic.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -536,3 +538,88 @@ def test_full_size_invariants(precision):
     loss = out['rgb_fine'].sum() + out['depth_coarse'].sum()
     g1 = torch.autograd.grad(loss, model.fine_model.pts_linears[3].weight, retain_graph=False)[0]
     assert bool(torch.isfinite(g1).all()) and float(g1.abs().max()) > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# next row N1: device-side ray construction, post-processing and the one-call frame renderer
+# ------------------------------------------------------------------------------------------------
+def _ulp_close(got, want, ulps, what):
+    import numpy as np
+    got, want = np.asarray(got, np.float32), np.asarray(want, np.float32)
+    tol = ulps * np.spacing(np.maximum(np.abs(want), np.float32(1e-30)))
+    bad = np.abs(got.astype(np.float64) - want.astype(np.float64)) > tol
+    assert not bad.any(), f'{what}: {int(bad.sum())} values differ by more than {ulps} ulp (max abs {np.abs(got - want).max():.3e})'
+
+
+@pytest.mark.parametrize('cam_name', ['llff', 're10k'])
+def test_generate_rays_vs_reference(cam_name):
+    """get_rays / get_ndc_rays / get_view_dirs: CUDA kernel against the numpy oracle on the whole frame and against the
+    vectors of the unmodified reference.  fp32 throughout; the matrix products may associate differently (<= 4 ulp on the
+    directions; the NDC quantities divide by them, <= 32 ulp)."""
+    import numpy as np
+    from oracle import rays_oracle as ro
+    from simplenerf_b200.render import FrameRenderer
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rays.npz'))
+    cam = synthetic.CAMERAS[cam_name]
+    configs = synthetic.make_configs('vanilla')
+    model = get_model(configs, None).to(DEV).eval()
+    fr = FrameRenderer(model, cam['resolution'], g[f'{cam_name}_intrinsic'], cam['near'], cam['far'])
+    got = {k: v.cpu().numpy() for k, v in fr.rays(g[f'{cam_name}_pose']).items()}
+    want = ro.frame_rays(cam['resolution'], g[f'{cam_name}_intrinsic'], g[f'{cam_name}_pose'], cam['near'])
+    pick = g[f'{cam_name}_pick']
+    for key, ulps in (('rays_o', 0), ('rays_d', 4), ('view_dirs', 8), ('rays_o_ndc', 32), ('rays_d_ndc', 64)):
+        _ulp_close(got[key], want[key], ulps, f'{cam_name} {key} vs oracle')
+        _ulp_close(got[key][pick], g[f'{cam_name}_{key}'], ulps, f'{cam_name} {key} vs reference golden')
+    h, w = cam['resolution']
+    assert got['near'].shape == (h * w, 1) and float(got['far'][0, 0]) == float(np.float32(cam['far']))
+    # a row band equals the rows of the full frame (tile-sharded rendering)
+    band = FrameRenderer(model, cam['resolution'], g[f'{cam_name}_intrinsic'], cam['near'], cam['far'], rows=(100, 103))
+    sub = band.rays(g[f'{cam_name}_pose'])
+    for key in ('rays_d', 'rays_o_ndc', 'rays_d_ndc', 'view_dirs'):
+        assert np.array_equal(sub[key].cpu().numpy(), got[key][100 * w:103 * w])
+
+
+def test_postprocess_frame_exact():
+    """post_process_image / post_process_depth: bit exact (round half to even, clip)."""
+    import ctypes as C
+    import numpy as np
+    from simplenerf_b200 import _lib
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rays.npz'))
+    rgb = cuda(torch.from_numpy(g['post_rgb']))
+    n = rgb.shape[0]
+    depth = cuda(torch.from_numpy(g['post_depth_in'][:n].copy()))
+    image = torch.empty((n, 3), dtype=torch.uint8, device=DEV)
+    table = (C.c_void_p * 1)(depth.data_ptr())
+    _lib.check(_lib.load().snerf_postprocess_frame(rgb.data_ptr(), image.data_ptr(), table, 1, n, None), 'snerf_postprocess_frame')
+    torch.cuda.synchronize()
+    assert np.array_equal(image.cpu().numpy(), g['post_image'])
+    assert np.array_equal(depth.cpu().numpy(), g['post_depth'][:n])
+
+
+def test_frame_renderer_equals_model_on_oracle_rays():
+    """predict_frame: the one-call renderer gives what the drop-in gives on the oracle's host-built rays, post-processed
+    by the oracle (the reference's Tester path), on a row band of the LLFF camera."""
+    import numpy as np
+    from oracle import rays_oracle as ro
+    from simplenerf_b200.render import FrameRenderer
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rays.npz'))
+    cam = synthetic.CAMERAS['llff']
+    h, w = cam['resolution']
+    configs = synthetic.make_configs('vanilla')
+    state = gu.full_state(configs, 7, dense=True)
+    model = _build(configs, state, 'bf16').eval()
+    r0, r1 = 300, 308
+    fr = FrameRenderer(model, (h, w), g['llff_intrinsic'], cam['near'], cam['far'], rows=(r0, r1))
+    got = fr.render(g['llff_pose'])
+    rays = ro.frame_rays((h, w), g['llff_intrinsic'], g['llff_pose'], cam['near'])
+    n = (r1 - r0) * w
+    batch = {k: cuda(torch.from_numpy(v[r0 * w:r1 * w].copy())) for k, v in rays.items()}
+    ones = torch.ones((n, 1), device=DEV)
+    batch.update(near=cam['near'] * ones, far=float(np.float32(cam['far'])) * ones, near_ndc=0 * ones, far_ndc=ones)
+    with torch.no_grad():
+        out = model(batch)
+    want_img = ro.post_process_image(out['rgb_fine'].cpu().numpy().reshape(r1 - r0, w, 3))
+    assert got['image'].dtype == np.uint8 and got['image'].shape == (r1 - r0, w, 3)
+    assert np.abs(got['image'].astype(np.int32) - want_img.astype(np.int32)).max() <= 1      # rays differ by ulps -> at most one grey level
+    np.testing.assert_allclose(got['depth'], ro.post_process_depth(out['depth_fine'].cpu().numpy().reshape(r1 - r0, w)), rtol=2e-3, atol=2e-3)
+    assert (got['depth_ndc'] >= 0).all() and np.isfinite(got['depth_var_ndc']).all()
