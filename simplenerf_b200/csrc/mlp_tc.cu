@@ -414,6 +414,82 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 }
                 return;
             }
+            if (kind == EPI_VIEW) {
+                // ---- view layer (N = 128) + rgb head: fp32 on the un-rounded activations.  The 128 columns are split over all
+                // 16 warps (32 each: half a panel), since only the rgb head and -- in training -- the stash consume them ----
+                const int tile = tile_of(2 * g + x);
+                const long long pt = (long long)tile * kTileRows + row;
+                const bool valid = pt < p.n_points;
+                const int pan = j >> 1, u0 = 2 * (j & 1);
+                float head[4] = {0.f, 0.f, 0.f, 0.f};
+                if (!(p.debug & 2)) {
+                    const uint32_t vaddr = tmem + ((uint32_t)(q * 32) << 16) + x * 256 + pan * 64 + u0 * 16;
+                    uint32_t rr[2][16];
+                    tmem_ld16_issue(vaddr, rr[0]);
+                    tmem_ld16_issue(vaddr + 16, rr[1]);
+                    if (save && jx > 0) mbar_wait(&bars->stash_done[x], (jx - 1) & 1);
+                    const int ray = valid ? (int)((unsigned)pt / (unsigned)p.n_samples) : 0;   // host guarantees n_points < 2^31
+                    const float* vbias = p.view_bias + (size_t)ray * 128 + pan * 64 + u0 * 16;
+                    uint8_t* vdst = smem + kOffH + x * 65536 + pan * kPanelBytes + (uint32_t)row * kRowBytes;
+                    const uint32_t rx = (uint32_t)row & 7u;
+                    tmem_ld_wait16(rr[0]);
+                    tmem_ld_wait16(rr[1]);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int col0 = pan * 64 + (u0 + k) * 16;
+                        float v[16];
+                        const float4* bb = reinterpret_cast<const float4*>(vbias + k * 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b = __ldg(bb + i);
+                            v[4 * i + 0] = fmaxf(__uint_as_float(rr[k][4 * i + 0]) + b.x, 0.f);
+                            v[4 * i + 1] = fmaxf(__uint_as_float(rr[k][4 * i + 1]) + b.y, 0.f);
+                            v[4 * i + 2] = fmaxf(__uint_as_float(rr[k][4 * i + 2]) + b.z, 0.f);
+                            v[4 * i + 3] = fmaxf(__uint_as_float(rr[k][4 * i + 3]) + b.w, 0.f);
+                        }
+#pragma unroll
+                        for (int hh = 0; hh < 3; ++hh) {
+                            const float4* w = reinterpret_cast<const float4*>(s_wrgb + hh * 128 + col0);
+                            float a = head[hh];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 ww = w[i];
+                                a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
+                            }
+                            head[hh] = a;
+                        }
+                        if (save) {      // hv goes to the stash only (it feeds no later layer)
+                            const uint32_t c0 = (uint32_t)(2 * (u0 + k));
+                            *reinterpret_cast<uint4*>(vdst + ((c0 ^ rx) << 4)) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            *reinterpret_cast<uint4*>(vdst + (((c0 + 1) ^ rx) << 4)) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                        }
+                    }
+                    if (save) fence_async_smem();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (save) mbar_arrive(&bars->stash_ready[x]);
+                    mbar_arrive_cluster(x ? ready1 : ready0);
+                    if (tr) p.trace[(x * 16 + s) * 16 + 3] = clock64();
+                }
+                if (j > 0) {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) s_part[((j - 1) * 128 + row) * 4 + h] = head[h];
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+                if (j == 0 && valid) {
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj) {
+                        const float4 o = *reinterpret_cast<const float4*>(s_part + (jj * 128 + row) * 4);
+                        head[0] += o.x; head[1] += o.y; head[2] += o.z;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h] + s_misc[4 + h]);         // :704-707
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // the partial sums may be overwritten by the next head step
+                return;
+            }
             // ---- last trunk layer (sigma / rgb head) and the view layer (rgb head): fp32 on the un-rounded activations ----
             const int tile = tile_of(2 * g + x);
             const long long pt = (long long)tile * kTileRows + row;
