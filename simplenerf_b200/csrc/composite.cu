@@ -25,9 +25,11 @@ struct CompositeArgs {
     bool ndc, white;
 };
 
-__device__ __forceinline__ float warp_sum(float v) {
+// sum over the G lanes (32 or 16) that share a ray
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
 }
 
@@ -60,8 +62,10 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v
     }
 }
 
-// Per-ray quantities shared by forward and backward.  CONTIG: lane owns samples lane*C + i, else lane + 32*i.
-template <int C, bool CONTIG>
+// Per-ray quantities shared by forward and backward.  CONTIG: lane l of the ray's G-lane group owns samples l*C + i
+// (G = 16 puts two rays in a warp: 64-sample rays are issue-bound, and the per-ray setup, scans and reductions are then paid
+// once per two rays); else (G = 32) lane owns samples lane + 32*i.  `lane` below is the lane WITHIN the group.
+template <int C, bool CONTIG, int G = kWarp>
 struct RayState {
     float sig[C], zz[C], zm[C];      // sigma, z (ndc or metric), metric z
     float delta[C], alpha[C], trans[C], w[C];
@@ -89,7 +93,7 @@ struct RayState {
             const float up = __shfl_down_sync(kFull, zz[0], 1);      // first depth of the next lane
 #pragma unroll
             for (int i = 0; i < C - 1; ++i) znext[i] = zz[i + 1];
-            znext[C - 1] = lane == kWarp - 1 ? tail : up;
+            znext[C - 1] = lane == G - 1 ? tail : up;
         } else {
 #pragma unroll
             for (int i = 0; i < C; ++i) {
@@ -118,7 +122,7 @@ struct RayState {
             // exclusive product scan over lanes, then walk the lane's own samples                  // :447
             float incl = fprod;
 #pragma unroll
-            for (int o = 1; o < kWarp; o <<= 1) {
+            for (int o = 1; o < G; o <<= 1) {
                 const float v = __shfl_up_sync(kFull, incl, o);
                 if (lane >= o) incl *= v;
             }
@@ -155,23 +159,26 @@ struct RayState {
                 dsum_ndc += w[i] * zz[i];
             }
         }
-        acc = warp_sum(acc);                                                                        // :451
-        dsum = warp_sum(dsum);
-        dsum_ndc = warp_sum(dsum_ndc);
+        acc = group_sum<G>(acc);                                                                    // :451
+        dsum = group_sum<G>(dsum);
+        dsum_ndc = group_sum<G>(dsum_ndc);
     }
 };
 
-template <int C, bool CONTIG>
+template <int C, bool CONTIG, int G>
 __global__ void __launch_bounds__(kCompWarps* kWarp) composite_fwd_kernel(const CompositeArgs a) {
-    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-    const int ray = blockIdx.x * kCompWarps + warp;
-    if (ray >= a.n_rays) return;
+    static_assert(G == kWarp || (CONTIG && G == 16), "two rays per warp only with lane-contiguous ownership");
+    const int warp = threadIdx.x / kWarp, lane = (threadIdx.x % kWarp) % G;
+    const int ray_raw = (blockIdx.x * kCompWarps + warp) * (kWarp / G) + (threadIdx.x % kWarp) / G;
+    if (G == kWarp && ray_raw >= a.n_rays) return;
+    const bool valid = ray_raw < a.n_rays;               // G = 16: the odd last ray's partner half works on a copy and stores nothing
+    const int ray = valid ? ray_raw : a.n_rays - 1;
     const int s = a.s;
     // the colour row is requested before the depth / density rows are consumed: one memory round trip per ray, not two
     const float* rgb = a.rgb + (size_t)ray * s * 3;
     float c[CONTIG ? 3 * C : 1];
     if constexpr (CONTIG) load_vec<3 * C>(rgb + lane * 3 * C, c);
-    RayState<C, CONTIG> r;
+    RayState<C, CONTIG, G> r;
     r.load_and_scan(a, ray, lane);
 
     float cr = 0.f, cg = 0.f, cb = 0.f;
@@ -183,9 +190,9 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_fwd_kernel(const 
             cb += r.w[i] * c[3 * i + 2];
         }
         const size_t o = (size_t)ray * s + lane * C;
-        if (a.alpha) store_vec<C>(a.alpha + o, r.alpha);
-        if (a.vis) store_vec<C>(a.vis + o, r.trans);
-        if (a.weights) store_vec<C>(a.weights + o, r.w);
+        if (a.alpha && valid) store_vec<C>(a.alpha + o, r.alpha);
+        if (a.vis && valid) store_vec<C>(a.vis + o, r.trans);
+        if (a.weights && valid) store_vec<C>(a.weights + o, r.w);
     } else {
 #pragma unroll
         for (int i = 0; i < C; ++i) {
@@ -201,9 +208,9 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_fwd_kernel(const 
             }
         }
     }
-    cr = warp_sum(cr);
-    cg = warp_sum(cg);
-    cb = warp_sum(cb);
+    cr = group_sum<G>(cr);
+    cg = group_sum<G>(cg);
+    cb = group_sum<G>(cb);
     const float inv = 1.f / (r.acc + 1e-6f);
     const float depth = r.dsum * inv;                                                               // :453 / :459
     const float depth_ndc = r.dsum_ndc * inv;                                                       // :456
@@ -214,9 +221,9 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_fwd_kernel(const 
         var += r.w[i] * e * e;                                                                      // :454 / :460
         var_ndc += r.w[i] * en * en;                                                                // :457
     }
-    var = warp_sum(var);
-    var_ndc = warp_sum(var_ndc);
-    if (lane == 0) {
+    var = group_sum<G>(var);
+    var_ndc = group_sum<G>(var_ndc);
+    if (lane == 0 && valid) {
         const float bg = a.white ? 1.f - r.acc : 0.f;                                               // :463
         a.rgb_map[(size_t)ray * 3 + 0] = cr + bg;
         a.rgb_map[(size_t)ray * 3 + 1] = cg + bg;
@@ -236,16 +243,19 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_fwd_kernel(const 
 //   G_k   = g_k alpha_k + dL/dT_k
 //   dL/dalpha_k = g_k T_k + d_alpha_k - (sum_{j>k} G_j T_j) / f_k
 //   dL/dsigma_k = dL/dalpha_k * delta_k * (1 - alpha_k)
-template <int C, bool CONTIG>
+template <int C, bool CONTIG, int G>
 __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const CompositeArgs a) {
-    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-    const int ray = blockIdx.x * kCompWarps + warp;
-    if (ray >= a.n_rays) return;
+    static_assert(G == kWarp || (CONTIG && G == 16), "two rays per warp only with lane-contiguous ownership");
+    const int warp = threadIdx.x / kWarp, lane = (threadIdx.x % kWarp) % G;
+    const int ray_raw = (blockIdx.x * kCompWarps + warp) * (kWarp / G) + (threadIdx.x % kWarp) / G;
+    if (G == kWarp && ray_raw >= a.n_rays) return;
+    const bool valid = ray_raw < a.n_rays;
+    const int ray = valid ? ray_raw : a.n_rays - 1;
     const int s = a.s;
     const float* rgb = a.rgb + (size_t)ray * s * 3;
     float c[CONTIG ? 3 * C : 1];
     if constexpr (CONTIG) load_vec<3 * C>(rgb + lane * 3 * C, c);     // in flight during the scan
-    RayState<C, CONTIG> r;
+    RayState<C, CONTIG, G> r;
     r.load_and_scan(a, ray, lane);
 
     const float inv = 1.f / (r.acc + 1e-6f);
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const 
         float dr[3 * C];
 #pragma unroll
         for (int i = 0; i < C; ++i) { dr[3 * i] = r.w[i] * gr; dr[3 * i + 1] = r.w[i] * gg; dr[3 * i + 2] = r.w[i] * gb; }
-        store_vec<3 * C>(a.d_rgb + ((size_t)ray * s + lane * C) * 3, dr);
+        if (valid) store_vec<3 * C>(a.d_rgb + ((size_t)ray * s + lane * C) * 3, dr);
     } else {
 #pragma unroll
         for (int i = 0; i < C; ++i) {
@@ -316,11 +326,11 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const 
     // suffix sums  sum_{j>k} G_j T_j
     float ds[C];
     if constexpr (CONTIG) {
-        float incl = lane_gt;    // inclusive suffix over lanes
+        float incl = lane_gt;    // inclusive suffix over the lanes of the ray's group
 #pragma unroll
-        for (int off = 1; off < kWarp; off <<= 1) {
+        for (int off = 1; off < G; off <<= 1) {
             const float v = __shfl_down_sync(kFull, incl, off);
-            if (lane + off < kWarp) incl += v;
+            if (lane + off < G) incl += v;
         }
         float suffix = incl - lane_gt;           // everything owned by later lanes
 #pragma unroll
@@ -331,7 +341,7 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const 
             ds[i] = d_alpha * r.delta[i] * (1.f - r.alpha[i]);
             suffix += gt[i];
         }
-        store_vec<C>(a.d_sigma + (size_t)ray * s + lane * C, ds);
+        if (valid) store_vec<C>(a.d_sigma + (size_t)ray * s + lane * C, ds);
     } else {
         float carry = 0.f;
 #pragma unroll
@@ -356,13 +366,13 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const 
     }
 }
 
-template <int C, bool CONTIG>
+template <int C, bool CONTIG, int G = kWarp>
 static int launch_composite(const CompositeArgs& a, bool backward, cudaStream_t st) {
-    const int blocks = ceil_div(a.n_rays, kCompWarps);
+    const int blocks = ceil_div(a.n_rays, kCompWarps * (kWarp / G));
     if (backward)
-        composite_bwd_kernel<C, CONTIG><<<blocks, kCompWarps * kWarp, 0, st>>>(a);
+        composite_bwd_kernel<C, CONTIG, G><<<blocks, kCompWarps * kWarp, 0, st>>>(a);
     else
-        composite_fwd_kernel<C, CONTIG><<<blocks, kCompWarps * kWarp, 0, st>>>(a);
+        composite_fwd_kernel<C, CONTIG, G><<<blocks, kCompWarps * kWarp, 0, st>>>(a);
     SNERF_LAUNCH_OK(backward ? "composite_bwd_kernel" : "composite_fwd_kernel");
     return SNERF_OK;
 }
@@ -370,7 +380,7 @@ static int launch_composite(const CompositeArgs& a, bool backward, cudaStream_t 
 static int dispatch_composite(const CompositeArgs& a, bool backward, cudaStream_t st) {
     if (a.n_rays == 0) return SNERF_OK;
     switch (a.s) {   // vectorised, lane-contiguous kernels for the sample counts the model uses
-        case 64: return launch_composite<2, true>(a, backward, st);
+        case 64: return launch_composite<4, true, 16>(a, backward, st);    // two rays per warp, float4 rows
         case 128: return launch_composite<4, true>(a, backward, st);
         case 192: return launch_composite<6, true>(a, backward, st);
         case 256: return launch_composite<8, true>(a, backward, st);
