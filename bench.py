@@ -33,6 +33,12 @@ RAYS_PER_GPU = 4096
 # launches of one step): profiles/r1_final_ncu_full_summary.md.  Algorithmic figure: forward
 # 5.0 + dgrad 5.25 + wgrad 10.8 KB/point x 1 572 864 points = 33.1 GB.
 MLP_DRAM_BYTES_PER_STEP = 31.47e9
+# algorithmic GB per step and kernel: main / fine / pts-aug MLPs keep 9.5 panels x 512 B per point (4.75 KB) + 0.25 KB of
+# sign bits, views-aug 8 panels (4 KB); 4096 rays x (64 + 64 + 192) points with view layers + 4096 x 64 without.
+_P_VIEW, _P_NOVIEW = 4096 * (64 + 64 + 192), 4096 * 64
+ALG_GB = {'forward': (_P_VIEW * (4864 + 256) + _P_NOVIEW * (4096 + 256)) / 1e9,
+          'dgrad': (_P_VIEW * (4864 + 256 + 256) + _P_NOVIEW * (4096 + 256)) / 1e9,
+          'wgrad': (_P_VIEW * 80 * 128 + _P_NOVIEW * 72 * 128) / 1e9}
 TRAIN_FLOP_PER_RAY = 2 * 648_585_216          # fwd+bwd MACs per ray (4 MLPs) x 2
 RENDER_FLOP_PER_RAY = 2 * 256 * 593_408       # vanilla coarse+fine eval
 STREAMS = (('rgb_coarse', 'depth_coarse'), ('rgb_fine', 'depth_fine'),
@@ -253,19 +259,27 @@ def run_ours(args):
         step(resident)
 
     # ---- value: inputs resident in HBM; MLP kernels timed with CUDA events inside the timed region ----
-    events = {'mlp_forward': [], 'mlp_backward': []}
+    events = {'mlp_forward': [], 'mlp_backward': [], 'dgrad': [], 'wgrad': []}
 
     class Timer:
         def __init__(self, name):
             self.name = name
+            self.split_event = None
 
         def __enter__(self):
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if self.name == 'mlp_backward':      # the C side records this event between the dgrad and the wgrad launch
+                self.split_event = torch.cuda.Event(enable_timing=True)
+                self.split_event.record()        # materialises the handle
             self.e0.record()
+            return self
 
         def __exit__(self, *exc):
             self.e1.record()
             events[self.name].append((self.e0, self.e1))
+            if self.split_event is not None:
+                events['dgrad'].append((self.e0, self.split_event))
+                events['wgrad'].append((self.split_event, self.e1))
             return False
 
     ops.TIMER['hook'] = Timer
@@ -361,6 +375,14 @@ def run_ours(args):
                          # the training step moves 31.5 GB through HBM for 5.3 TFLOP: it sits between the two roofs
                          'hbm': {'achieved': MLP_DRAM_BYTES_PER_STEP / (mlp_total * 1e-3) / 1e9, 'peak': pk['hbm'], 'unit': 'GB/s',
                                  'frac': MLP_DRAM_BYTES_PER_STEP / (mlp_total * 1e-3) / 1e9 / pk['hbm']},
+                         # per kernel, against the roof that bounds it in training: ALGORITHMIC bytes (DESIGN.md section 4:
+                         # KB per point x 1 572 864 points of a step; views-aug has no view layer) / live CUDA-event time
+                         'kernels': {k: {'bound': 'hbm', 'ms_per_step': mlp_ms[t], 'algorithmic_gb': gb,
+                                         'achieved': gb / (mlp_ms[t] * 1e-3), 'peak': pk['hbm'], 'unit': 'GB/s',
+                                         'frac': gb / (mlp_ms[t] * 1e-3) / pk['hbm']}
+                                     for k, t, gb in (('tc_forward_kernel', 'mlp_forward', ALG_GB['forward']),
+                                                      ('tc_dgrad_kernel', 'dgrad', ALG_GB['dgrad']),
+                                                      ('tc_wgrad_kernel', 'wgrad', ALG_GB['wgrad'])) if mlp_ms.get(t)},
                          'ms_per_step': {'mlp_forward': mlp_ms['mlp_forward'], 'mlp_backward': mlp_ms['mlp_backward'],
                                          'other': ms_step - mlp_total},
                          'frac_forward': n * 2 * 220_348_416 / (mlp_ms['mlp_forward'] * 1e-3) / 1e12 / pk['tflops'],

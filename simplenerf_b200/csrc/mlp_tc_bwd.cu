@@ -743,6 +743,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
 }
 
 static long long* g_wg_trace = nullptr;
+static cudaEvent_t g_split_event = nullptr;   // measurement: recorded between the dgrad and the wgrad launch (bench.py)
 static int g_wg_debug = 0;   // set by snerfdbg_set_wgrad_trace (debug only)
 
 // =================================================================================================
@@ -885,6 +886,7 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         for (int j = 0; j < nj; ++j) { wp.jobs[j].cta0 = (int16_t)c0; wp.jobs[j].n_cta = (int16_t)n[j]; c0 += n[j]; }
     }
     (void)grid;
+    if (g_split_event) cudaEventRecord(g_split_event, st);
     tc_wgrad_kernel<<<num_sms(), kWgThreads, kWgSmem, st>>>(wp);
     SNERF_LAUNCH_OK("tc_wgrad_kernel");
     return SNERF_OK;
@@ -893,4 +895,6 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
 }  // namespace snerf
 
 extern "C" void snerfdbg_set_wgrad_trace(long long* device_buffer) { snerf::g_wg_trace = device_buffer; }
+// measurement hook (not part of the public ABI): a cudaEvent_t recorded on the launch stream between dgrad and wgrad; null disables
+extern "C" void snerfdbg_set_backward_split_event(void* event) { snerf::g_split_event = (cudaEvent_t)event; }
 extern "C" void snerfdbg_set_wgrad_debug(int bits) { snerf::g_wg_debug = bits; }

@@ -179,11 +179,20 @@ def mlp_backward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, si
                  grads: List[Optional[torch.Tensor]], workspace, flags: int) -> None:
     n, s = z.shape
     LAUNCHES['count'] += (45 if flags & FLAG_PRECISE else 2)   # tensor path: dgrad chain + wgrad
-    with _timed('mlp_backward'):
-        _lib.check(_lib.load().snerf_mlp_backward(
-            C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
-            _ptr(z), _ptr(sigma), _ptr(rgb), _ptr(d_sigma), _ptr(d_rgb), pointer_table(grads), _ptr(workspace, torch.uint8),
-            workspace.numel(), n, s, flags, _stream()), 'snerf_mlp_backward')
+    with _timed('mlp_backward') as tm:
+        split = getattr(tm, 'split_event', None)        # bench.py: an event recorded between the dgrad and the wgrad launch
+        lib = _lib.load()
+        if split is not None:
+            lib.snerfdbg_set_backward_split_event.argtypes = [C.c_void_p]
+            lib.snerfdbg_set_backward_split_event(split.cuda_event)
+        try:
+            _lib.check(lib.snerf_mlp_backward(
+                C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
+                _ptr(z), _ptr(sigma), _ptr(rgb), _ptr(d_sigma), _ptr(d_rgb), pointer_table(grads), _ptr(workspace, torch.uint8),
+                workspace.numel(), n, s, flags, _stream()), 'snerf_mlp_backward')
+        finally:
+            if split is not None:
+                lib.snerfdbg_set_backward_split_event(None)
 
 
 def tensor_selftest() -> List[float]:
