@@ -32,7 +32,7 @@ RAYS_PER_GPU = 4096
 # DRAM bytes of the three MLP kernels per 4096-ray step (dram__bytes_read.sum + dram__bytes_write.sum, summed over the 12
 # launches of one step): profiles/r1_final_ncu_full_summary.md.  Algorithmic figure: forward
 # 5.0 + dgrad 5.25 + wgrad 10.8 KB/point x 1 572 864 points = 33.1 GB.
-MLP_DRAM_BYTES_PER_STEP = 31.47e9
+MLP_DRAM_BYTES_PER_STEP = 31.39e9
 # algorithmic GB per step and kernel: main / fine / pts-aug MLPs keep 9.5 panels x 512 B per point (4.75 KB) + 0.25 KB of
 # sign bits, views-aug 8 panels (4 KB); 4096 rays x (64 + 64 + 192) points with view layers + 4096 x 64 without.
 _P_VIEW, _P_NOVIEW = 4096 * (64 + 64 + 192), 4096 * 64
@@ -190,7 +190,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from simplenerf_b200 import _lib, ops, synthetic
-    from simplenerf_b200.distributed import allreduce_gradients
+    from simplenerf_b200.distributed import GradientExchange
     from simplenerf_b200.models import get_model
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -211,6 +211,7 @@ def run_ours(args):
     opt = (torch.optim.Adam(model.parameters(), lr=5e-4, betas=(0.9, 0.999), fused=True) if args.torch_adam
            else FusedAdam(model.parameters(), lr=5e-4, betas=(0.9, 0.999)))    # Trainer01.py:516, one launch
     params = [p for p in model.parameters()]
+    exchange = GradientExchange(params, weight=1.0 / world) if world > 1 else None
     n = RAYS_PER_GPU
     host = synthetic.make_ray_batch('llff', n, 1021 + rank)
     g = torch.Generator().manual_seed(3 + rank)
@@ -225,8 +226,8 @@ def run_ours(args):
         out = model(batch)
         loss = training_loss(out, batch['target_rgb'], batch['target_depth'])
         loss.backward()
-        if world > 1:   # ray-sharded data parallel: sum of shard gradients / world == gradient of the global mean loss
-            allreduce_gradients(params, weight=1.0 / world)
+        if exchange is not None:   # ray-sharded data parallel: sum of shard gradients / world == gradient of the global mean loss;
+            exchange.finish()      # the buckets were launched from autograd hooks while the backward pass was still running
         opt.step()
         return loss
 

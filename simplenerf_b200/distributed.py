@@ -76,3 +76,81 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], weight: float = 1.
         for p in loose:
             p.grad.copy_(packed[off:off + p.numel()].view_as(p))
             off += p.numel()
+
+
+class GradientExchange:
+    """Overlaps the gradient exchange with the backward pass: the all-reduce of an MLP's gradient bucket is launched from
+    an autograd hook as soon as the last gradient of that bucket has been produced, so the exchange of the fine MLP
+    (whose backward runs first) travels under the backward kernels of the coarse MLPs.
+
+        exchange = GradientExchange(model.parameters(), weight=1 / world)
+        loss.backward(); exchange.finish(); optimizer.step()
+
+    The first step learns which parameters share a bucket (it exchanges everything in `finish`); from the second step on
+    every complete bucket is reduced in place the moment it is ready."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], weight: float = 1.0, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.weight, self.group = weight, group
+        self.bucket_of: Dict[int, int] = {}          # id(param) -> bucket index (learned)
+        self.bucket_size: List[int] = []
+        self._seen: List[int] = []
+        self._handles: list = []
+        self._done: set = set()
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    def _active(self) -> bool:
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _reduce(self, buf: torch.Tensor) -> None:
+        world = dist.get_world_size(self.group) if self._active() else 1
+        use_avg = self._active() and dist.get_backend(self.group) == 'nccl' and abs(self.weight * world - 1.0) < 1e-12
+        if self.weight != 1.0 and not use_avg:
+            buf *= self.weight
+        if self._active():
+            self._handles.append(dist.all_reduce(buf, op=dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM, group=self.group,
+                                                 async_op=True))
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        b = self.bucket_of.get(id(p))
+        if b is None:
+            return
+        self._seen[b] += 1
+        if self._seen[b] == self.bucket_size[b]:
+            flats, loose = _grad_buckets([q for q in self.params if self.bucket_of.get(id(q)) == b and q.grad is not None])
+            if len(flats) == 1 and not loose:          # still one tiled bucket: exchange it now
+                self._reduce(flats[0])
+                self._done.update(id(q) for q in self.params if self.bucket_of.get(id(q)) == b)
+
+    def finish(self) -> None:
+        """Exchange whatever the hooks have not (first step, parameters outside buckets), then wait for everything."""
+        rest = [p for p in self.params if p.grad is not None and id(p) not in self._done]
+        if rest:
+            flats, loose = _grad_buckets(rest)
+            packed = torch.cat([p.grad.reshape(-1) for p in loose]) if loose else None
+            for b in flats + ([packed] if packed is not None else []):
+                self._reduce(b)
+        for h in self._handles:
+            h.wait()
+        if rest and packed is not None:
+            off = 0
+            for p in loose:
+                p.grad.copy_(packed[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        if not self.bucket_of:                       # learn the buckets from this step's gradients
+            by_storage: Dict[int, list] = {}
+            for p in self.params:
+                if p.grad is not None:
+                    by_storage.setdefault(p.grad.untyped_storage().data_ptr(), []).append(p)
+            for ps in by_storage.values():
+                if len(ps) > 1:
+                    for p in ps:
+                        self.bucket_of[id(p)] = len(self.bucket_size)
+                    self.bucket_size.append(len(ps))
+        self._seen = [0] * len(self.bucket_size)
+        self._handles, self._done = [], set()
+
+    def close(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

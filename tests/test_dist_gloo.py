@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 
 from oracle import nerf_oracle as orc
 from simplenerf_b200 import synthetic
-from simplenerf_b200.distributed import allreduce_gradients, shard_bounds, shard_rays
+from simplenerf_b200.distributed import GradientExchange, allreduce_gradients, shard_bounds, shard_rays
 
 N_RAYS = 24
 
@@ -80,6 +80,63 @@ def test_bucketed_gradients_are_reduced_in_place():
     for i, g in enumerate(ret['bucket'][:4]):       # 0.5 * ((i + 1) + (10 + i + 1))
         torch.testing.assert_close(g, torch.full_like(g, 0.5 * (2 * i + 12)))
     torch.testing.assert_close(ret['bucket'][4], torch.full((3,), 1.5))
+
+
+class _BucketFn(torch.autograd.Function):
+    """Stand-in for the drop-in's MLP backward: hands out the gradients of its parameters as views of one flat bucket."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        ctx.save_for_backward(x, *params)
+        return sum((p * x).sum() for p in params)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *params = ctx.saved_tensors
+        total = sum((p.numel() + 3) // 4 * 4 for p in params)
+        flat = torch.zeros(total)
+        out, off = [], 0
+        for p in params:
+            view = flat[off:off + p.numel()].view_as(p)
+            view.copy_(g * x.expand_as(p))
+            out.append(view)
+            off += (p.numel() + 3) // 4 * 4
+        return (None,) + tuple(out)
+
+
+def _exchange_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    blocks = [[torch.nn.Parameter(torch.ones(s)) for s in ((4, 3), (5,))], [torch.nn.Parameter(torch.ones(s)) for s in ((2, 2), (1,), (6,))]]
+    params = [p for blk in blocks for p in blk]
+    ex = GradientExchange(params, weight=0.5)
+    got = []
+    for step in range(3):                      # step 0 learns the buckets, steps 1-2 exchange from the hooks
+        for p in params:
+            p.grad = None
+        x = torch.tensor(float(rank + 1 + step))
+        (_BucketFn.apply(x, *blocks[0]) + _BucketFn.apply(x, *blocks[1])).backward()
+        hooked = len(ex._handles)
+        ex.finish()
+        got.append((hooked, [p.grad.clone() for p in params]))
+    ex.close()
+    if rank == 0:
+        ret['exchange'] = got
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_overlapped_with_backward():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_exchange_worker, args=(2, port, ret), nprocs=2, join=True)
+    for step, (hooked, grads) in enumerate(ret['exchange']):
+        assert hooked == (0 if step == 0 else 2)            # both buckets launched from the hooks after the first step
+        want = 0.5 * ((1 + step) + (2 + step))              # weight * (x of rank 0 + x of rank 1)
+        for g in grads:
+            torch.testing.assert_close(g, torch.full_like(g, want))
 
 
 def test_shard_bounds_cover_everything():
