@@ -184,40 +184,79 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
 }
 
 // ------------------------------------------------------------------------------------------------
-// fine, the model's shape (64 coarse depths, 32*NPL new samples): one warp per ray, everything in registers
-// except three small smem rows.  The new samples are sorted with a register bitonic network (shuffles), then
-// merged with the already sorted coarse depths by rank (binary searches), so no 256-slot smem sort is needed.
+// fine, the model's shape (64 coarse depths, 32*NPL new samples): one warp per ray, values in registers, three small
+// smem rows per warp.  The kernel is instruction-bound (1.8 KB of HBM traffic per ray against several hundred warp
+// instructions), so every stage is written for instruction count:
+//   * cdf and mid points interleaved as float2 -> the two gathers of a sample are two LDS.64;
+//   * searchsorted(right=True) over the 63 cdf entries = a branch-free 6-step descent (LDS, FSETP, predicated add);
+//   * the new samples are sorted (only when they are not already in order) by a bitonic network in its "flip"
+//     form -- every compare-exchange is ascending, so the direction is a compile-time constant inside a lane and
+//     one lane-bit predicate across lanes: FMNMX per element in registers, SHFL + FMNMX across lanes;
+//   * the merge with the (sorted) coarse depths is by rank from the coarse side only: coarse depth k goes to slot
+//     k + #(samples < depth) of a row pre-filled with a sentinel, and the samples fill the remaining slots in order
+//     (per-lane hole count + one warp scan), straight into the registers that are stored to HBM.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastWarps = 8;
 constexpr int kSc = 64;
+
+// Shared-memory accesses by 32-bit shared-space address.  The descents below keep absolute addresses in registers so
+// that a step is LDS [reg+imm], FSETP, predicated add (written with C++ pointers, nvcc re-derives base + offset and
+// spends a fourth instruction per step).  volatile + "memory": ordered against the surrounding stores / __syncwarp.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
 
 template <int NPL>
 __device__ __forceinline__ void bitonic_sort_registers(float (&v)[NPL], int lane) {
     constexpr int N = NPL * kWarp;
 #pragma unroll
     for (int k = 2; k <= N; k <<= 1) {
+        // flip stage: element idx meets idx ^ (k-1); the lower index keeps the minimum
+        if (k <= NPL) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int r = 0; r < NPL; ++r) {
+                const int q = r ^ (k - 1);
+                if (r < q) {
+                    const float a = v[r], b = v[q];
+                    v[r] = fminf(a, b);
+                    v[q] = fmaxf(a, b);
+                }
+            }
+        } else {
+            const int m = k / NPL - 1;                        // partner lane = lane ^ m, partner register = NPL-1-r
+            const bool lower = (lane & ((m + 1) >> 1)) == 0;  // top bit of the mask decides who is the lower index
+            float o[NPL];
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) o[r] = __shfl_xor_sync(kFull, v[NPL - 1 - r], m);
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) v[r] = lower ? fminf(v[r], o[r]) : fmaxf(v[r], o[r]);
+        }
+        // half cleaners: idx meets idx ^ j, ascending
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
             if (j >= NPL) {
-                const int d = j / NPL;                        // partner lane distance
-                const bool lower = (lane & d) == 0;           // this lane holds the lower-index element of each pair
+                const int d = j / NPL;
+                const bool lower = (lane & d) == 0;
 #pragma unroll
                 for (int r = 0; r < NPL; ++r) {
-                    const int idx = lane * NPL + r;
-                    const bool up = (idx & k) == 0;           // ascending block
                     const float o = __shfl_xor_sync(kFull, v[r], d);
-                    const bool take_min = lower == up;
-                    v[r] = take_min ? fminf(v[r], o) : fmaxf(v[r], o);
+                    v[r] = lower ? fminf(v[r], o) : fmaxf(v[r], o);
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < NPL; ++r) {
                     if ((r & j) == 0) {
-                        const int idx = lane * NPL + r;
-                        const bool up = (idx & k) == 0;
                         const float a = v[r], b = v[r + j];
-                        v[r] = up ? fminf(a, b) : fmaxf(a, b);
-                        v[r + j] = up ? fmaxf(a, b) : fminf(a, b);
+                        v[r] = fminf(a, b);
+                        v[r + j] = fmaxf(a, b);
                     }
                 }
             }
@@ -231,24 +270,52 @@ __global__ void __launch_bounds__(kFastWarps* kWarp)
                             const float* __restrict__ u, int u_stride, float* __restrict__ z_fine,
                             float* __restrict__ samples_dbg, float* __restrict__ cdf_dbg, int* __restrict__ below_dbg,
                             int* __restrict__ above_dbg, int n_rays) {
-    constexpr int NNEW = NPL * kWarp, TOT = kSc + NNEW, NB = kSc - 1;
-    __shared__ float s_all[kFastWarps][kSc + kSc + kSc + NNEW + TOT];
+    constexpr int NNEW = NPL * kWarp, TOT = kSc + NNEW, NB = kSc - 1, OPL = TOT / kWarp;
+    constexpr uint32_t kHole = 0xffffffffu;   // a NaN pattern no depth can carry
+    static_assert(OPL % 2 == 0 && (NNEW & (NNEW - 1)) == 0, "row shapes");
+    struct __align__(16) Row {
+        float2 cb[kSc];      // (cdf[k], bins[k]), 63 used: the two gathers of a sample
+        float ss[NNEW];      // sorted new samples
+        float outm[TOT];     // merged row: coarse depths scattered into holes (must follow ss)
+        float ecdf[kSc];     // cdf[0..62] as an implicit search tree in breadth-first order (root at [1])
+        float ess[NNEW];     // ss[0..NNEW-2] likewise
+    };
+    // Breadth-first ("Eytzinger") copies for the two descents: the nodes a warp can touch at level k are 2^k
+    // consecutive words, so 32 lanes never meet in a bank on different words (a descent over the sorted array reads
+    // nodes 2^(6-k) words apart -- up to 8 lanes per bank; ncu: 117 conflict cycles per ray, L1 data pipe saturated).
+    constexpr int LOGN = NPL == 2 ? 6 : NPL == 4 ? 7 : 8;
+    static_assert((1 << LOGN) == NNEW, "LOGN");
+    __shared__ Row s_rows[kFastWarps];
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int ray = blockIdx.x * kFastWarps + warp;
     if (ray >= n_rays) return;
-    float* cdf = s_all[warp];            // [64] (63 used)
-    float* bins = cdf + kSc;             // [64] (63 used)
-    float* zcs = bins + kSc;             // [64] coarse depths
-    float* ss = zcs + kSc;               // [NNEW] sorted new samples
-    float* outm = ss + NNEW;             // [TOT] merged row
+    Row& row = s_rows[warp];
 
     // ---- coarse depths, mid points, weights: lane owns coarse indices 2*lane, 2*lane+1 ----
     const float2 z2 = __ldg(reinterpret_cast<const float2*>(z_coarse + (size_t)ray * kSc) + lane);
     const float2 w2 = __ldg(reinterpret_cast<const float2*>(w_coarse + (size_t)ray * kSc) + lane);
+    float us[NPL];
+    {
+        const float* urow = u + (size_t)ray * u_stride + lane * NPL;
+        if constexpr (NPL % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < NPL / 4; ++i) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(urow) + i);
+                us[4 * i] = t.x; us[4 * i + 1] = t.y; us[4 * i + 2] = t.z; us[4 * i + 3] = t.w;
+            }
+        } else {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(urow));
+            us[0] = t.x; us[1] = t.y;
+        }
+    }
+    // pre-fill this lane's slots of the merged row with holes
+#pragma unroll
+    for (int i = 0; i < OPL / 2; ++i)
+        *reinterpret_cast<uint2*>(row.outm + lane * OPL + 2 * i) = make_uint2(kHole, kHole);
+
     const float znext = __shfl_down_sync(kFull, z2.x, 1);
-    *reinterpret_cast<float2*>(zcs + 2 * lane) = z2;
-    bins[2 * lane] = __fmul_rn(.5f, __fadd_rn(z2.y, z2.x));                                     // :310
-    if (lane < kWarp - 1) bins[2 * lane + 1] = __fmul_rn(.5f, __fadd_rn(znext, z2.y));
+    const float bin_a = __fmul_rn(.5f, __fadd_rn(z2.y, z2.x));                                   // :310
+    const float bin_b = __fmul_rn(.5f, __fadd_rn(znext, z2.y));                                  // (lane 31: unused)
     // interior weights k = 1 .. 62, + 1e-5                                                      // :331
     const float wa = lane > 0 ? __fadd_rn(w2.x, 1e-5f) : 0.f;              // k = 2*lane
     const float wb = lane < kWarp - 1 ? __fadd_rn(w2.y, 1e-5f) : 0.f;      // k = 2*lane + 1
@@ -267,59 +334,62 @@ __global__ void __launch_bounds__(kFastWarps* kWarp)
         if (lane >= o) incl += v;
     }
     const double before = incl - lane_pdf;
-    cdf[2 * lane] = (float)(before + (double)pa);                                               // cdf[0] = 0  (:334)
-    if (lane < kWarp - 1) cdf[2 * lane + 1] = (float)(before + (double)pa + (double)pb);
+    const float cdf_a = (float)(before + (double)pa);                                           // cdf[0] = 0  (:334)
+    const float cdf_b = lane < kWarp - 1 ? (float)(before + (double)pa + (double)pb)
+                                         : __int_as_float(0x7f800000);                          // entry 63: never read
+    *reinterpret_cast<float4*>(&row.cb[2 * lane]) = make_float4(cdf_a, bin_a, cdf_b, bin_b);
+    // sorted index j = node t = j + 1 of the in-order numbering: level = top - ctz(t), slot = 2^level + (t >> (ctz(t)+1))
+    const int tz1 = __ffs(lane + 1) - 1;                              // ctz(lane + 1)
+    row.ecdf[32 + lane] = cdf_a;                                      // j = 2*lane:   t odd, bottom level
+    if (lane < kWarp - 1) row.ecdf[(16 >> tz1) + ((lane + 1) >> (tz1 + 1))] = cdf_b;   // j = 2*lane+1: t = 2*(lane+1)
     __syncwarp();
     if (cdf_dbg != nullptr) {
-        cdf_dbg[(size_t)ray * NB + 2 * lane] = cdf[2 * lane];
-        if (lane < kWarp - 1) cdf_dbg[(size_t)ray * NB + 2 * lane + 1] = cdf[2 * lane + 1];
+        cdf_dbg[(size_t)ray * NB + 2 * lane] = cdf_a;
+        if (lane < kWarp - 1) cdf_dbg[(size_t)ray * NB + 2 * lane + 1] = cdf_b;
     }
 
     // ---- invert the cdf for this lane's NPL uniforms (:345-359) ----
-    float us[NPL], smp[NPL];
-    const float* urow = u + (size_t)ray * u_stride + lane * NPL;
-    if constexpr (NPL % 4 == 0) {
+    // searchsorted(right=True) = #(cdf[j] <= u) over 63 = 2^6 - 1 sorted entries: 6-step descent on byte offsets
+    // node i -> 2i + (cdf <= u); after 6 levels i - 64 = #(cdf <= u).  On byte addresses a = E + 4i: a' = 2a - E (+4)
+    const uint32_t cbp = smem_addr(row.cb), ecp = smem_addr(row.ecdf);
+    uint32_t off[NPL];   // address of entry #(cdf <= u) of cb
 #pragma unroll
-        for (int i = 0; i < NPL / 4; ++i) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(urow) + i);
-            us[4 * i] = t.x; us[4 * i + 1] = t.y; us[4 * i + 2] = t.z; us[4 * i + 3] = t.w;
-        }
-    } else {
+    for (int r = 0; r < NPL; ++r) off[r] = ecp + 4;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) us[i] = __ldg(urow + i);
-    }
-    int lo[NPL], hi[NPL];
-#pragma unroll
-    for (int r = 0; r < NPL; ++r) { lo[r] = 0; hi[r] = NB; }
-#pragma unroll
-    for (int step = 0; step < 6; ++step) {          // NB = 63 < 2^6: searchsorted(right=True)
+    for (int level = 0; level < 6; ++level) {
 #pragma unroll
         for (int r = 0; r < NPL; ++r) {
-            if (lo[r] < hi[r]) {
-                const int mid = (lo[r] + hi[r]) >> 1;
-                if (cdf[mid] <= us[r]) lo[r] = mid + 1; else hi[r] = mid;
-            }
+            const float c = lds_f32(off[r]);
+            off[r] = 2 * off[r] - ecp;
+            if (c <= us[r]) off[r] += 4;
         }
     }
 #pragma unroll
+    for (int r = 0; r < NPL; ++r) off[r] = 2 * (off[r] - ecp) - 64 * 8 + cbp;
+    float smp[NPL];
+#pragma unroll
     for (int r = 0; r < NPL; ++r) {
-        const int below = max(lo[r] - 1, 0);                                                    // :346
-        const int above = min(lo[r], NB - 1);                                                   // :347
-        const float c0 = cdf[below], c1 = cdf[above];
-        float denom = __fsub_rn(c1, c0);                                                        // :356
+        const float2 lo = lds_f32x2(max(off[r], cbp + 8) - 8);                                  // below  :346
+        const float2 hi = lds_f32x2(min(off[r], cbp + (NB - 1) * 8));                           // above  :347
+        float denom = __fsub_rn(hi.x, lo.x);                                                    // :356
         if (denom < 1e-5f) denom = 1.f;                                                         // :357
-        const float t = __fdiv_rn(__fsub_rn(us[r], c0), denom);                                 // :358
-        const float b0 = bins[below], b1 = bins[above];
-        smp[r] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));                                // :359
-        if (samples_dbg != nullptr) samples_dbg[(size_t)ray * NNEW + lane * NPL + r] = smp[r];
-        if (below_dbg != nullptr) below_dbg[(size_t)ray * NNEW + lane * NPL + r] = below;
-        if (above_dbg != nullptr) above_dbg[(size_t)ray * NNEW + lane * NPL + r] = above;
+        const float t = __fdiv_rn(__fsub_rn(us[r], lo.x), denom);                               // :358
+        smp[r] = __fadd_rn(lo.y, __fmul_rn(t, __fsub_rn(hi.y, lo.y)));                          // :359
+    }
+    if (samples_dbg != nullptr) {     // parity-test outputs, in the caller's order of uniforms
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            samples_dbg[(size_t)ray * NNEW + lane * NPL + r] = smp[r];
+            const int pos = (int)(off[r] - cbp) / 8;
+            if (below_dbg != nullptr) below_dbg[(size_t)ray * NNEW + lane * NPL + r] = max(pos - 1, 0);
+            if (above_dbg != nullptr) above_dbg[(size_t)ray * NNEW + lane * NPL + r] = min(pos, NB - 1);
+        }
     }
 
-    // ---- sort the new samples (values only), then merge by rank with the sorted coarse depths (:314) ----
+    // ---- sort the new samples (values only) (:314) ----
     // Sorted uniforms (the deterministic linspace of eval / rendering) give samples that are already in order: the
     // inverse cdf is monotone.  That is checked on the samples themselves (rounding could break it by an ulp), and
-    // the 128-element bitonic network -- about 40 % of the kernel's instructions -- is skipped when it holds.
+    // the 128-element bitonic network is skipped when it holds.
     {
         bool in_order = true;
 #pragma unroll
@@ -328,47 +398,80 @@ __global__ void __launch_bounds__(kFastWarps* kWarp)
         if (lane < kWarp - 1) in_order &= smp[NPL - 1] <= nxt;
         if (!__all_sync(kFull, in_order)) bitonic_sort_registers<NPL>(smp, lane);
     }
+    if constexpr (NPL % 4 == 0) {
 #pragma unroll
-    for (int r = 0; r < NPL; ++r) ss[lane * NPL + r] = smp[r];
-    __syncwarp();
-    // new sample at sorted position i goes to  i + #(coarse <= sample)
+        for (int i = 0; i < NPL / 4; ++i)
+            *reinterpret_cast<float4*>(row.ss + lane * NPL + 4 * i) = make_float4(smp[4 * i], smp[4 * i + 1], smp[4 * i + 2], smp[4 * i + 3]);
+    } else {
+        *reinterpret_cast<float2*>(row.ss + lane * NPL) = make_float2(smp[0], smp[1]);
+    }
+    // breadth-first copy of ss[0 .. NNEW-2] (ss[NNEW-1] is compared separately)
+    const float ss_last = __shfl_sync(kFull, smp[NPL - 1], kWarp - 1);
 #pragma unroll
     for (int r = 0; r < NPL; ++r) {
-        int l = 0, h = kSc;
+        const int t = lane * NPL + r + 1;
+        const int tz = r + 1 < NPL ? __ffs(r + 1) - 1 : __ffs(NPL) - 1 + tz1;      // ctz(t)
+        if (r + 1 < NPL || lane < kWarp - 1) row.ess[((NNEW / 2) >> tz) + (t >> (tz + 1))] = smp[r];
+    }
+    __syncwarp();
+
+    // ---- merge: coarse depth k goes to slot k + #(samples < depth); lower_bound over NNEW = 2^m sorted samples ----
+    {
+        const uint32_t esp = smem_addr(row.ess), omp = smem_addr(row.outm);
+        const float zv[2] = {z2.x, z2.y};
+        uint32_t p[2] = {esp + 4, esp + 4};
 #pragma unroll
-        for (int step = 0; step < 7; ++step) {
-            if (l < h) {
-                const int mid = (l + h) >> 1;
-                if (zcs[mid] <= smp[r]) l = mid + 1; else h = mid;
+        for (int level = 0; level < LOGN; ++level) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float c = lds_f32(p[q]);
+                p[q] = 2 * p[q] - esp;
+                if (c < zv[q]) p[q] += 4;
             }
         }
-        outm[lane * NPL + r + l] = smp[r];
-    }
-    // coarse depth k goes to  k + #(samples < depth)
-    {
-        const float zv[2] = {z2.x, z2.y};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            int l = 0, h = NNEW;
-#pragma unroll
-            for (int step = 0; step < 9; ++step) {
-                if (l < h) {
-                    const int mid = (l + h) >> 1;
-                    if (ss[mid] < zv[q]) l = mid + 1; else h = mid;
-                }
-            }
-            outm[2 * lane + q + l] = zv[q];
+            // (p - esp) / 4 - NNEW = #(ss[0..NNEW-2] < z);  + the last sample
+            if (ss_last < zv[q]) p[q] += 4;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(p[q] - esp + omp + (2 * lane + q - NNEW) * 4), "f"(zv[q]) : "memory");
         }
     }
     __syncwarp();
-    float* dst = z_fine + (size_t)ray * TOT;
-    if constexpr (TOT % 64 == 0) {
+    // the samples fill the holes in order: this lane's first sample index = holes in all lower lanes
+    uint32_t ov[OPL];
 #pragma unroll
-        for (int i = 0; i < TOT / 64; ++i)
-            *reinterpret_cast<float2*>(dst + i * 64 + 2 * lane) = *reinterpret_cast<const float2*>(outm + i * 64 + 2 * lane);
-    } else {
-        for (int i = lane; i < TOT; i += kWarp) dst[i] = outm[i];
+    for (int i = 0; i < OPL / 2; ++i) {
+        const uint2 t = *reinterpret_cast<const uint2*>(row.outm + lane * OPL + 2 * i);
+        ov[2 * i] = t.x; ov[2 * i + 1] = t.y;
     }
+    int holes = 0;
+#pragma unroll
+    for (int i = 0; i < OPL; ++i) holes += ov[i] == kHole ? 1 : 0;
+    int incl_h = holes;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl_h, o);
+        if (lane >= o) incl_h += v;
+    }
+    // (coarse depths that are not sorted collide and leave more than NNEW holes: the index then runs on into
+    //  outm, which follows ss inside the row, so the read stays inside this warp's shared memory)
+    uint32_t sp = smem_addr(row.ss) + (incl_h - holes) * 4;
+#pragma unroll
+    for (int i = 0; i < OPL; ++i) {
+        if (ov[i] == kHole) {
+            ov[i] = __float_as_uint(lds_f32(sp));
+            sp += 4;
+        }
+    }
+    // back through the row so that the HBM stores are coalesced (lane-contiguous slots are 4*OPL bytes apart)
+#pragma unroll
+    for (int i = 0; i < OPL / 2; ++i)
+        *reinterpret_cast<uint2*>(row.outm + lane * OPL + 2 * i) = make_uint2(ov[2 * i], ov[2 * i + 1]);
+    __syncwarp();
+    float* dst = z_fine + (size_t)ray * TOT;
+#pragma unroll
+    for (int i = 0; i < TOT / 64; ++i)
+        *reinterpret_cast<float2*>(dst + i * 64 + 2 * lane) = *reinterpret_cast<const float2*>(row.outm + i * 64 + 2 * lane);
 }
 
 }  // namespace snerf

@@ -25,9 +25,12 @@ def timeit(fn, iters=10):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
+# optional quick mode: SCAN_S=64,256 SCAN_LOGN=20,22 restrict the sweep
+SS = tuple(int(x) for x in os.environ.get('SCAN_S', '64,128,256').split(','))
+LOGNS = tuple(int(x) for x in os.environ.get('SCAN_LOGN', '16,18,20,22').split(','))
 rows = []
-for s in (64, 128, 256):
-    for logn in (16, 18, 20, 22):
+for s in SS:
+    for logn in LOGNS:
         n = 1 << logn
         if n * s * 4 * 9 > 60e9:
             continue
@@ -50,6 +53,10 @@ for s in (64, 128, 256):
             u = torch.rand((n, 128), device=DEV, generator=g)
             t = timeit(lambda: ops.sample_fine(z, w, u))
             rows.append(('sample_pdf+merge (u supplied)', 64, n, 1792 * n, t))
+            us = torch.sort(u, -1)[0].contiguous()
+            t = timeit(lambda: ops.sample_fine(z, w, us))
+            rows.append(('sample_pdf+merge (sorted u supplied)', 64, n, 1792 * n, t))
+            del us
             lin = torch.linspace(0, 1, 128).to(DEV)
             t = timeit(lambda: ops.sample_fine(z, w, lin))
             rows.append(('sample_pdf+merge (linspace row)', 64, n, 1280 * n, t))
