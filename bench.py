@@ -123,6 +123,15 @@ def training_loss(out, target, tdepth):
     return sum(((out[a] - target) ** 2).mean() + 0.1 * ((out[b] - tdepth) ** 2).mean() for a, b in STREAMS)
 
 
+def fused_training_loss(out, target, tdepth):
+    """The same function as training_loss in one forward and one backward launch (snerf_ray_losses_*: MSE01-03 /
+    SparseDepthMSE01-03 semantics with every ray masked in): 8 streams, rgb weight 1, depth weight 0.1."""
+    from simplenerf_b200.loss_functions import ray_losses
+    preds = [out[a] for a, _ in STREAMS] + [out[b] for _, b in STREAMS]
+    n = len(STREAMS)
+    return ray_losses(preds, [target] * n + [tdepth] * n, [None] * (2 * n), [1.0] * n + [0.1] * n)[-1]
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------
@@ -224,7 +233,7 @@ def run_ours(args):
     def step(batch):
         opt.zero_grad(set_to_none=True)
         out = model(batch)
-        loss = training_loss(out, batch['target_rgb'], batch['target_depth'])
+        loss = (training_loss if args.torch_loss else fused_training_loss)(out, batch['target_rgb'], batch['target_depth'])
         loss.backward()
         if exchange is not None:   # ray-sharded data parallel: sum of shard gradients / world == gradient of the global mean loss;
             exchange.finish()      # the buckets were launched from autograd hooks while the backward pass was still running
@@ -406,6 +415,7 @@ def main():
     ap.add_argument('--no-render', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--quick-cpu', action='store_true')
+    ap.add_argument('--torch-loss', action='store_true', help='eager torch loss (8 masked means, ~80 launches) instead of snerf_ray_losses_*')
     ap.add_argument('--torch-adam', action='store_true', help='torch.optim.Adam(fused=True) instead of simplenerf_b200.optim.FusedAdam')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -157,6 +157,30 @@ int snerf_adam_step(float* const* params, const float* const* grads, float* cons
                     const long long* numel, int n_tensors, float lr, float beta1, float beta2, float eps, int step,
                     void* stream);
 
+/* ---- (f) N3, the masked per-ray losses of the training step ---------------------------------------
+ * One "stream" = one masked mean-squared error of the reference's loss modules: MSE01/02/03.compute_mse
+ * (src/loss_functions/MSE01.py:53-67: pred[mask] vs target[mask], mean over channels then over rays) and
+ * SparseDepthMSE01/02/03.compute_depth_loss (SparseDepthMSE01.py:58-71, one channel).  The weighted sum is
+ * LossComputer.compute_losses (LossComputer01.py:33-52).  The table is a HOST array; its pointers are device pointers. */
+#define SNERF_LOSS_MAX_STREAMS 8
+typedef struct snerf_loss_stream {
+    const float* pred;    /* [n_rays, channels]                                       */
+    const float* target;  /* [n_rays, channels]                                       */
+    const uint8_t* mask;  /* [n_rays] bool; nullable = every ray                      */
+    float* grad;          /* [n_rays, channels], written by the backward call only    */
+    int32_t channels;     /* 3 (rgb) or 1 (depth); 1..4                               */
+    float weight;         /* loss weight (LossComputer.get_loss_weight)               */
+} snerf_loss_stream;
+size_t snerf_ray_losses_workspace_bytes(void);
+/* values[n_streams + 1]: the mean of every stream (0 when its mask is empty), then the weighted total;
+ * counts[n_streams]: masked-in rays per stream.  The workspace must be zeroed once after allocation.                 */
+int snerf_ray_losses_forward(const snerf_loss_stream* streams, int n_streams, int n_rays, float* values,
+                             int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+/* grad_values[n_streams + 1] (device): incoming gradient of `values`; stream s receives
+ * (grad_values[s] + grad_values[n_streams] * weight_s) * 2 (pred - target) / (count_s * channels) on masked rays, else 0. */
+int snerf_ray_losses_backward(const snerf_loss_stream* streams, int n_streams, int n_rays, const int32_t* counts,
+                              const float* grad_values, void* stream);
+
 /* Self-test of the tcgen05 GEMM building blocks against a CUDA-core GEMM (used by tests).
  * Returns SNERF_OK and writes the max abs error of each mode to host_max_err[4].               */
 int snerf_tensor_selftest(float* host_max_err, void* stream);

@@ -18,6 +18,12 @@ class MlpDesc(C.Structure):
                                          'view_width', 'head_out')]
 
 
+class LossStream(C.Structure):
+    _fields_ = [('pred', C.c_void_p), ('target', C.c_void_p), ('mask', C.c_void_p), ('grad', C.c_void_p),
+                ('channels', C.c_int32), ('weight', C.c_float)]
+
+
+LOSS_MAX_STREAMS = 8
 _fp = C.c_void_p   # device pointers travel as integers
 _SIGNATURES = {
     'snerf_abi_version': (C.c_int, []),
@@ -39,6 +45,9 @@ _SIGNATURES = {
     'snerf_postprocess_frame': (C.c_int, [_fp, _fp, C.POINTER(_fp), C.c_int, C.c_longlong, _fp]),
     'snerf_adam_step': (C.c_int, [C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_fp), C.POINTER(C.c_longlong), C.c_int,
                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _fp]),
+    'snerf_ray_losses_workspace_bytes': (C.c_size_t, []),
+    'snerf_ray_losses_forward': (C.c_int, [C.POINTER(LossStream), C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
+    'snerf_ray_losses_backward': (C.c_int, [C.POINTER(LossStream), C.c_int, C.c_int, _fp, _fp, _fp]),
     'snerf_tensor_selftest': (C.c_int, [C.POINTER(C.c_float), _fp]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -1,0 +1,172 @@
+"""Host mirror of the reference's loss front end for the masked per-ray losses.
+
+`FusedLossComputer(configs).compute_losses(input_dict, output_dict)` has the contract of
+`loss_functions.LossComputer01.LossComputer.compute_losses` (src/loss_functions/LossComputer01.py:33-52): it returns
+`{loss_name: {'loss_value': tensor}, ..., 'TotalLoss': tensor}` and `TotalLoss.backward()` fills the gradients of the
+model outputs.  The six losses that are plain masked means -- MSE01/02/03 (MSE01.py:26-67) and SparseDepthMSE01/02/03
+(SparseDepthMSE01.py:26-71) -- run as ONE forward launch and ONE backward launch of `snerf_ray_losses_*` instead of
+~20 eager kernels and a boolean-mask gather (a device synchronisation) per stream.  Every other configured loss
+(the patch-reprojection losses, which the shipped configuration weights with 0 for the first 10 000 iterations) is
+taken from `extra_losses` (name -> object with the reference's `compute_loss` signature, e.g. the reference's own
+instance) and added with torch; a configured loss that is neither fused nor supplied raises unless its weight at this
+iteration is 0.  There is no CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib, ops
+
+# loss name -> (kind, config sub-key of configs['model'] holding its MLPs or None for the main model, output prefix)
+_RGB = {'MSE01': (None, ''), 'MSE02': ('points_augmentation', 'points_augmentation_'),
+        'MSE03': ('views_augmentation', 'views_augmentation_')}
+_DEPTH = {'SparseDepthMSE01': (None, ''), 'SparseDepthMSE02': ('points_augmentation', 'points_augmentation_'),
+          'SparseDepthMSE03': ('views_augmentation', 'views_augmentation_')}
+FUSED_LOSSES = tuple(_RGB) + tuple(_DEPTH)
+
+
+def get_loss_weight(loss_configs: dict, iter_num: int) -> float:
+    """LossComputer.get_loss_weight (LossComputer01.py:54-69)."""
+    if 'weight' in loss_configs:
+        return loss_configs['weight']
+    if 'iter_weights' in loss_configs:
+        for key in sorted((int(k) for k in loss_configs['iter_weights']), reverse=True):
+            if iter_num >= key:
+                return loss_configs['iter_weights'][str(key)]
+    raise RuntimeError(f"loss_weight is None for {loss_configs.get('name')} at iter {iter_num}")
+
+
+def stream_plan(configs: dict, loss_name: str, input_dict: dict, output_dict: dict) -> List[Tuple[str, str, str]]:
+    """The (prediction key, target key, mask key) triples one reference loss module reads, in its order."""
+    model = configs['model']
+    if loss_name in _RGB:
+        sub, prefix = _RGB[loss_name]
+        mlps = model if sub is None else model[sub]
+        plan = []
+        for level in ('coarse', 'fine'):                                                     # MSE01.py:32-45, MSE02.py:32-45
+            key = f'{prefix}rgb_{level}'
+            if f'{level}_mlp' in mlps and (sub is None or key in output_dict):
+                plan.append((key, 'target_rgb', 'indices_mask_nerf'))
+        return plan
+    sub, prefix = _DEPTH[loss_name]
+    if 'indices_mask_sparse_depth' not in input_dict:                                        # SparseDepthMSE01.py:31-32
+        return []
+    mlps = model if sub is None else model[sub]
+    # SparseDepthMSE02.py:37-45 reads depth_fine (not the augmented fine depth) when an augmented fine MLP exists
+    key = 'depth_fine' if 'fine_mlp' in mlps else f'{prefix}depth_coarse'
+    return [(key, 'sparse_depth_values', 'indices_mask_sparse_depth')]
+
+
+class _RayLosses(torch.autograd.Function):
+    """values[n+1] = per-stream masked means, then their weighted sum; preds are differentiable."""
+
+    @staticmethod
+    def forward(ctx, targets, masks, weights, workspace, *preds):
+        n_streams, n_rays = len(preds), preds[0].shape[0]
+        dev = preds[0].device
+        table = (_lib.LossStream * n_streams)()
+        keep = []
+        for s, (p, t, m, w) in enumerate(zip(preds, targets, masks, weights)):
+            p32, t32 = ops._f32(p).reshape(n_rays, -1), ops._f32(t).reshape(n_rays, -1)
+            if p32.shape != t32.shape:
+                raise RuntimeError(f'stream {s}: prediction {tuple(p.shape)} vs target {tuple(t.shape)}')
+            m8 = None
+            if m is not None:
+                m8 = m.detach().contiguous().view(torch.uint8) if m.dtype == torch.bool else m.detach().to(torch.uint8).contiguous()
+                if m8.shape[0] != n_rays:
+                    raise RuntimeError(f'stream {s}: mask of {m8.shape[0]} rays for {n_rays} rays')
+            keep.append((p32, t32, m8))
+            table[s].pred, table[s].target = ops._ptr(p32), ops._ptr(t32)
+            table[s].mask = ops._ptr(m8, torch.uint8)
+            table[s].grad = None
+            table[s].channels, table[s].weight = p32.shape[1], float(w)
+        values = torch.empty(n_streams + 1, device=dev, dtype=torch.float32)
+        counts = torch.empty(n_streams, device=dev, dtype=torch.int32)
+        ops.LAUNCHES['count'] += 1
+        _lib.check(_lib.load().snerf_ray_losses_forward(table, n_streams, n_rays, ops._ptr(values), ops._ptr(counts, torch.int32),
+                                                        ops._ptr(workspace, torch.uint8), workspace.numel(), ops._stream()),
+                   'snerf_ray_losses_forward')
+        ctx.keep, ctx.counts, ctx.weights, ctx.shapes = keep, counts, [float(w) for w in weights], [p.shape for p in preds]
+        return values
+
+    @staticmethod
+    def backward(ctx, g_values):
+        n_streams, n_rays = len(ctx.keep), ctx.keep[0][0].shape[0]
+        table = (_lib.LossStream * n_streams)()
+        grads = []
+        for s, (p32, t32, m8) in enumerate(ctx.keep):
+            g = torch.empty_like(p32)
+            grads.append(g)
+            table[s].pred, table[s].target, table[s].mask = ops._ptr(p32), ops._ptr(t32), ops._ptr(m8, torch.uint8)
+            table[s].grad, table[s].channels, table[s].weight = ops._ptr(g), p32.shape[1], ctx.weights[s]
+        ops.LAUNCHES['count'] += 1
+        _lib.check(_lib.load().snerf_ray_losses_backward(table, n_streams, n_rays, ops._ptr(ctx.counts, torch.int32),
+                                                         ops._ptr(ops._f32(g_values)), ops._stream()), 'snerf_ray_losses_backward')
+        return (None, None, None, None) + tuple(g.reshape(shape) for g, shape in zip(grads, ctx.shapes))
+
+
+_WORKSPACES: Dict[torch.device, torch.Tensor] = {}
+
+
+def _workspace(dev: torch.device) -> torch.Tensor:
+    if dev not in _WORKSPACES:      # zeroed once; the kernel leaves its ticket counter at zero
+        _WORKSPACES[dev] = torch.zeros(_lib.load().snerf_ray_losses_workspace_bytes(), device=dev, dtype=torch.uint8)
+    return _WORKSPACES[dev]
+
+
+def ray_losses(preds: Sequence[torch.Tensor], targets: Sequence[torch.Tensor], masks: Sequence[Optional[torch.Tensor]],
+               weights: Sequence[float]) -> torch.Tensor:
+    """values[len(preds) + 1]: masked mean squared error of every stream, then sum_s weights[s] * values[s]."""
+    if not 1 <= len(preds) <= _lib.LOSS_MAX_STREAMS:
+        raise RuntimeError(f'{len(preds)} loss streams (1..{_lib.LOSS_MAX_STREAMS} per call)')
+    if not preds[0].is_cuda:
+        raise RuntimeError('simplenerf_b200 kernels need CUDA tensors (no CPU fallback exists)')
+    return _RayLosses.apply(list(targets), list(masks), list(weights), _workspace(preds[0].device), *preds)
+
+
+class FusedLossComputer:
+    def __init__(self, configs: dict, extra_losses: Optional[dict] = None):
+        self.configs = configs
+        self.loss_configs = {lc['name']: lc for lc in configs['losses']}
+        self.extra_losses = dict(extra_losses or {})
+
+    def compute_losses(self, input_dict: dict, output_dict: dict, return_loss_maps: bool = False) -> dict:
+        if return_loss_maps:
+            raise NotImplementedError('loss maps are a validation-time output; use the reference LossComputer for them')
+        iter_num = input_dict['iter_num']
+        preds, targets, masks, weights, owner = [], [], [], [], []
+        extra_total = 0
+        loss_values: Dict[str, dict] = {}
+        for name, lc in self.loss_configs.items():
+            weight = get_loss_weight(lc, iter_num)
+            if name in FUSED_LOSSES:
+                plan = stream_plan(self.configs, name, input_dict, output_dict)
+                for pred_key, target_key, mask_key in plan:
+                    target = input_dict[target_key]
+                    preds.append(output_dict[pred_key])
+                    targets.append(target[:, 0] if target_key == 'sparse_depth_values' else target)   # SparseDepthMSE01.py:34
+                    masks.append(input_dict[mask_key])
+                    weights.append(weight)
+                    owner.append(name)
+                if not plan:
+                    loss_values[name] = {'loss_value': torch.zeros((), device=input_dict['rays_o'].device)}
+            elif name in self.extra_losses:
+                loss_dict = self.extra_losses[name].compute_loss(input_dict, output_dict, return_loss_maps=False)
+                if loss_dict is not None:                                                     # LossComputer01.py:46
+                    loss_values[name] = loss_dict
+                    extra_total = extra_total + weight * loss_dict['loss_value']
+            elif weight != 0:
+                raise RuntimeError(f'Unknown Loss Function: {name} (not fused; pass an object for it in extra_losses)')
+        total = extra_total
+        for i in range(0, len(preds), _lib.LOSS_MAX_STREAMS):
+            sl = slice(i, i + _lib.LOSS_MAX_STREAMS)
+            values = ray_losses(preds[sl], targets[sl], masks[sl], weights[sl])
+            for j, name in enumerate(owner[sl]):        # a module with a coarse and a fine stream reports their sum (MSE01.py:35,42)
+                prev = loss_values.get(name, {}).get('loss_value')
+                loss_values[name] = {'loss_value': values[j] if prev is None else prev + values[j]}
+            total = total + values[-1]
+        loss_values['TotalLoss'] = total
+        return loss_values
