@@ -181,6 +181,44 @@ int snerf_ray_losses_forward(const snerf_loss_stream* streams, int n_streams, in
 int snerf_ray_losses_backward(const snerf_loss_stream* streams, int n_streams, int n_rays, const int32_t* counts,
                               const float* grad_values, void* stream);
 
+/* Patch-reprojection depth losses: compute_loss_nerf of PointsAugmentationDepthLoss02 / ViewsAugmentationDepthLoss02 /
+ * CoarseFineConsistencyLoss02 (src/loss_functions/PointsAugmentationDepthLoss02.py:98-176, identical in the three
+ * modules; reprojection: src/utils/CommonUtils01.py:45-72).  One call compares ONE main depth with up to 4 other
+ * depths.  Host struct; every pointer is a device pointer.
+ *   proj[v]    = intrinsics[0] @ diag(1,-1,-1) @ poses[v,:3,:3]^T  (row-major 3x3),  origins[v] = poses[v,:3,3],
+ *   closest[v] = index of the second smallest camera distance from view v (:126-130).
+ * Default behaviour is the reference's: through its in-place masking on detach() aliases (:204-206) only the term that
+ * pulls the MAIN depth towards the other depth survives; SNERF_REPROJ_SYMMETRIC adds the other term.              */
+#define SNERF_REPROJ_MAX_OTHERS 4
+#define SNERF_REPROJ_SYMMETRIC 1u
+typedef struct snerf_reproj_args {
+    const float* depth_main;                            /* [n_rays]                                   */
+    const float* depth_other[SNERF_REPROJ_MAX_OTHERS];  /* [n_rays] each                              */
+    float* grad_main;                                   /* backward output [n_rays]                   */
+    float* grad_other[SNERF_REPROJ_MAX_OTHERS];         /* backward outputs, nullable                 */
+    float weight[SNERF_REPROJ_MAX_OTHERS];              /* loss weights                               */
+    int32_t n_others;
+    const float* rays_o;                                /* [n_rays,3]                                 */
+    const float* rays_d;                                /* [n_rays,3]                                 */
+    const int32_t* pixel_id;                            /* [n_rays,3] = (view, x, y)                  */
+    const uint8_t* mask_nerf;                           /* [n_rays] bool; nullable = every ray        */
+    const float* images;                                /* [n_views, height, width, 3]                */
+    const float* proj;                                  /* [n_views, 9]                               */
+    const float* origins;                               /* [n_views, 3]                               */
+    const int32_t* closest;                             /* [n_views]                                  */
+    int32_t n_views, height, width;
+    int32_t half_patch;                                 /* patch_size // 2 (square patches, <= 2)     */
+    float rmse_threshold;
+    uint32_t flags;
+} snerf_reproj_args;
+/* codes[n_others, n_rays]: bit 0 = the main model is the more accurate one on this ray, bit 1 = the other model is;
+ * values[n_others + 1]: loss per pair, then the weighted total; counts[1]: rays with mask_nerf.
+ * Workspace: snerf_ray_losses_workspace_bytes(), zeroed once.                                                      */
+int snerf_reprojection_losses_forward(const snerf_reproj_args* args, int n_rays, uint8_t* codes, float* values,
+                                      int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+int snerf_reprojection_losses_backward(const snerf_reproj_args* args, int n_rays, const uint8_t* codes,
+                                       const int32_t* counts, const float* grad_values, void* stream);
+
 /* Self-test of the tcgen05 GEMM building blocks against a CUDA-core GEMM (used by tests).
  * Returns SNERF_OK and writes the max abs error of each mode to host_max_err[4].               */
 int snerf_tensor_selftest(float* host_max_err, void* stream);

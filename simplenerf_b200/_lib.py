@@ -23,7 +23,17 @@ class LossStream(C.Structure):
                 ('channels', C.c_int32), ('weight', C.c_float)]
 
 
+class ReprojArgs(C.Structure):
+    _fields_ = [('depth_main', C.c_void_p), ('depth_other', C.c_void_p * 4), ('grad_main', C.c_void_p), ('grad_other', C.c_void_p * 4),
+                ('weight', C.c_float * 4), ('n_others', C.c_int32), ('rays_o', C.c_void_p), ('rays_d', C.c_void_p),
+                ('pixel_id', C.c_void_p), ('mask_nerf', C.c_void_p), ('images', C.c_void_p), ('proj', C.c_void_p),
+                ('origins', C.c_void_p), ('closest', C.c_void_p), ('n_views', C.c_int32), ('height', C.c_int32),
+                ('width', C.c_int32), ('half_patch', C.c_int32), ('rmse_threshold', C.c_float), ('flags', C.c_uint32)]
+
+
 LOSS_MAX_STREAMS = 8
+REPROJ_MAX_OTHERS = 4
+REPROJ_SYMMETRIC = 1
 _fp = C.c_void_p   # device pointers travel as integers
 _SIGNATURES = {
     'snerf_abi_version': (C.c_int, []),
@@ -48,6 +58,8 @@ _SIGNATURES = {
     'snerf_ray_losses_workspace_bytes': (C.c_size_t, []),
     'snerf_ray_losses_forward': (C.c_int, [C.POINTER(LossStream), C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     'snerf_ray_losses_backward': (C.c_int, [C.POINTER(LossStream), C.c_int, C.c_int, _fp, _fp, _fp]),
+    'snerf_reprojection_losses_forward': (C.c_int, [C.POINTER(ReprojArgs), C.c_int, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    'snerf_reprojection_losses_backward': (C.c_int, [C.POINTER(ReprojArgs), C.c_int, _fp, _fp, _fp, _fp]),
     'snerf_tensor_selftest': (C.c_int, [C.POINTER(C.c_float), _fp]),
 }
 EXPORTS = tuple(_SIGNATURES)

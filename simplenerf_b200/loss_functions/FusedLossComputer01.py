@@ -5,9 +5,11 @@
 `{loss_name: {'loss_value': tensor}, ..., 'TotalLoss': tensor}` and `TotalLoss.backward()` fills the gradients of the
 model outputs.  The six losses that are plain masked means -- MSE01/02/03 (MSE01.py:26-67) and SparseDepthMSE01/02/03
 (SparseDepthMSE01.py:26-71) -- run as ONE forward launch and ONE backward launch of `snerf_ray_losses_*` instead of
-~20 eager kernels and a boolean-mask gather (a device synchronisation) per stream.  Every other configured loss
-(the patch-reprojection losses, which the shipped configuration weights with 0 for the first 10 000 iterations) is
-taken from `extra_losses` (name -> object with the reference's `compute_loss` signature, e.g. the reference's own
+~20 eager kernels and a boolean-mask gather (a device synchronisation) per stream; the three patch-reprojection depth
+losses PointsAugmentationDepthLoss02 / ViewsAugmentationDepthLoss02 / CoarseFineConsistencyLoss02 share one forward and
+one backward launch of `snerf_reprojection_losses_*` (one warp per ray; the source patch and the main model's patch are
+gathered once for all three).  Every other configured loss
+is taken from `extra_losses` (name -> object with the reference's `compute_loss` signature, e.g. the reference's own
 instance) and added with torch; a configured loss that is neither fused nor supplied raises unless its weight at this
 iteration is 0.  There is no CPU path: tensors must live on a CUDA device.
 """
@@ -25,6 +27,10 @@ _RGB = {'MSE01': (None, ''), 'MSE02': ('points_augmentation', 'points_augmentati
         'MSE03': ('views_augmentation', 'views_augmentation_')}
 _DEPTH = {'SparseDepthMSE01': (None, ''), 'SparseDepthMSE02': ('points_augmentation', 'points_augmentation_'),
           'SparseDepthMSE03': ('views_augmentation', 'views_augmentation_')}
+# patch-reprojection depth losses: name -> (config sub-key of the other model or None for the fine model, other depth key)
+_REPROJ = {'PointsAugmentationDepthLoss02': ('points_augmentation', 'points_augmentation_depth_coarse'),
+           'ViewsAugmentationDepthLoss02': ('views_augmentation', 'views_augmentation_depth_coarse'),
+           'CoarseFineConsistencyLoss02': (None, 'depth_fine')}
 FUSED_LOSSES = tuple(_RGB) + tuple(_DEPTH)
 
 
@@ -108,6 +114,95 @@ class _RayLosses(torch.autograd.Function):
         return (None, None, None, None) + tuple(g.reshape(shape) for g, shape in zip(grads, ctx.shapes))
 
 
+class _ReprojectionLosses(torch.autograd.Function):
+    """values[k+1] = the reprojection loss of (main, other_k) for every k, then their weighted sum."""
+
+    @staticmethod
+    def forward(ctx, views, rays, weights, half_patch, threshold, symmetric, workspace, depth_main, *depth_others):
+        n_rays, k = depth_main.shape[0], len(depth_others)
+        dev = depth_main.device
+        main32 = ops._f32(depth_main).reshape(-1)
+        others32 = [ops._f32(d).reshape(-1) for d in depth_others]
+        args = _lib.ReprojArgs()
+        args.depth_main, args.n_others = ops._ptr(main32), k
+        for i, d in enumerate(others32):
+            if d.shape[0] != n_rays:
+                raise RuntimeError(f'other depth {i}: {d.shape[0]} rays for {n_rays}')
+            args.depth_other[i], args.weight[i] = ops._ptr(d), float(weights[i])
+        rays_o, rays_d, pixel_id, mask = rays
+        rays_o, rays_d = ops._f32(rays_o), ops._f32(rays_d)
+        pixel_id = pixel_id.detach().to(torch.int32).contiguous()
+        m8 = None if mask is None else (mask.detach().contiguous().view(torch.uint8) if mask.dtype == torch.bool
+                                        else mask.detach().to(torch.uint8).contiguous())
+        images, proj, origins, closest = views
+        args.rays_o, args.rays_d, args.pixel_id = ops._ptr(rays_o), ops._ptr(rays_d), ops._ptr(pixel_id, torch.int32)
+        args.mask_nerf, args.images = ops._ptr(m8, torch.uint8), ops._ptr(images)
+        args.proj, args.origins, args.closest = ops._ptr(proj), ops._ptr(origins), ops._ptr(closest, torch.int32)
+        args.n_views, args.height, args.width = images.shape[0], images.shape[1], images.shape[2]
+        args.half_patch, args.rmse_threshold = int(half_patch), float(threshold)
+        args.flags = _lib.REPROJ_SYMMETRIC if symmetric else 0
+        codes = torch.empty((k, n_rays), device=dev, dtype=torch.uint8)
+        values = torch.empty(k + 1, device=dev, dtype=torch.float32)
+        counts = torch.empty(1, device=dev, dtype=torch.int32)
+        ops.LAUNCHES['count'] += 1
+        _lib.check(_lib.load().snerf_reprojection_losses_forward(C.byref(args), n_rays, ops._ptr(codes, torch.uint8), ops._ptr(values),
+                                                                 ops._ptr(counts, torch.int32), ops._ptr(workspace, torch.uint8),
+                                                                 workspace.numel(), ops._stream()),
+                   'snerf_reprojection_losses_forward')
+        ctx.keep = (main32, others32, codes, counts, [float(w) for w in weights], bool(symmetric))
+        ctx.shapes = [depth_main.shape] + [d.shape for d in depth_others]
+        ctx.mark_non_differentiable(codes)
+        return values, codes
+
+    @staticmethod
+    def backward(ctx, g_values, _g_codes):
+        main32, others32, codes, counts, weights, symmetric = ctx.keep
+        n_rays, k = main32.shape[0], len(others32)
+        args = _lib.ReprojArgs()
+        g_main = torch.empty_like(main32)
+        g_others = [torch.empty_like(d) for d in others32]
+        args.depth_main, args.grad_main, args.n_others = ops._ptr(main32), ops._ptr(g_main), k
+        for i, (d, g) in enumerate(zip(others32, g_others)):
+            args.depth_other[i], args.grad_other[i], args.weight[i] = ops._ptr(d), ops._ptr(g), weights[i]
+        args.flags = _lib.REPROJ_SYMMETRIC if symmetric else 0
+        ops.LAUNCHES['count'] += 1
+        _lib.check(_lib.load().snerf_reprojection_losses_backward(C.byref(args), n_rays, ops._ptr(codes, torch.uint8),
+                                                                  ops._ptr(counts, torch.int32), ops._ptr(ops._f32(g_values)),
+                                                                  ops._stream()), 'snerf_reprojection_losses_backward')
+        grads = [g.reshape(shape) for g, shape in zip([g_main] + g_others, ctx.shapes)]
+        return (None,) * 7 + tuple(grads)
+
+
+def view_tables(poses: torch.Tensor, intrinsics: torch.Tensor):
+    """Per-view tables of the reprojection kernel, with the reference's own torch expressions:
+    proj[v] = intrinsics[:1] @ permuter @ R_v^T (CommonUtils01.py:60-69), origins, and the nearest other view
+    (second smallest camera distance, PointsAugmentationDepthLoss02.py:126-130)."""
+    permuter = torch.eye(3, device=poses.device)
+    permuter[1:] *= -1
+    proj = (intrinsics[:1].float() @ permuter[None] @ poses[:, :3, :3].float().transpose(1, 2)).reshape(-1, 9).contiguous()
+    origins = poses[:, :3, 3].float().contiguous()
+    dist = torch.sqrt(torch.sum(torch.square(origins[:, None, :] - origins[None, :, :]), dim=2))
+    closest = torch.kthvalue(dist, 2, dim=1)[1].to(torch.int32).contiguous()
+    return proj, origins, closest
+
+
+def reprojection_losses(depth_main, depth_others, weights, rays_o, rays_d, pixel_id, mask_nerf, images, poses, intrinsics,
+                        patch_size=(5, 5), rmse_threshold=0.1, symmetric=False, tables=None):
+    """values[len(depth_others) + 1] (loss per pair, then the weighted total) and codes[len(depth_others), N]
+    (bit 0: the main model is the more accurate one on the ray, bit 1: the other model is)."""
+    if not depth_main.is_cuda:
+        raise RuntimeError('simplenerf_b200 kernels need CUDA tensors (no CPU fallback exists)')
+    if not 1 <= len(depth_others) <= _lib.REPROJ_MAX_OTHERS:
+        raise RuntimeError(f'{len(depth_others)} other depths (1..{_lib.REPROJ_MAX_OTHERS} per call)')
+    px, py = patch_size
+    if px != py:
+        raise NotImplementedError('square patches only (the reference pads W by hpy and H by hpx, :156)')
+    proj, origins, closest = tables if tables is not None else view_tables(poses, intrinsics)
+    views = (ops._f32(images), proj, origins, closest)
+    return _ReprojectionLosses.apply(views, (rays_o, rays_d, pixel_id, mask_nerf), list(weights), px // 2, rmse_threshold,
+                                     symmetric, _workspace(depth_main.device), depth_main, *depth_others)
+
+
 _WORKSPACES: Dict[torch.device, torch.Tensor] = {}
 
 
@@ -128,16 +223,35 @@ def ray_losses(preds: Sequence[torch.Tensor], targets: Sequence[torch.Tensor], m
 
 
 class FusedLossComputer:
-    def __init__(self, configs: dict, extra_losses: Optional[dict] = None):
+    def __init__(self, configs: dict, extra_losses: Optional[dict] = None, symmetric_reprojection: bool = False):
         self.configs = configs
         self.loss_configs = {lc['name']: lc for lc in configs['losses']}
         self.extra_losses = dict(extra_losses or {})
+        self.symmetric_reprojection = symmetric_reprojection     # False = what the reference computes (see losses.cu)
+        self._tables = None                                      # (key, per-view tables) of the last poses seen
+
+    def _view_tables(self, poses, intrinsics):
+        key = (poses.data_ptr(), poses._version, intrinsics.data_ptr(), intrinsics._version, tuple(poses.shape))
+        if self._tables is None or self._tables[0] != key:
+            self._tables = (key, view_tables(poses, intrinsics))
+        return self._tables[1]
+
+    def _reprojection_plan(self, name: str):
+        """(other depth key) if the reference module would compute a coarse pair, else None (:44-51, CoarseFine :34-37)."""
+        model = self.configs['model']
+        sub, other_key = _REPROJ[name]
+        if sub is None:
+            return other_key if ('coarse_mlp' in model and 'fine_mlp' in model) else None
+        if 'fine_mlp' in model and 'fine_mlp' in model[sub]:
+            raise NotImplementedError(f'{name}: fine-level augmentation pairs are not built (never enabled in a shipped config)')
+        return other_key if ('coarse_mlp' in model and 'coarse_mlp' in model[sub]) else None
 
     def compute_losses(self, input_dict: dict, output_dict: dict, return_loss_maps: bool = False) -> dict:
         if return_loss_maps:
             raise NotImplementedError('loss maps are a validation-time output; use the reference LossComputer for them')
         iter_num = input_dict['iter_num']
         preds, targets, masks, weights, owner = [], [], [], [], []
+        reproj: Dict[tuple, list] = {}
         extra_total = 0
         loss_values: Dict[str, dict] = {}
         for name, lc in self.loss_configs.items():
@@ -153,6 +267,21 @@ class FusedLossComputer:
                     owner.append(name)
                 if not plan:
                     loss_values[name] = {'loss_value': torch.zeros((), device=input_dict['rays_o'].device)}
+            elif name in _REPROJ and name not in self.extra_losses:
+                other_key = self._reprojection_plan(name)
+                if other_key is None:
+                    loss_values[name] = {'loss_value': torch.zeros((), device=input_dict['rays_o'].device)}
+                    continue
+                setting = (tuple(lc['patch_size']), float(lc['rmse_threshold']))
+                reproj.setdefault(setting, []).append((name, other_key, weight))
+                if name == 'CoarseFineConsistencyLoss02' and 'sparse_depth' in self.configs['data_loader'] \
+                        and input_dict.get('indices_mask_sparse_depth') is not None:
+                    # compute_loss_sd (CoarseFineConsistencyLoss02.py:174-189): the fine depth supervises the coarse depth
+                    preds.append(output_dict['depth_coarse'])
+                    targets.append(output_dict['depth_fine'].detach())
+                    masks.append(input_dict['indices_mask_sparse_depth'])
+                    weights.append(weight)
+                    owner.append(name)
             elif name in self.extra_losses:
                 loss_dict = self.extra_losses[name].compute_loss(input_dict, output_dict, return_loss_maps=False)
                 if loss_dict is not None:                                                     # LossComputer01.py:46
@@ -168,5 +297,20 @@ class FusedLossComputer:
                 prev = loss_values.get(name, {}).get('loss_value')
                 loss_values[name] = {'loss_value': values[j] if prev is None else prev + values[j]}
             total = total + values[-1]
+        if reproj:
+            cd = input_dict['common_data']
+            poses, images, intrinsics = cd['poses'], cd['images'], cd['intrinsics']
+            if poses.dim() == 4:      # still carrying the replica dimension that LossComputer01.py:34-38 strips
+                poses, images, intrinsics = poses[0], images[0], intrinsics[0]
+            tables = self._view_tables(poses, intrinsics)
+            for (patch, threshold), items in reproj.items():
+                values, _ = reprojection_losses(output_dict['depth_coarse'], [output_dict[k] for _, k, _ in items],
+                                                [w for _, _, w in items], input_dict['rays_o'], input_dict['rays_d'],
+                                                input_dict['pixel_id'], input_dict['indices_mask_nerf'], images, poses, intrinsics,
+                                                patch, threshold, self.symmetric_reprojection, tables)
+                for j, (name, _, _) in enumerate(items):
+                    prev = loss_values.get(name, {}).get('loss_value')
+                    loss_values[name] = {'loss_value': values[j] if prev is None else prev + values[j]}
+                total = total + values[-1]
         loss_values['TotalLoss'] = total
         return loss_values
