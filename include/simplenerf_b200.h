@@ -219,6 +219,21 @@ int snerf_reprojection_losses_forward(const snerf_reproj_args* args, int n_rays,
 int snerf_reprojection_losses_backward(const snerf_reproj_args* args, int n_rays, const uint8_t* codes,
                                        const int32_t* counts, const float* grad_values, void* stream);
 
+/* ---- (f) N3, batch assembly: the per-ray tables of one training batch in one launch ---------------
+ * Replaces the `-1 * ones` + `t[mask] = table[indices[mask]]` pairs of load_nerf_cached_batch
+ * (src/data_preprocessors/DataPreprocessor01.py:572-620) and load_sparse_depth_cached_batch (:655-700):
+ *   dst[i, :] = (mask == NULL || mask[i]) ? src[indices[i], :] : fill.   Rows are row_bytes wide (a multiple of 4),
+ * fill_bits is the 32-bit pattern of the fill value (-1.0f or int32 -1).  Host array of tables, device pointers.        */
+#define SNERF_GATHER_MAX_TABLES 24
+typedef struct snerf_gather_table {
+    const void* src;      /* [n_source_rows, row_bytes]              */
+    void* dst;            /* [n_rows, row_bytes]                     */
+    const uint8_t* mask;  /* [n_rows] bool; nullable = every row     */
+    int32_t row_bytes;
+    uint32_t fill_bits;
+} snerf_gather_table;
+int snerf_gather_rows(const snerf_gather_table* tables, int n_tables, const int64_t* indices, int n_rows, void* stream);
+
 /* Self-test of the tcgen05 GEMM building blocks against a CUDA-core GEMM (used by tests).
  * Returns SNERF_OK and writes the max abs error of each mode to host_max_err[4].               */
 int snerf_tensor_selftest(float* host_max_err, void* stream);

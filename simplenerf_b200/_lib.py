@@ -31,6 +31,11 @@ class ReprojArgs(C.Structure):
                 ('width', C.c_int32), ('half_patch', C.c_int32), ('rmse_threshold', C.c_float), ('flags', C.c_uint32)]
 
 
+class GatherTable(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('mask', C.c_void_p), ('row_bytes', C.c_int32), ('fill_bits', C.c_uint32)]
+
+
+GATHER_MAX_TABLES = 24
 LOSS_MAX_STREAMS = 8
 REPROJ_MAX_OTHERS = 4
 REPROJ_SYMMETRIC = 1
@@ -60,6 +65,7 @@ _SIGNATURES = {
     'snerf_ray_losses_backward': (C.c_int, [C.POINTER(LossStream), C.c_int, C.c_int, _fp, _fp, _fp]),
     'snerf_reprojection_losses_forward': (C.c_int, [C.POINTER(ReprojArgs), C.c_int, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     'snerf_reprojection_losses_backward': (C.c_int, [C.POINTER(ReprojArgs), C.c_int, _fp, _fp, _fp, _fp]),
+    'snerf_gather_rows': (C.c_int, [C.POINTER(GatherTable), C.c_int, _fp, C.c_int, _fp]),
     'snerf_tensor_selftest': (C.c_int, [C.POINTER(C.c_float), _fp]),
 }
 EXPORTS = tuple(_SIGNATURES)

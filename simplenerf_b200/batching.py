@@ -1,0 +1,82 @@
+"""Batch assembly on the device: host mirror of the tensor part of
+`DataPreprocessor.load_cached_next_batch` (src/data_preprocessors/DataPreprocessor01.py:514-551).
+
+`assemble_batch(tables, indices, mask_nerf, mask_sd, ndc)` returns the per-ray entries of the reference's batch dict
+(same keys, shapes, dtypes and -1 fill) from the cached per-pixel tables, in ONE launch of `snerf_gather_rows` instead
+of a fill, two boolean-mask index operations and a scatter per tensor.  `tables` holds the reference's
+`preprocessed_data_dict['nerf_data']` tensors (rays_o, rays_d, view_dirs, pixel_id, target_rgb, near_array, far_array and
+their *_ndc variants) and, when there are sparse-depth rays, `preprocessed_data_dict['sparse_depth_data']` under the key
+'sparse_depth_data' (depths, reprojection_errors, depths_ndc).  There is no CPU path."""
+from __future__ import annotations
+
+import struct
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib, ops
+
+_MINUS_ONE_F32 = struct.unpack('<I', struct.pack('<f', -1.0))[0]
+_MINUS_ONE_I32 = 0xFFFFFFFF
+
+# batch key -> nerf_data key; gathered on the NeRF rows and on the sparse-depth rows (:584-590 and :670-675)
+_RAY_KEYS = {'rays_o': 'rays_o', 'rays_d': 'rays_d', 'view_dirs': 'view_dirs', 'pixel_id': 'pixel_id', 'near': 'near_array',
+             'far': 'far_array'}
+_RAY_KEYS_NDC = {'rays_o_ndc': 'rays_o_ndc', 'rays_d_ndc': 'rays_d_ndc', 'near_ndc': 'near_array_ndc', 'far_ndc': 'far_array_ndc'}
+# batch key -> sparse_depth_data key; sparse-depth rows only (:679-684, :697-699)
+_SD_KEYS = {'sparse_depth_values': 'depths', 'sparse_depth_errors': 'reprojection_errors'}
+_SD_KEYS_NDC = {'sparse_depth_values_ndc': 'depths_ndc'}
+
+
+def _mask8(m: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if m is None:
+        return None
+    return m.contiguous().view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8).contiguous()
+
+
+def gather_rows(entries, indices: torch.Tensor) -> None:
+    """entries: list of (src [M, ...], dst [N, ...], mask [N] or None); dst[i] = src[indices[i]] where the mask holds, else -1."""
+    n = indices.shape[0]
+    if not indices.is_cuda:
+        raise RuntimeError('simplenerf_b200 kernels need CUDA tensors (no CPU fallback exists)')
+    indices = indices.to(torch.int64).contiguous()
+    lib = _lib.load()
+    for i in range(0, len(entries), _lib.GATHER_MAX_TABLES):
+        part = entries[i:i + _lib.GATHER_MAX_TABLES]
+        table = (_lib.GatherTable * len(part))()
+        keep = []
+        for k, (src, dst, mask) in enumerate(part):
+            if src.dtype != dst.dtype or src.shape[1:] != dst.shape[1:] or dst.shape[0] != n or src.element_size() != 4:
+                raise RuntimeError(f'table {i + k}: source {tuple(src.shape)} {src.dtype} vs destination {tuple(dst.shape)} {dst.dtype}')
+            src = src.contiguous()
+            m8 = _mask8(mask)
+            keep.append((src, m8))
+            table[k].src, table[k].dst = src.data_ptr(), ops._ptr(dst, dst.dtype)
+            table[k].mask = None if m8 is None else ops._ptr(m8, torch.uint8)
+            table[k].row_bytes = 4 * (src[0].numel() if src.dim() > 1 else 1)
+            table[k].fill_bits = _MINUS_ONE_F32 if dst.dtype == torch.float32 else _MINUS_ONE_I32
+        ops.LAUNCHES['count'] += 1
+        _lib.check(lib.snerf_gather_rows(table, len(part), ops._ptr(indices, torch.int64), n, ops._stream()), 'snerf_gather_rows')
+
+
+def assemble_batch(tables: Dict, indices: torch.Tensor, mask_nerf: torch.Tensor, mask_sd: Optional[torch.Tensor] = None,
+                   ndc: bool = True) -> Dict[str, torch.Tensor]:
+    n, dev = indices.shape[0], indices.device
+    both = None if mask_sd is None else (mask_nerf | mask_sd)       # rows that end up filled after both reference passes
+    ray_mask = mask_nerf if mask_sd is None else both
+    out: Dict[str, torch.Tensor] = {}
+    entries = []
+
+    def add(key, src, mask):
+        out[key] = torch.empty((n,) + tuple(src.shape[1:]), device=dev, dtype=src.dtype)
+        entries.append((src, out[key], mask))
+
+    for key, src_key in {**_RAY_KEYS, **(_RAY_KEYS_NDC if ndc else {})}.items():
+        add(key, tables[src_key], ray_mask)
+    add('target_rgb', tables['target_rgb'], mask_nerf)                                           # :588, NeRF rows only
+    if mask_sd is not None:
+        sd = tables['sparse_depth_data']
+        for key, src_key in {**_SD_KEYS, **(_SD_KEYS_NDC if ndc else {})}.items():
+            add(key, sd[src_key], mask_sd)
+    gather_rows(entries, indices)
+    return out

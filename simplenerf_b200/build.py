@@ -8,7 +8,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libsimplenerf_b200.so')
-SOURCES = ['api.cu', 'sampling.cu', 'composite.cu', 'mlp_simt.cu', 'mlp_tc.cu', 'mlp_tc_bwd.cu', 'adam.cu', 'raygen.cu', 'losses.cu', 'tmem_bench.cu', 'pair_probe.cu']
+SOURCES = ['api.cu', 'sampling.cu', 'composite.cu', 'mlp_simt.cu', 'mlp_tc.cu', 'mlp_tc_bwd.cu', 'adam.cu', 'raygen.cu', 'losses.cu', 'gather.cu', 'tmem_bench.cu', 'pair_probe.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
