@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_fwd_kernel(const 
 //   dL/dalpha_k = g_k T_k + d_alpha_k - (sum_{j>k} G_j T_j) / f_k
 //   dL/dsigma_k = dL/dalpha_k * delta_k * (1 - alpha_k)
 template <int C, bool CONTIG, int G>
-__global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const CompositeArgs a) {
+__global__ void __launch_bounds__(kCompWarps* kWarp, (C >= 8 ? 3 : 0)) composite_bwd_kernel(const CompositeArgs a) {
     static_assert(G == kWarp || (CONTIG && G == 16), "two rays per warp only with lane-contiguous ownership");
     const int warp = threadIdx.x / kWarp, lane = (threadIdx.x % kWarp) % G;
     const int ray_raw = (blockIdx.x * kCompWarps + warp) * (kWarp / G) + (threadIdx.x % kWarp) / G;
@@ -306,7 +306,25 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const 
         }
     }
     // d rgb = w * d rgb_map
-    if constexpr (CONTIG) {
+    if constexpr (CONTIG && (C > 4)) {
+        // 3C floats per lane are 72 / 96 bytes apart: a direct vector store touches 32 sectors per request and fills a
+        // quarter / half of each (ncu, S=192: 30 sectors per store request, 4x the useful L2 write traffic).  The row goes
+        // through shared memory and leaves as whole 512-byte warp stores.
+        __shared__ __align__(16) float s_rows[kCompWarps][3 * C * kWarp];
+        float* row = s_rows[warp];
+        float dr[3 * C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) { dr[3 * i] = r.w[i] * gr; dr[3 * i + 1] = r.w[i] * gg; dr[3 * i + 2] = r.w[i] * gb; }
+        store_vec<3 * C>(row + lane * 3 * C, dr);     // 8/16-byte shared stores: at most two lanes per bank
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(a.d_rgb + (size_t)ray * s * 3);
+#pragma unroll
+        for (int i = 0; i < (3 * C * kWarp / 4 + kWarp - 1) / kWarp; ++i) {
+            const int q = i * kWarp + lane;
+            if (q < 3 * C * kWarp / 4) dst[q] = reinterpret_cast<const float4*>(row)[q];
+        }
+        __syncwarp();
+    } else if constexpr (CONTIG) {
         float dr[3 * C];
 #pragma unroll
         for (int i = 0; i < C; ++i) { dr[3 * i] = r.w[i] * gr; dr[3 * i + 1] = r.w[i] * gg; dr[3 * i + 2] = r.w[i] * gb; }
@@ -341,7 +359,17 @@ __global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_kernel(const 
             ds[i] = d_alpha * r.delta[i] * (1.f - r.alpha[i]);
             suffix += gt[i];
         }
-        if (valid) store_vec<C>(a.d_sigma + (size_t)ray * s + lane * C, ds);
+        if constexpr (C > 4) {       // as above: C floats per lane -> coalesced float2 stores through the (now free) row
+            __shared__ __align__(16) float s_sig[kCompWarps][C * kWarp];
+            float* row = s_sig[warp];
+            store_vec<C>(row + lane * C, ds);
+            __syncwarp();
+            float2* dst = reinterpret_cast<float2*>(a.d_sigma + (size_t)ray * s);
+#pragma unroll
+            for (int i = 0; i < C / 2; ++i) dst[i * kWarp + lane] = reinterpret_cast<const float2*>(row)[i * kWarp + lane];
+        } else {
+            if (valid) store_vec<C>(a.d_sigma + (size_t)ray * s + lane * C, ds);
+        }
     } else {
         float carry = 0.f;
 #pragma unroll

@@ -42,13 +42,19 @@ __global__ void __launch_bounds__(256) sample_coarse_kernel(const float* __restr
     z_out[gid] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), t_rand[gid]));                      // :301
 }
 
-// s % 4 == 0: thread handles samples 4q..4q+3 of one ray; q4 = s / 4 threads per ray
+// s % 4 == 0: thread handles samples 4q..4q+3 of one ray; q4 = s / 4 threads per ray.  The kernel is issue-bound (ncu: 66 %
+// issue slots at 0.67 of the HBM bandwidth), so the model's own shape (64 samples, linear in depth) is a compile-time
+// specialisation: no runtime division for the ray index, no disparity branch in the six interpolations.
+template <int S_FIXED, bool LINDISP_RT>
 __global__ void __launch_bounds__(256) sample_coarse_vec4_kernel(const float* __restrict__ near,
                                                                  const float* __restrict__ far,
                                                                  const float* __restrict__ t_vals,
                                                                  const float* __restrict__ t_rand,
-                                                                 float* __restrict__ z_out, int n_rays, int s, int q4,
-                                                                 bool lindisp) {
+                                                                 float* __restrict__ z_out, int n_rays, int s_rt, int q4_rt,
+                                                                 bool lindisp_rt) {
+    const int s = S_FIXED > 0 ? S_FIXED : s_rt;
+    const int q4 = S_FIXED > 0 ? S_FIXED / 4 : q4_rt;
+    const bool lindisp = LINDISP_RT ? lindisp_rt : false;
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned ray = gid / (unsigned)q4;
     if (ray >= (unsigned)n_rays) return;
@@ -490,8 +496,13 @@ extern "C" int snerf_sample_coarse(const float* near, const float* far, const fl
     if (n_samples % 4 == 0 && aligned && total / 4 < (1LL << 31)) {
         const int q4 = n_samples / 4;
         const long long threads = (long long)n_rays * q4;
-        sample_coarse_vec4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            near, far, t_vals, t_rand, z_out, n_rays, n_samples, q4, lindisp);
+        const unsigned blocks = (unsigned)((threads + 255) / 256);
+        if (n_samples == 64 && !lindisp)
+            sample_coarse_vec4_kernel<64, false><<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, t_vals, t_rand, z_out, n_rays,
+                                                                                         n_samples, q4, lindisp);
+        else
+            sample_coarse_vec4_kernel<0, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, t_vals, t_rand, z_out, n_rays,
+                                                                                        n_samples, q4, lindisp);
         SNERF_LAUNCH_OK("sample_coarse_vec4_kernel");
         return SNERF_OK;
     }
