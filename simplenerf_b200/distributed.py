@@ -23,6 +23,24 @@ def shard_rays(batch: Dict, rank: int, world: int) -> Dict:
     return {k: (v[lo:hi] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == n else v) for k, v in batch.items()}
 
 
+def mask_count_weights(masks: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
+    """the reference's losses are means over MASKED subsets of the whole batch (MSE01.py:53-59,
+    SparseDepthMSE01.py:58-63), computed on the gathered outputs of all replicas.  With one process per GPU every rank takes
+    the mean over its own masked rays; scaling the rank's loss of a mask by  n_rank * world / n_global  makes the AVERAGE
+    of the ranks' gradients (what the gradient exchange computes) equal the gradient of the global masked mean.  One
+    all-reduce of len(masks) counts per step; every scale is 1 when there is one rank.  -> mask name -> 0-dim tensor."""
+    names = sorted(masks)
+    local = torch.stack([masks[k].sum().to(torch.float32) for k in names])
+    active = dist.is_initialized() and dist.get_world_size(group) > 1
+    if not active:
+        return {k: torch.ones((), device=local.device) for k in names}
+    world = dist.get_world_size(group)
+    total = local.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    scale = torch.where(total > 0, local * world / total.clamp(min=1), torch.zeros_like(local))
+    return {k: scale[i] for i, k in enumerate(names)}
+
+
 def _grad_buckets(params: List[torch.nn.Parameter]):
     """Gradients that are views of one flat bucket (the drop-in's backward hands out one zero-padded fp32 bucket per MLP)
     are exchanged in place; anything else goes through a temporary flat copy.  Returns (flat tensors, loose params)."""

@@ -223,7 +223,12 @@ def ray_losses(preds: Sequence[torch.Tensor], targets: Sequence[torch.Tensor], m
 
 
 class FusedLossComputer:
-    def __init__(self, configs: dict, extra_losses: Optional[dict] = None, symmetric_reprojection: bool = False):
+    def __init__(self, configs: dict, extra_losses: Optional[dict] = None, symmetric_reprojection: bool = False,
+                 ray_sharded: bool = False, group=None):
+        """ray_sharded: this process sees one shard of the step's rays (one process per GPU); the masked means are then
+        weighted by  n_rank * world / n_global  per mask (distributed.mask_count_weights) so that the average of the ranks'
+        gradients is the gradient of the reference's global masked means."""
+        self.ray_sharded, self.group = ray_sharded, group
         self.configs = configs
         self.loss_configs = {lc['name']: lc for lc in configs['losses']}
         self.extra_losses = dict(extra_losses or {})
@@ -290,13 +295,23 @@ class FusedLossComputer:
             elif weight != 0:
                 raise RuntimeError(f'Unknown Loss Function: {name} (not fused; pass an object for it in extra_losses)')
         total = extra_total
+        scales = None
+        if self.ray_sharded:
+            from ..distributed import mask_count_weights
+            named = {k: input_dict[k] for k in ('indices_mask_nerf', 'indices_mask_sparse_depth') if input_dict.get(k) is not None}
+            scales = mask_count_weights(named, self.group)
+            by_ptr = {m.data_ptr(): scales[k] for k, m in named.items()}
         for i in range(0, len(preds), _lib.LOSS_MAX_STREAMS):
             sl = slice(i, i + _lib.LOSS_MAX_STREAMS)
             values = ray_losses(preds[sl], targets[sl], masks[sl], weights[sl])
             for j, name in enumerate(owner[sl]):        # a module with a coarse and a fine stream reports their sum (MSE01.py:35,42)
                 prev = loss_values.get(name, {}).get('loss_value')
                 loss_values[name] = {'loss_value': values[j] if prev is None else prev + values[j]}
-            total = total + values[-1]
+            if scales is None:
+                total = total + values[-1]
+            else:       # per-stream weight * count scale, applied on the device
+                w = torch.stack([by_ptr[m.data_ptr()] * wt for m, wt in zip(masks[sl], weights[sl])])
+                total = total + (values[:-1] * w).sum()
         if reproj:
             cd = input_dict['common_data']
             poses, images, intrinsics = cd['poses'], cd['images'], cd['intrinsics']
@@ -311,6 +326,10 @@ class FusedLossComputer:
                 for j, (name, _, _) in enumerate(items):
                     prev = loss_values.get(name, {}).get('loss_value')
                     loss_values[name] = {'loss_value': values[j] if prev is None else prev + values[j]}
-                total = total + values[-1]
+                if scales is None:
+                    total = total + values[-1]
+                else:       # the reprojection losses are means over the rays of the NeRF mask
+                    w = torch.tensor([wt for _, _, wt in items], device=values.device) * scales['indices_mask_nerf']
+                    total = total + (values[:-1] * w).sum()
         loss_values['TotalLoss'] = total
         return loss_values

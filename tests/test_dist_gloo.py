@@ -158,3 +158,52 @@ def test_two_rank_gradient_equals_single_process():
     _loss(model, batch, target).backward()
     for k, p in model.named_parameters():
         torch.testing.assert_close(ret['grads'][k], p.grad, rtol=1e-4, atol=1e-7, msg=lambda m, k=k: f'{k}: {m}')
+
+
+# ---- masked means under ray sharding: count-weighted rank losses average to the global masked mean ----
+def _masked_case():
+    g = torch.Generator().manual_seed(8)
+    n = 40
+    pred = torch.rand((n, 3), generator=g)
+    target = torch.rand((n, 3), generator=g)
+    mask_nerf = torch.rand((n,), generator=g) < 0.7
+    mask_nerf[:20] = torch.rand((20,), generator=g) < 0.3      # the two shards hold different numbers of masked rays
+    return pred, target, mask_nerf, ~mask_nerf
+
+
+def _mask_worker(rank, world, port, ret):
+    from oracle import loss_oracle
+    from simplenerf_b200.distributed import mask_count_weights
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    pred, target, m1, m2 = _masked_case()
+    lo, hi = shard_bounds(pred.shape[0], rank, world)
+    p = pred[lo:hi].clone().requires_grad_()
+    scales = mask_count_weights({'indices_mask_nerf': m1[lo:hi], 'indices_mask_sparse_depth': m2[lo:hi]})
+    loss = scales['indices_mask_nerf'] * loss_oracle.masked_mse(p, target[lo:hi], m1[lo:hi]) + \
+        0.1 * scales['indices_mask_sparse_depth'] * loss_oracle.masked_mse(p, target[lo:hi], m2[lo:hi])
+    loss.backward()
+    grad = torch.zeros_like(pred)
+    grad[lo:hi] = p.grad / world            # what averaging the ranks' parameter gradients does to each ray's contribution
+    dist.all_reduce(grad)
+    total = loss.detach().clone() / world
+    dist.all_reduce(total)
+    if rank == 0:
+        ret['grad'], ret['loss'] = grad, total
+    dist.destroy_process_group()
+
+
+def test_count_weighted_masked_means_equal_the_global_mean():
+    from oracle import loss_oracle
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_mask_worker, args=(2, port, ret), nprocs=2, join=True)
+    pred, target, m1, m2 = _masked_case()
+    p = pred.clone().requires_grad_()
+    want = loss_oracle.masked_mse(p, target, m1) + 0.1 * loss_oracle.masked_mse(p, target, m2)
+    want.backward()
+    torch.testing.assert_close(ret['loss'], want.detach(), rtol=1e-6, atol=0)
+    torch.testing.assert_close(ret['grad'], p.grad, rtol=1e-5, atol=1e-9)

@@ -220,3 +220,34 @@ def test_ray_losses_general_gradient_and_large_batch():
     (got * coef.cuda()).sum().backward()
     for a, b in zip(pg, pc):
         torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_train_step_driver_runs_the_whole_iteration():
+    """RayShardedTrainStep = Trainer01.train_one_iter for one rank: batch assembly -> model -> fused losses -> backward ->
+    one-launch Adam, in sub-batches; the total loss falls over a few iterations and every configured loss is reported."""
+    from simplenerf_b200.models import get_model
+    from simplenerf_b200.optim import FusedAdam
+    from simplenerf_b200.trainer import RayShardedTrainStep
+    g = gu.load('losses.npz')
+    inp, _ = _reproj_case(g, 'r', 'cuda:0')
+    n = inp['rays_o'].shape[0]
+    configs = dict(synthetic.make_configs('simplenerf', ndc=False), losses=[dict(lc) for lc in LOSSES + REPROJ], sub_batch_size=512)
+    configs['data_loader'] = dict(configs['data_loader'], sparse_depth={})
+    gen = torch.Generator().manual_seed(5)
+    d = inp['rays_d']
+    batch = dict(inp, view_dirs=d / d.norm(dim=-1, keepdim=True), near=torch.full((n, 1), 2.0, device='cuda'),
+                 far=torch.full((n, 1), 6.0, device='cuda'), num_frames=3,
+                 target_rgb=torch.rand((n, 3), generator=gen).cuda(), sparse_depth_values=torch.full((n, 1), 4.0, device='cuda'))
+    model = get_model(configs, None)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synthetic.densify_state(synthetic.deterministic_state(shapes, 2)))
+    model = model.to('cuda:0').train()
+    step = RayShardedTrainStep(configs, model, FusedLossComputer(configs, ray_sharded=True), FusedAdam(model.parameters(), lr=5e-4))
+    totals = []
+    for it in range(6):
+        batch['iter_num'] = 20000 + it
+        losses = step(batch)
+        assert set(losses) == {lc['name'] for lc in LOSSES + REPROJ} | {'TotalLoss'}
+        totals.append(float(losses['TotalLoss']))
+    assert all(torch.isfinite(torch.tensor(totals))) and totals[-1] < totals[0], totals
