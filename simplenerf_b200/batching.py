@@ -80,3 +80,70 @@ def assemble_batch(tables: Dict, indices: torch.Tensor, mask_nerf: torch.Tensor,
             add(key, sd[src_key], mask_sd)
     gather_rows(entries, indices)
     return out
+
+
+class HostBatchStager:
+    """Host -> device input pipeline for batches that are assembled on the host (the reference's loader
+    hands the model a dict of ~12 small tensors): ONE pinned staging buffer per slot, ONE host -> device copy per batch on a
+    copy stream, double buffered, so the copy of batch i+1 travels under the kernels of batch i.
+
+        stager = HostBatchStager(example_batch, device)          # layout from an example (keys, shapes, dtypes)
+        host = stager.host_views(slot)                            # dict of pinned views: fill them in place (or `stage` copies)
+        stager.submit(slot)                                       # async copy on the copy stream
+        batch = stager.device_batch(slot)                         # the compute stream waits for that copy only
+        ...                                                       # run the step on `batch`
+        stager.release(slot)                                      # the slot may be overwritten once these kernels are done
+    Non-tensor entries of the example (iter_num, num_frames, common_data) are passed through by reference."""
+
+    def __init__(self, example: Dict, device, slots: int = 2):
+        self.device = torch.device(device)
+        self.layout = []                      # (key, offset, nbytes, shape, dtype)
+        self.passthrough = {k: v for k, v in example.items() if not isinstance(v, torch.Tensor)}
+        off = 0
+        for k, v in example.items():
+            if isinstance(v, torch.Tensor):
+                nbytes = v.numel() * v.element_size()
+                self.layout.append((k, off, nbytes, tuple(v.shape), v.dtype))
+                off += (nbytes + 255) // 256 * 256
+        self.nbytes = max(off, 256)
+        self.host = [torch.empty(self.nbytes, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(slots)]
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.copied = [torch.cuda.Event() for _ in range(slots)]
+        self.free = [None] * slots            # event after the last kernel that read the slot
+
+    def _views(self, buf: torch.Tensor) -> Dict:
+        out = dict(self.passthrough)
+        for k, off, nbytes, shape, dtype in self.layout:
+            out[k] = buf[off:off + nbytes].view(dtype).view(shape)
+        return out
+
+    def host_views(self, slot: int) -> Dict:
+        return self._views(self.host[slot])
+
+    def stage(self, slot: int, batch: Dict) -> None:
+        """Copy a host batch into the slot's pinned buffer (skip when the loader fills `host_views` directly) and submit."""
+        views = self.host_views(slot)
+        for k, _, _, _, _ in self.layout:
+            views[k].copy_(batch[k])
+        self.submit(slot)
+
+    def submit(self, slot: int) -> None:
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[slot] is not None:
+                self.copy_stream.wait_event(self.free[slot])
+            self.dev[slot].copy_(self.host[slot], non_blocking=True)
+            self.copied[slot].record(self.copy_stream)
+
+    def device_batch(self, slot: int) -> Dict:
+        torch.cuda.current_stream(self.device).wait_event(self.copied[slot])
+        return self._views(self.dev[slot])
+
+    def release(self, slot: int) -> None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[slot] = ev
+
+    @property
+    def bytes_per_batch(self) -> int:
+        return sum(n for _, _, n, _, _ in self.layout)

@@ -57,3 +57,23 @@ def test_gather_refuses_cpu_tensors():
     from simplenerf_b200.batching import gather_rows
     with pytest.raises(RuntimeError, match='CUDA'):
         gather_rows([(torch.zeros(4, 3), torch.zeros(2, 3), None)], torch.zeros(2, dtype=torch.int64))
+
+
+@pytest.mark.gpu
+def test_host_batch_stager_round_trip_and_slot_reuse():
+    from simplenerf_b200 import synthetic
+    from simplenerf_b200.batching import HostBatchStager
+    example = synthetic.make_ray_batch('llff', 777, 3)
+    example['pixel_id'] = torch.randint(0, 1000, (777, 3), dtype=torch.int32)
+    stager = HostBatchStager(example, 'cuda:0', slots=2)
+    assert stager.bytes_per_batch == sum(v.numel() * v.element_size() for v in example.values() if isinstance(v, torch.Tensor))
+    for it in range(5):                       # slots are reused; every batch must arrive intact
+        batch = {k: (v + it if isinstance(v, torch.Tensor) else v) for k, v in example.items()}
+        slot = it % 2
+        stager.stage(slot, batch)
+        got = stager.device_batch(slot)
+        assert got['iter_num'] == example['iter_num'] and got['num_frames'] == 3
+        for k, v in batch.items():
+            if isinstance(v, torch.Tensor):
+                assert got[k].dtype == v.dtype and got[k].shape == v.shape and torch.equal(got[k].cpu(), v), k
+        stager.release(slot)
