@@ -173,7 +173,8 @@ typedef struct snerf_loss_stream {
 } snerf_loss_stream;
 size_t snerf_ray_losses_workspace_bytes(void);
 /* values[n_streams + 1]: the mean of every stream (0 when its mask is empty), then the weighted total;
- * counts[n_streams]: masked-in rays per stream.  The workspace must be zeroed once after allocation.                 */
+ * counts[n_streams]: masked-in rays per stream.  The workspace must be zeroed once after allocation and belongs to
+ * one stream at a time (block partials and a ticket counter live in it between the blocks of one launch).           */
 int snerf_ray_losses_forward(const snerf_loss_stream* streams, int n_streams, int n_rays, float* values,
                              int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 /* grad_values[n_streams + 1] (device): incoming gradient of `values`; stream s receives
@@ -223,7 +224,8 @@ int snerf_reprojection_losses_backward(const snerf_reproj_args* args, int n_rays
  * Replaces the `-1 * ones` + `t[mask] = table[indices[mask]]` pairs of load_nerf_cached_batch
  * (src/data_preprocessors/DataPreprocessor01.py:572-620) and load_sparse_depth_cached_batch (:655-700):
  *   dst[i, :] = (mask == NULL || mask[i]) ? src[indices[i], :] : fill.   Rows are row_bytes wide (a multiple of 4),
- * fill_bits is the 32-bit pattern of the fill value (-1.0f or int32 -1).  Host array of tables, device pointers.        */
+ * fill_bits is the 32-bit pattern of the fill value (-1.0f or int32 -1).  Host array of tables, device pointers.
+ * indices[i] of a masked-in row must be a valid source row (not checked, like every device-side index here).            */
 #define SNERF_GATHER_MAX_TABLES 24
 typedef struct snerf_gather_table {
     const void* src;      /* [n_source_rows, row_bytes]              */

@@ -203,13 +203,16 @@ def reprojection_losses(depth_main, depth_others, weights, rays_o, rays_d, pixel
                                      symmetric, _workspace(depth_main.device), depth_main, *depth_others)
 
 
-_WORKSPACES: Dict[torch.device, torch.Tensor] = {}
+_WORKSPACES: Dict[tuple, torch.Tensor] = {}
 
 
 def _workspace(dev: torch.device) -> torch.Tensor:
-    if dev not in _WORKSPACES:      # zeroed once; the kernel leaves its ticket counter at zero
-        _WORKSPACES[dev] = torch.zeros(_lib.load().snerf_ray_losses_workspace_bytes(), device=dev, dtype=torch.uint8)
-    return _WORKSPACES[dev]
+    """Per (device, stream): the forward kernels keep block partials and a ticket counter in it, so two streams must not
+    share one.  Zeroed once; the kernel leaves its ticket counter at zero."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    if key not in _WORKSPACES:
+        _WORKSPACES[key] = torch.zeros(_lib.load().snerf_ray_losses_workspace_bytes(), device=dev, dtype=torch.uint8)
+    return _WORKSPACES[key]
 
 
 def ray_losses(preds: Sequence[torch.Tensor], targets: Sequence[torch.Tensor], masks: Sequence[Optional[torch.Tensor]],
