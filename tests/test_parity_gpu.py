@@ -63,9 +63,11 @@ def _pdf_case(n, seed, sc=64, n_new=128):
     return z, w, u
 
 
-@pytest.mark.parametrize('n', [1, 33, 4096])
-def test_sample_fine_indices_exact_and_sorted(n):
-    z, w, u = _pdf_case(n, 5)
+@pytest.mark.parametrize('n,sc,n_new', [(1, 64, 128), (33, 64, 128), (4096, 64, 128),
+                                        (515, 64, 64), (515, 64, 256),        # the other two register-resident shapes
+                                        (77, 32, 50), (77, 100, 300)])        # generic shapes (shared-memory kernel)
+def test_sample_fine_indices_exact_and_sorted(n, sc, n_new):
+    z, w, u = _pdf_case(n, 5, sc, n_new)
     z_fine, dbg = ops.sample_fine(cuda(z), cuda(w), cuda(u), debug=True)
     cdf = dbg['cdf'].cpu()
     # (L-a) indices are exactly searchsorted(right=True) on the kernel's own cdf, clamps included
@@ -84,6 +86,24 @@ def test_sample_fine_indices_exact_and_sorted(n):
     zf = z_fine.cpu()
     assert bool((zf[:, 1:] >= zf[:, :-1]).all())
     assert torch.equal(zf, torch.sort(torch.cat([z, want], -1), -1)[0])
+
+
+@pytest.mark.parametrize('n_new', [64, 128, 256])
+def test_sample_fine_sorted_uniforms_and_ties(n_new):
+    """Sorted uniforms take the no-sort path; duplicated coarse depths, samples equal to a coarse depth (empty rays put
+    samples exactly on mid points) and uniforms at both ends of [0, 1] exercise the rank merge's tie handling."""
+    z, w, u = _pdf_case(300, 6, 64, n_new)
+    u = torch.sort(u, -1)[0].contiguous()
+    u[:, 0], u[:, -1] = 0.0, 1.0
+    z[10:20, 5] = z[10:20, 6]                                  # equal neighbours among the coarse depths
+    z[20:30, :] = torch.linspace(0, 1, 64)                      # dyadic depths: mid points and samples collide with them
+    w[20:30] = 0
+    z_fine, dbg = ops.sample_fine(cuda(z), cuda(w), cuda(u), debug=True)
+    zf = z_fine.cpu()
+    assert torch.equal(zf, torch.sort(torch.cat([z, dbg['samples'].cpu()], -1), -1)[0])
+    lin = torch.linspace(0., 1., n_new)
+    z_fine2, dbg2 = ops.sample_fine(cuda(z), cuda(w), cuda(lin), debug=True)      # the shared deterministic row
+    assert torch.equal(z_fine2.cpu(), torch.sort(torch.cat([z, dbg2['samples'].cpu()], -1), -1)[0])
 
 
 def test_sample_fine_vs_oracle_end_to_end():
