@@ -190,17 +190,21 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
 }
 
 // ------------------------------------------------------------------------------------------------
-// fine, the model's shape (64 coarse depths, 32*NPL new samples): one warp per ray, values in registers, three small
-// smem rows per warp.  The kernel is instruction-bound (1.8 KB of HBM traffic per ray against several hundred warp
-// instructions), so every stage is written for instruction count:
+// fine, the model's shape (64 coarse depths, 32*NPL new samples): values in registers, a few small smem rows per ray.
+// The kernel is NOT HBM-bound: 1.8 KB of traffic per ray against ~480 (ordered uniforms) / ~770 (random uniforms) warp
+// instructions and ~120 shared-memory wavefronts; ncu shows 75-82 % of the issue slots and 76-80 % of the L1 data pipe
+// in use.  Every stage is therefore written for instruction and wavefront count:
+//   * the cdf stage (fp64 reduction and scan, IEEE divisions) runs for two rays at once, one per half warp;
 //   * cdf and mid points interleaved as float2 -> the two gathers of a sample are two LDS.64;
-//   * searchsorted(right=True) over the 63 cdf entries = a branch-free 6-step descent (LDS, FSETP, predicated add);
+//   * searchsorted(right=True) over the 63 cdf entries and the coarse depths' ranks among the sorted samples are
+//     branch-free descents over breadth-first copies of the tables (LDS, FSETP, LEA, predicated add; no bank conflicts);
 //   * the new samples are sorted (only when they are not already in order) by a bitonic network in its "flip"
 //     form -- every compare-exchange is ascending, so the direction is a compile-time constant inside a lane and
-//     one lane-bit predicate across lanes: FMNMX per element in registers, SHFL + FMNMX across lanes;
-//   * the merge with the (sorted) coarse depths is by rank from the coarse side only: coarse depth k goes to slot
-//     k + #(samples < depth) of a row pre-filled with a sentinel, and the samples fill the remaining slots in order
-//     (per-lane hole count + one warp scan), straight into the registers that are stored to HBM.
+//     one lane-bit predicate across lanes;
+//   * the merge with the (sorted) coarse depths is by rank from the coarse side only: coarse depth k belongs in slot
+//     k + #(samples < depth); the occupancy of the merged row is OR-reduced into TOT/32 words, from which every lane
+//     derives which value belongs in the slots it stores (coalesced float2 rows): no scatter, no scan, no staging row;
+//   * a zero numerator is kept out of the division (its slow path costs the whole warp ~110 instructions).
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastWarps = 8;
 constexpr int kSc = 64;
@@ -270,19 +274,18 @@ __device__ __forceinline__ void bitonic_sort_registers(float (&v)[NPL], int lane
     }
 }
 
-template <int NPL>
-__global__ void __launch_bounds__(kFastWarps* kWarp)
+template <int NPL, int WARPS>
+__global__ void __launch_bounds__(WARPS* kWarp)
     sample_fine_fast_kernel(const float* __restrict__ z_coarse, const float* __restrict__ w_coarse,
                             const float* __restrict__ u, int u_stride, float* __restrict__ z_fine,
                             float* __restrict__ samples_dbg, float* __restrict__ cdf_dbg, int* __restrict__ below_dbg,
                             int* __restrict__ above_dbg, int n_rays) {
-    constexpr int NNEW = NPL * kWarp, TOT = kSc + NNEW, NB = kSc - 1, OPL = TOT / kWarp;
-    constexpr uint32_t kHole = 0xffffffffu;   // a NaN pattern no depth can carry
-    static_assert(OPL % 2 == 0 && (NNEW & (NNEW - 1)) == 0, "row shapes");
+    constexpr int NNEW = NPL * kWarp, TOT = kSc + NNEW, NB = kSc - 1;
+    static_assert(TOT % 64 == 0 && (NNEW & (NNEW - 1)) == 0, "row shapes");
     struct __align__(16) Row {
         float2 cb[kSc];      // (cdf[k], bins[k]), 63 used: the two gathers of a sample
         float ss[NNEW];      // sorted new samples
-        float outm[TOT];     // merged row: coarse depths scattered into holes (must follow ss)
+        float zc[kSc];       // coarse depths (must follow ss: the merge reads both through one index)
         float ecdf[kSc];     // cdf[0..62] as an implicit search tree in breadth-first order (root at [1])
         float ess[NNEW];     // ss[0..NNEW-2] likewise
     };
@@ -291,15 +294,74 @@ __global__ void __launch_bounds__(kFastWarps* kWarp)
     // nodes 2^(6-k) words apart -- up to 8 lanes per bank; ncu: 117 conflict cycles per ray, L1 data pipe saturated).
     constexpr int LOGN = NPL == 2 ? 6 : NPL == 4 ? 7 : 8;
     static_assert((1 << LOGN) == NNEW, "LOGN");
-    __shared__ Row s_rows[kFastWarps];
+    // Two rays per warp.  The cdf stage is per-warp overhead (fp64 reduction and scan, IEEE divisions): it runs once for
+    // both rays, one per half warp with four coarse entries per lane (four shuffle steps instead of five, half the
+    // instructions per ray); everything after it needs all 32 lanes per ray and runs for one ray after the other.
+    __shared__ Row s_rows[WARPS][2];
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-    const int ray = blockIdx.x * kFastWarps + warp;
-    if (ray >= n_rays) return;
-    Row& row = s_rows[warp];
+    const int ray0 = (blockIdx.x * WARPS + warp) * 2;
+    if (ray0 >= n_rays) return;
+    const int n_here = min(2, n_rays - ray0);
+    const int tz1 = __ffs(lane + 1) - 1;                              // ctz(lane + 1)
+    {
+        const int half = lane >> 4, gl = lane & 15;
+        const int fray = ray0 + min(half, n_here - 1);                // (an odd last ray is prepared twice)
+        Row& frow = s_rows[warp][half];
+        // lane owns coarse indices 4*gl .. 4*gl+3
+        const float4 z4 = __ldg(reinterpret_cast<const float4*>(z_coarse + (size_t)fray * kSc) + gl);
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_coarse + (size_t)fray * kSc) + gl);
+        const float znext = __shfl_down_sync(kFull, z4.x, 1);         // (gl == 15: another ray's value, bin 63 is unused)
+        *reinterpret_cast<float4*>(frow.zc + 4 * gl) = z4;
+        const float zs[5] = {z4.x, z4.y, z4.z, z4.w, znext};
+        const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+        float bin[4], wk[4], pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bin[i] = __fmul_rn(.5f, __fadd_rn(zs[i + 1], zs[i]));                               // :310
+            const bool interior = !((gl == 0 && i == 0) || (gl == 15 && i == 3));               // weights k = 1 .. 62
+            wk[i] = interior ? __fadd_rn(ws[i], 1e-5f) : 0.f;                                   // :331
+        }
+        double total = ((double)wk[0] + (double)wk[1]) + ((double)wk[2] + (double)wk[3]);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+        const float norm = (float)total;                                                        // :332
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[i] = wk[i] != 0.f ? __fdiv_rn(wk[i], norm) : 0.f;
+        // cdf[k] = sum_{k' <= k} pdf(k'): torch's CPU cumsum keeps an fp64 running sum, rounded per prefix  :333
+        double run[4];
+        run[0] = (double)pk[0];
+#pragma unroll
+        for (int i = 1; i < 4; ++i) run[i] = run[i - 1] + (double)pk[i];
+        double incl = run[3];
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const double v = __shfl_up_sync(kFull, incl, o);
+            if (gl >= o) incl += v;
+        }
+        const double before = incl - run[3];
+        float cdf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cdf[i] = (float)(before + run[i]);                          // cdf[0] = 0  (:334)
+        if (gl == 15) cdf[3] = __int_as_float(0x7f800000);                                      // entry 63: never read
+        *reinterpret_cast<float4*>(&frow.cb[4 * gl]) = make_float4(cdf[0], bin[0], cdf[1], bin[1]);
+        *reinterpret_cast<float4*>(&frow.cb[4 * gl + 2]) = make_float4(cdf[2], bin[2], cdf[3], bin[3]);
+        // sorted index j = node t = j + 1 of the in-order numbering: level = 5 - ctz(t), slot = 2^level + (t >> (ctz(t)+1))
+        const int tzg = __ffs(gl + 1) - 1;                            // ctz(gl + 1)
+        *reinterpret_cast<float2*>(frow.ecdf + 32 + 2 * gl) = make_float2(cdf[0], cdf[2]);      // t = 4gl+1, 4gl+3: bottom level
+        frow.ecdf[16 + gl] = cdf[1];                                                            // t = 4gl+2
+        if (gl < 15) frow.ecdf[(8 >> tzg) + ((gl + 1) >> (tzg + 1))] = cdf[3];                  // t = 4(gl+1)
+        if (cdf_dbg != nullptr && half < n_here) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (4 * gl + i < NB) cdf_dbg[(size_t)fray * NB + 4 * gl + i] = cdf[i];
+        }
+    }
+    __syncwarp();
 
-    // ---- coarse depths, mid points, weights: lane owns coarse indices 2*lane, 2*lane+1 ----
-    const float2 z2 = __ldg(reinterpret_cast<const float2*>(z_coarse + (size_t)ray * kSc) + lane);
-    const float2 w2 = __ldg(reinterpret_cast<const float2*>(w_coarse + (size_t)ray * kSc) + lane);
+  for (int which = 0; which < n_here; ++which) {
+    const int ray = ray0 + which;
+    Row& row = s_rows[warp][which];
+    const float2 z2 = *reinterpret_cast<const float2*>(row.zc + 2 * lane);     // this lane's coarse depths 2*lane, 2*lane+1
     float us[NPL];
     {
         const float* urow = u + (size_t)ray * u_stride + lane * NPL;
@@ -314,46 +376,6 @@ __global__ void __launch_bounds__(kFastWarps* kWarp)
             us[0] = t.x; us[1] = t.y;
         }
     }
-    // pre-fill this lane's slots of the merged row with holes
-#pragma unroll
-    for (int i = 0; i < OPL / 2; ++i)
-        *reinterpret_cast<uint2*>(row.outm + lane * OPL + 2 * i) = make_uint2(kHole, kHole);
-
-    const float znext = __shfl_down_sync(kFull, z2.x, 1);
-    const float bin_a = __fmul_rn(.5f, __fadd_rn(z2.y, z2.x));                                   // :310
-    const float bin_b = __fmul_rn(.5f, __fadd_rn(znext, z2.y));                                  // (lane 31: unused)
-    // interior weights k = 1 .. 62, + 1e-5                                                      // :331
-    const float wa = lane > 0 ? __fadd_rn(w2.x, 1e-5f) : 0.f;              // k = 2*lane
-    const float wb = lane < kWarp - 1 ? __fadd_rn(w2.y, 1e-5f) : 0.f;      // k = 2*lane + 1
-    double total = (double)wa + (double)wb;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
-    const float norm = (float)total;                                                            // :332
-    const float pa = lane > 0 ? __fdiv_rn(wa, norm) : 0.f;
-    const float pb = lane < kWarp - 1 ? __fdiv_rn(wb, norm) : 0.f;
-    // cdf[k] = sum_{k' <= k} pdf(k'): torch's CPU cumsum keeps an fp64 running sum, rounded per prefix  :333
-    const double lane_pdf = (double)pa + (double)pb;
-    double incl = lane_pdf;
-#pragma unroll
-    for (int o = 1; o < kWarp; o <<= 1) {
-        const double v = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const double before = incl - lane_pdf;
-    const float cdf_a = (float)(before + (double)pa);                                           // cdf[0] = 0  (:334)
-    const float cdf_b = lane < kWarp - 1 ? (float)(before + (double)pa + (double)pb)
-                                         : __int_as_float(0x7f800000);                          // entry 63: never read
-    *reinterpret_cast<float4*>(&row.cb[2 * lane]) = make_float4(cdf_a, bin_a, cdf_b, bin_b);
-    // sorted index j = node t = j + 1 of the in-order numbering: level = top - ctz(t), slot = 2^level + (t >> (ctz(t)+1))
-    const int tz1 = __ffs(lane + 1) - 1;                              // ctz(lane + 1)
-    row.ecdf[32 + lane] = cdf_a;                                      // j = 2*lane:   t odd, bottom level
-    if (lane < kWarp - 1) row.ecdf[(16 >> tz1) + ((lane + 1) >> (tz1 + 1))] = cdf_b;   // j = 2*lane+1: t = 2*(lane+1)
-    __syncwarp();
-    if (cdf_dbg != nullptr) {
-        cdf_dbg[(size_t)ray * NB + 2 * lane] = cdf_a;
-        if (lane < kWarp - 1) cdf_dbg[(size_t)ray * NB + 2 * lane + 1] = cdf_b;
-    }
-
     // ---- invert the cdf for this lane's NPL uniforms (:345-359) ----
     // searchsorted(right=True) = #(cdf[j] <= u) over 63 = 2^6 - 1 sorted entries: 6-step descent on byte offsets
     // node i -> 2i + (cdf <= u); after 6 levels i - 64 = #(cdf <= u).  On byte addresses a = E + 4i: a' = 2a - E (+4)
@@ -379,7 +401,11 @@ __global__ void __launch_bounds__(kFastWarps* kWarp)
         const float2 hi = lds_f32x2(min(off[r], cbp + (NB - 1) * 8));                           // above  :347
         float denom = __fsub_rn(hi.x, lo.x);                                                    // :356
         if (denom < 1e-5f) denom = 1.f;                                                         // :357
-        const float t = __fdiv_rn(__fsub_rn(us[r], lo.x), denom);                               // :358
+        // (u - cdf_below) == 0 -- every ray's first sample under the deterministic linspace -- would send the whole warp
+        //  through the division's slow path (FCHK flags a zero numerator): ~110 instructions per ray.  0 / denom = +0.
+        const float num = __fsub_rn(us[r], lo.x);
+        const float q = __fdiv_rn(num == 0.f ? 1.f : num, denom);
+        const float t = num == 0.f ? 0.f : q;                                                   // :358
         smp[r] = __fadd_rn(lo.y, __fmul_rn(t, __fsub_rn(hi.y, lo.y)));                          // :359
     }
     if (samples_dbg != nullptr) {     // parity-test outputs, in the caller's order of uniforms
@@ -421,9 +447,9 @@ __global__ void __launch_bounds__(kFastWarps* kWarp)
     }
     __syncwarp();
 
-    // ---- merge: coarse depth k goes to slot k + #(samples < depth); lower_bound over NNEW = 2^m sorted samples ----
+    // ---- merge: coarse depth k belongs in slot k + #(samples < depth); lower_bound over NNEW = 2^m sorted samples ----
     {
-        const uint32_t esp = smem_addr(row.ess), omp = smem_addr(row.outm);
+        const uint32_t esp = smem_addr(row.ess);
         const float zv[2] = {z2.x, z2.y};
         uint32_t p[2] = {esp + 4, esp + 4};
 #pragma unroll
@@ -435,49 +461,48 @@ __global__ void __launch_bounds__(kFastWarps* kWarp)
                 if (c < zv[q]) p[q] += 4;
             }
         }
+        // (p - esp) / 4 - NNEW = #(ss[0..NNEW-2] < z), + the last sample: slot of coarse depth k = k + #(samples < depth)
+        uint32_t slot[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            // (p - esp) / 4 - NNEW = #(ss[0..NNEW-2] < z);  + the last sample
             if (ss_last < zv[q]) p[q] += 4;
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(p[q] - esp + omp + (2 * lane + q - NNEW) * 4), "f"(zv[q]) : "memory");
+            slot[q] = ((p[q] - esp) >> 2) + (uint32_t)(2 * lane + q - NNEW);
+        }
+        // Occupancy of the merged row as TOT/32 words (one warp OR-reduction each): bit s = slot s holds a coarse depth.
+        // From it every lane derives, for the slots it will STORE (64 i + 2 lane, + 1: coalesced float2 rows), how many
+        // coarse depths precede the slot -- which is both the coarse index (if the slot is a coarse one) and, subtracted
+        // from the slot, the sample index.  No scatter, no scan, no trip of the row through shared memory.
+        constexpr int W = TOT / 32;
+        uint32_t occ[W];
+        int before[W + 1];
+        before[0] = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const uint32_t mine = ((slot[0] >> 5) == (uint32_t)j ? 1u << (slot[0] & 31) : 0u) |
+                                  ((slot[1] >> 5) == (uint32_t)j ? 1u << (slot[1] & 31) : 0u);
+            occ[j] = __reduce_or_sync(kFull, mine);
+            before[j + 1] = before[j] + __popc(occ[j]);
+        }
+        // one table: sorted samples, then the coarse depths (zc follows ss inside the row).  Coarse depths that are not
+        // sorted collide on a slot and leave fewer than 64 bits: the sample index then runs on into zc, still inside the row.
+        const uint32_t tab = smem_addr(row.ss);
+        const bool upper = lane >= 16;
+        const int bit = (2 * lane) & 31;
+        float* dst = z_fine + (size_t)ray * TOT;
+#pragma unroll
+        for (int i = 0; i < TOT / 64; ++i) {
+            const uint32_t word = upper ? occ[2 * i + 1] : occ[2 * i];
+            const int r0 = (upper ? before[2 * i + 1] : before[2 * i]) + __popc(word & ((1u << bit) - 1u));
+            const int is0 = (word >> bit) & 1, is1 = (word >> (bit + 1)) & 1;
+            const int r1 = r0 + is0;
+            const int s0 = 64 * i + 2 * lane;
+            const int i0 = is0 ? NNEW + r0 : s0 - r0;
+            const int i1 = is1 ? NNEW + r1 : s0 + 1 - r1;
+            const float v0 = lds_f32(tab + 4 * i0), v1 = lds_f32(tab + 4 * i1);
+            *reinterpret_cast<float2*>(dst + s0) = make_float2(v0, v1);
         }
     }
-    __syncwarp();
-    // the samples fill the holes in order: this lane's first sample index = holes in all lower lanes
-    uint32_t ov[OPL];
-#pragma unroll
-    for (int i = 0; i < OPL / 2; ++i) {
-        const uint2 t = *reinterpret_cast<const uint2*>(row.outm + lane * OPL + 2 * i);
-        ov[2 * i] = t.x; ov[2 * i + 1] = t.y;
-    }
-    int holes = 0;
-#pragma unroll
-    for (int i = 0; i < OPL; ++i) holes += ov[i] == kHole ? 1 : 0;
-    int incl_h = holes;
-#pragma unroll
-    for (int o = 1; o < kWarp; o <<= 1) {
-        const int v = __shfl_up_sync(kFull, incl_h, o);
-        if (lane >= o) incl_h += v;
-    }
-    // (coarse depths that are not sorted collide and leave more than NNEW holes: the index then runs on into
-    //  outm, which follows ss inside the row, so the read stays inside this warp's shared memory)
-    uint32_t sp = smem_addr(row.ss) + (incl_h - holes) * 4;
-#pragma unroll
-    for (int i = 0; i < OPL; ++i) {
-        if (ov[i] == kHole) {
-            ov[i] = __float_as_uint(lds_f32(sp));
-            sp += 4;
-        }
-    }
-    // back through the row so that the HBM stores are coalesced (lane-contiguous slots are 4*OPL bytes apart)
-#pragma unroll
-    for (int i = 0; i < OPL / 2; ++i)
-        *reinterpret_cast<uint2*>(row.outm + lane * OPL + 2 * i) = make_uint2(ov[2 * i], ov[2 * i + 1]);
-    __syncwarp();
-    float* dst = z_fine + (size_t)ray * TOT;
-#pragma unroll
-    for (int i = 0; i < TOT / 64; ++i)
-        *reinterpret_cast<float2*>(dst + i * 64 + 2 * lane) = *reinterpret_cast<const float2*>(row.outm + i * 64 + 2 * lane);
+  }   // rays of this warp
 }
 
 }  // namespace snerf
@@ -524,17 +549,17 @@ extern "C" int snerf_sample_fine(const float* z_coarse, const float* weights_coa
     const bool aligned = ((reinterpret_cast<uintptr_t>(z_coarse) | reinterpret_cast<uintptr_t>(weights_coarse) |
                            reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(z_fine)) & 15) == 0 && u_stride % 4 == 0;
     if (s_coarse == kSc && aligned && (n_new == 64 || n_new == 128 || n_new == 256)) {
-        const int blocks = ceil_div(n_rays, kFastWarps);
         const cudaStream_t st = (cudaStream_t)stream;
+        // two rays per warp; the 256-sample row needs 8.5 KB of shared memory per warp, so its blocks have four warps
         if (n_new == 64)
-            sample_fine_fast_kernel<2><<<blocks, kFastWarps * kWarp, 0, st>>>(z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg,
-                                                                             cdf_dbg, below_dbg, above_dbg, n_rays);
+            sample_fine_fast_kernel<2, kFastWarps><<<ceil_div(n_rays, 2 * kFastWarps), kFastWarps * kWarp, 0, st>>>(
+                z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays);
         else if (n_new == 128)
-            sample_fine_fast_kernel<4><<<blocks, kFastWarps * kWarp, 0, st>>>(z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg,
-                                                                             cdf_dbg, below_dbg, above_dbg, n_rays);
+            sample_fine_fast_kernel<4, kFastWarps><<<ceil_div(n_rays, 2 * kFastWarps), kFastWarps * kWarp, 0, st>>>(
+                z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays);
         else
-            sample_fine_fast_kernel<8><<<blocks, kFastWarps * kWarp, 0, st>>>(z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg,
-                                                                             cdf_dbg, below_dbg, above_dbg, n_rays);
+            sample_fine_fast_kernel<8, 4><<<ceil_div(n_rays, 2 * 4), 4 * kWarp, 0, st>>>(
+                z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays);
         SNERF_LAUNCH_OK("sample_fine_fast_kernel");
         return SNERF_OK;
     }
