@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
 
 // ------------------------------------------------------------------------------------------------
 // fine, the model's shape (64 coarse depths, 32*NPL new samples): values in registers, a few small smem rows per ray.
-// The kernel is NOT HBM-bound: 1.8 KB of traffic per ray against ~480 (ordered uniforms) / ~770 (random uniforms) warp
+// The kernel is NOT HBM-bound: 1.8 KB of traffic per ray against ~540 (ordered uniforms) / ~780 (random uniforms) warp
 // instructions and ~120 shared-memory wavefronts; ncu shows 75-82 % of the issue slots and 76-80 % of the L1 data pipe
 // in use.  Every stage is therefore written for instruction and wavefront count:
 //   * the cdf stage (fp64 reduction and scan, IEEE divisions) runs for two rays at once, one per half warp;
