@@ -86,3 +86,72 @@ def test_synthetic_rays_match_reference_geometry():
     assert torch.allclose(b['rays_o_ndc'][:, 2], -torch.ones(64), atol=1e-5)
     f = synthetic.make_ray_batch('llff', 1008 * 2, 0, frame=True)
     assert f['rays_o'].shape == (2016, 3)
+
+
+# ---- N2 / N3 host logic that needs no GPU -----------------------------------------------------------------------
+class _StubModel(torch.nn.Module):
+    """rgb_fine = w * mean(rays_d) per ray: enough to see gradients accumulate over sub-batches."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.tensor(2.0))
+        self.calls = []
+
+    def forward(self, batch):
+        self.calls.append((batch['rays_o'].shape[0], batch['iter_num'], sorted(batch['common_data'])))
+        return {'rgb_fine': self.w * batch['rays_d'].mean(-1, keepdim=True).expand(-1, 3)}
+
+
+class _StubLosses:
+    def compute_losses(self, input_dict, output_dict):
+        mse = ((output_dict['rgb_fine'] - input_dict['target_rgb']) ** 2).mean()
+        return {'MSE01': {'loss_value': mse}, 'TotalLoss': 1.0 * mse}
+
+
+def test_train_step_mirrors_train_one_iter_on_cpu():
+    """RayShardedTrainStep (src/Trainer01.py:61-107): sub-batches of `sub_batch_size`, per-sub-batch backward with
+    accumulating gradients, loss values summed over sub-batches (update_losses_dict_ with num_samples_=1), one
+    optimizer step; tensors with one row per ray are sliced, everything else is passed through."""
+    from simplenerf_b200.trainer import RayShardedTrainStep
+    g = torch.Generator().manual_seed(0)
+    n = 10
+    batch = {'rays_o': torch.zeros(n, 3), 'rays_d': torch.rand((n, 3), generator=g), 'target_rgb': torch.rand((n, 3), generator=g),
+             'iter_num': 7, 'num_frames': 3, 'common_data': {'poses': torch.eye(4)[None].repeat(n, 1, 1)}}   # poses: n rows, but not per ray
+    model = _StubModel()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    step = RayShardedTrainStep({'sub_batch_size': 4}, model, _StubLosses(), opt)
+    losses = step(batch)
+    assert [c[0] for c in model.calls] == [4, 4, 2] and all(c[1] == 7 and c[2] == ['poses'] for c in model.calls)
+    # the same arithmetic by hand
+    w = torch.tensor(2.0, requires_grad=True)
+    total = 0
+    for lo in (0, 4, 8):
+        sl = slice(lo, lo + 4)
+        mse = ((w * batch['rays_d'][sl].mean(-1, keepdim=True).expand(-1, 3) - batch['target_rgb'][sl]) ** 2).mean()
+        mse.backward()
+        total = total + mse.detach()
+    torch.testing.assert_close(losses['TotalLoss'], total)
+    torch.testing.assert_close(losses['MSE01'], total)
+    torch.testing.assert_close(model.w.detach(), torch.tensor(2.0) - 0.1 * w.grad)
+    assert step(batch, shard=True)['TotalLoss'].shape == ()     # one rank: the shard is the whole batch
+
+
+def test_fused_loss_computer_plumbing_without_gpu():
+    """extra_losses are added with the reference's weight rule; a loss that is neither fused nor supplied raises only when its
+    weight is not 0; CPU tensors are refused before any kernel is reached."""
+    from simplenerf_b200.loss_functions import FusedLossComputer
+    configs = dict(synthetic.make_configs('simplenerf'),
+                   losses=[{'name': 'VisibilityPriorLoss01', 'iter_weights': {'0': 0, '100': 0.5}}])
+
+    class Extra:
+        def compute_loss(self, input_dict, output_dict, return_loss_maps=False):
+            return {'loss_value': output_dict['x'] * 2}
+
+    inp, out = {'iter_num': 50, 'rays_o': torch.zeros(2, 3)}, {'x': torch.tensor(3.0)}
+    assert float(FusedLossComputer(configs).compute_losses(inp, out)['TotalLoss']) == 0             # weight 0: skipped
+    got = FusedLossComputer(configs, extra_losses={'VisibilityPriorLoss01': Extra()}).compute_losses(dict(inp, iter_num=100), out)
+    assert float(got['TotalLoss']) == 3.0 and float(got['VisibilityPriorLoss01']['loss_value']) == 6.0
+    with pytest.raises(RuntimeError, match='Unknown Loss Function'):
+        FusedLossComputer(configs).compute_losses(dict(inp, iter_num=100), out)
+    with pytest.raises(NotImplementedError):
+        FusedLossComputer(configs).compute_losses(inp, out, return_loss_maps=True)
