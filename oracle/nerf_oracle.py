@@ -114,9 +114,11 @@ class MlpSpec:
 
 
 def mlp_forward(spec: MlpSpec, params: Dict[str, torch.Tensor], pts: torch.Tensor,
-                view_dirs: Optional[torch.Tensor], sigma_noise: Optional[torch.Tensor] = None
-                ) -> Dict[str, torch.Tensor]:
-    """pts [P,3], view_dirs [P,3] (already expanded per point, :375) -> sigma [P,1], rgb [P,3].
+                view_dirs: Optional[torch.Tensor], sigma_noise: Optional[torch.Tensor] = None,
+                view_dirs2: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """pts [P,3], view_dirs [P,3] (already expanded per point, :375) -> sigma [P,1], rgb [P,3]; with
+    ``predict_visibility`` also visibility [P,1] and, given view_dirs2 [P,nf-1,3] (the directions from the other
+    views' cameras to the point, :646-649), visibility2 [P,nf-1,1] (row a14 / N4).
 
     ``sigma_noise`` [P,1] is ``randn * raw_noise_std`` (:670), ``None`` in eval.
     Follows MLP.forward :626-654, trunk :656-685, view branch :687-715.
@@ -146,10 +148,43 @@ def mlp_forward(spec: MlpSpec, params: Dict[str, torch.Tensor], pts: torch.Tenso
         for i in range(spec.view_depth):                                  # :697-699
             hv = F.relu(F.linear(hv, params[f'views_linears.{i}.weight'], params[f'views_linears.{i}.bias']))
         vout = F.linear(hv, params['views_output_linear.weight'], params['views_output_linear.bias'])  # :701
+        ch = 0
         if spec.view_dep_rgb:
             out['rgb_view_dependent'] = torch.sigmoid(vout[..., 0:3])     # :704-707
             out['rgb'] = out['rgb_view_dependent']
+            ch = 3
+        if spec.predict_visibility:
+            out['visibility'] = torch.sigmoid(vout[..., ch:ch + 1])       # :710-713
+            if view_dirs2 is not None:                                    # :646-649: the view branch again, per other view
+                venc2 = positional_encoding(view_dirs2, spec.view_degree)
+                hv2 = torch.cat([feat[:, None, :].repeat([1, view_dirs2.shape[1], 1]), venc2], -1)     # :691-695
+                for i in range(spec.view_depth):
+                    hv2 = F.relu(F.linear(hv2, params[f'views_linears.{i}.weight'], params[f'views_linears.{i}.bias']))
+                vout2 = F.linear(hv2, params['views_output_linear.weight'], params['views_output_linear.bias'])
+                out['visibility2'] = torch.sigmoid(vout2[..., ch:ch + 1])
     return out
+
+
+def other_view_dirs(z: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, rays_o2: torch.Tensor, ndc: bool) -> torch.Tensor:
+    """compute_other_view_dirs (:317-325): unit directions from the other views' camera centres rays_o2 [N,nf-1,3] to the
+    sample points; z [N,S] is NDC depth when ``ndc`` (converted with near hard-coded to 1 and a 1e-6 guard, :319-321)."""
+    if ndc:
+        tn = -(1 + rays_o[..., 2]) / rays_d[..., 2]
+        z = (((rays_o[..., None, 2] + tn[..., None] * rays_d[..., None, 2]) / (1 - z + 1e-6)) - rays_o[..., None, 2]) / rays_d[..., None, 2]
+    pts = rays_o[..., None, :] + z[..., None] * rays_d[..., None, :]
+    dirs = pts[:, :, None] - rays_o2[..., None, :, :]                     # (N, S, nf-1, 3)
+    return dirs / torch.norm(dirs, dim=-1, keepdim=True)
+
+
+def other_view_origins(poses: torch.Tensor, pixel_id: torch.Tensor, num_frames: int) -> torch.Tensor:
+    """render_rays :120-133 when the batch carries no rays_o2: camera centres of the num_frames-1 other views, in view
+    order with the ray's own view skipped."""
+    image_id = pixel_id[:, 0].long()
+    cols = []
+    for i in range(num_frames - 1):
+        other = i + (i >= image_id).long()
+        cols.append(poses[other][:, :3, 3])
+    return torch.stack(cols, dim=1)
 
 
 # --------------------------------------------------------------------------------------------
@@ -172,7 +207,7 @@ def ndc_to_metric_depth(z_ndc: torch.Tensor, rays_o: torch.Tensor, rays_d: torch
 
 def composite(sigma: torch.Tensor, rgb: torch.Tensor, z: torch.Tensor, ndc: bool,
               rays_o: torch.Tensor, rays_d: torch.Tensor, rays_d_ndc: Optional[torch.Tensor] = None,
-              white_bkgd: bool = False) -> Dict[str, torch.Tensor]:
+              white_bkgd: bool = False, visibility2: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """sigma [N,S], rgb [N,S,3], z [N,S] (z is NDC depth when ``ndc``) -> per-ray maps."""
     n = z.shape[0]
     if ndc:
@@ -201,6 +236,8 @@ def composite(sigma: torch.Tensor, rgb: torch.Tensor, z: torch.Tensor, ndc: bool
         rgb_map = rgb_map + (1. - acc[..., None])                         # :463
     out.update({'rgb': rgb_map, 'acc': acc, 'alpha': alpha, 'visibility': trans, 'weights': weights,
                 'depth': depth, 'depth_var': depth_var})
+    if visibility2 is not None:                                           # :479-482, [N,S,nf-1,1] -> [N,nf-1]
+        out['visibility2'] = torch.sum(weights[..., None] * visibility2[..., 0], dim=-2) / (acc[..., None] + 1e-6)
     return out
 
 
@@ -344,7 +381,7 @@ class NerfOracle(torch.nn.Module):
         return dict(getattr(self, slot).named_parameters())
 
     def _run_mlp(self, slot: str, pts: torch.Tensor, view_dirs: Optional[torch.Tensor],
-                 rnd: Randoms) -> Dict[str, torch.Tensor]:
+                 rnd: Randoms, view_dirs2: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """run_network + batchify (:363-428): flatten, expand view dirs per point, reshape back."""
         spec = self.specs[slot]
         n, s = pts.shape[:2]
@@ -352,6 +389,9 @@ class NerfOracle(torch.nn.Module):
         vd = None
         if spec.use_view_dirs:
             vd = view_dirs[:, None].expand(pts.shape).reshape(-1, 3)     # :375-376
+        vd2 = None
+        if spec.use_view_dirs and spec.predict_visibility and view_dirs2 is not None:         # :379-382
+            vd2 = view_dirs2.reshape(-1, view_dirs2.shape[-2], 3)
         noise = None
         if self.training and self.configs['model']['raw_noise_std'] > 0.:
             noise = rnd.sigma_noise(slot, n * s) * self.configs['model']['raw_noise_std']
@@ -359,16 +399,21 @@ class NerfOracle(torch.nn.Module):
         pieces: Dict[str, List[torch.Tensor]] = {}
         params = self._params(slot)
         for i in range(0, flat.shape[0], chunk):                          # :404
+            extra = {} if vd2 is None else {'view_dirs2': vd2[i:i + chunk]}
             part = self.mlp_impl(spec, params, flat[i:i + chunk], None if vd is None else vd[i:i + chunk],
-                               None if noise is None else noise[i:i + chunk])
+                               None if noise is None else noise[i:i + chunk], **extra)
             for k, v in part.items():
                 pieces.setdefault(k, []).append(v)
-        return {k: torch.cat(v, 0).reshape(n, s, -1) for k, v in pieces.items()}
+        return {k: torch.cat(v, 0).reshape([n, s] + list(v[0].shape[1:])) for k, v in pieces.items()}    # :387-389
 
-    def _stream(self, out: dict, prefix: str, suffix: str, slot: str, pts, view_dirs, z, batch, rnd, retraw):
-        raw = self._run_mlp(slot, pts, view_dirs, rnd)
+    def _stream(self, out: dict, prefix: str, suffix: str, slot: str, pts, view_dirs, z, batch, rnd, retraw, rays_o2=None):
+        vd2 = None
+        if rays_o2 is not None and self.specs[slot].predict_visibility:   # :149-151 / :214-216
+            vd2 = other_view_dirs(z, batch['rays_o'], batch['rays_d'], rays_o2, self.ndc)
+        raw = self._run_mlp(slot, pts, view_dirs, rnd, vd2)
         maps = composite(raw['sigma'][..., 0], raw['rgb'], z, self.ndc, batch['rays_o'], batch['rays_d'],
-                         batch.get('rays_d_ndc'), self.configs['model']['white_bkgd'])
+                         batch.get('rays_d_ndc'), self.configs['model']['white_bkgd'],
+                         raw.get('visibility2') if rays_o2 is not None else None)
         for k, v in maps.items():
             out[f'{prefix}{k}_{suffix}'] = v
         if retraw:
@@ -377,9 +422,13 @@ class NerfOracle(torch.nn.Module):
         return maps
 
     # -- a13 --------------------------------------------------------------------------------
-    def render_rays(self, batch: dict, retraw: bool, rnd: Randoms) -> Dict[str, torch.Tensor]:
+    def render_rays(self, batch: dict, retraw: bool, rnd: Randoms, sec_views_vis: bool = False) -> Dict[str, torch.Tensor]:
         cfg = self.configs['model']
         n = batch['rays_o'].shape[0]
+        rays_o2 = None
+        if sec_views_vis and any(spec.predict_visibility for k, spec in self.specs.items() if k in ('coarse_model', 'fine_model')):   # :19-20, :119
+            rays_o2 = batch['rays_o2'] if 'rays_o2' in batch else other_view_origins(
+                batch['common_data']['poses'], batch['pixel_id'], batch['num_frames'])
         o, d = (batch['rays_o_ndc'], batch['rays_d_ndc']) if self.ndc else (batch['rays_o'], batch['rays_d'])
         near, far = (batch['near_ndc'], batch['far_ndc']) if self.ndc else (batch['near'], batch['far'])
         view_dirs = batch.get('view_dirs')
@@ -390,7 +439,7 @@ class NerfOracle(torch.nn.Module):
         z_c = stratified_z(near, far, s_c, cfg['lindisp'], rnd.t_rand(n, s_c) if perturb else None)
         pts_c = o[..., None, :] + d[..., None, :] * z_c[..., :, None]     # :140/:142
         out['z_vals_coarse'] = z_c
-        maps_c = self._stream(out, '', 'coarse', 'coarse_model', pts_c, view_dirs, z_c, batch, rnd, retraw)
+        maps_c = self._stream(out, '', 'coarse', 'coarse_model', pts_c, view_dirs, z_c, batch, rnd, retraw, rays_o2)
         if self.training and 'pts_aug_coarse_model' in self.specs:        # :170
             self._stream(out, 'points_augmentation_', 'coarse', 'pts_aug_coarse_model', pts_c, view_dirs, z_c,
                          batch, rnd, retraw)
@@ -403,7 +452,7 @@ class NerfOracle(torch.nn.Module):
             z_f = fine_z(z_c, maps_c['weights'], n_f, rnd.u(n, n_f) if perturb else None)    # :202
             pts_f = o[..., None, :] + d[..., None, :] * z_f[..., :, None]
             out['z_vals_fine'] = z_f
-            self._stream(out, '', 'fine', 'fine_model', pts_f, view_dirs, z_f, batch, rnd, retraw)
+            self._stream(out, '', 'fine', 'fine_model', pts_f, view_dirs, z_f, batch, rnd, retraw, rays_o2)
             if self.training and 'pts_aug_fine_model' in self.specs:      # :234
                 self._stream(out, 'points_augmentation_', 'fine', 'pts_aug_fine_model', pts_f, view_dirs, z_f,
                              batch, rnd, retraw)
@@ -420,13 +469,17 @@ class NerfOracle(torch.nn.Module):
     def forward(self, input_batch: dict, retraw: bool = False, sec_views_vis: bool = False):
         rnd = self.randoms or Randoms(self.configs['model'].get('netchunk'))
         retraw = retraw or self.training                                  # :74
+        sec_views_vis = sec_views_vis or self.training
+        if 'common_data' in input_batch:                                  # :69-73 (on a copy: the caller's dict stays as it was)
+            input_batch = dict(input_batch, common_data={k: (v[0] if isinstance(v, torch.Tensor) else v)
+                                                         for k, v in input_batch['common_data'].items()})
         n = input_batch['rays_o'].shape[0]
         chunk = self.configs['model']['chunk']
         parts: Dict[str, List[torch.Tensor]] = {}
         for i in range(0, n, chunk):                                      # :88
             sub = {k: (v[i:i + chunk] if isinstance(v, torch.Tensor) and v.shape[:1] == (n,) else v)
                    for k, v in input_batch.items()}
-            for k, v in self.render_rays(sub, retraw, rnd).items():
+            for k, v in self.render_rays(sub, retraw, rnd, sec_views_vis).items():
                 parts.setdefault(k, []).append(v)
         return {k: torch.cat(v, 0) for k, v in parts.items()}             # :504-512
 

@@ -114,3 +114,59 @@ def test_rays_oracle_matches_reference_golden():
             np.testing.assert_array_equal(rays[key][pick], g[f'{cam_name}_{key}'], err_msg=f'{cam_name} {key}')
     np.testing.assert_array_equal(ro.post_process_image(g['post_rgb']), g['post_image'])
     np.testing.assert_array_equal(ro.post_process_depth(g['post_depth_in']), g['post_depth'])
+
+
+# ------------------------------------------------------------------------------------------------
+# row a14 / N4: the secondary-view visibility head (predict_visibility=True) -- oracle only so far; the CUDA path
+# refuses the configuration (FusedSimpleNeRF raises NotImplementedError), this pins what it will have to reproduce
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_visibility_head_oracle_matches_reference(tag):
+    g = gu.load('render_visibility.npz')
+    seed, n, ndc, given = [int(v) for v in g[f'{tag}_meta']]
+    configs = synthetic.make_configs('vanilla', ndc=bool(ndc))
+    for k in ('coarse_mlp', 'fine_mlp'):
+        configs['model'][k]['predict_visibility'] = True
+    state = gu.full_state(configs, seed, True)
+    np.testing.assert_allclose(gu.checksum(state), g[f'{tag}_checksum'].numpy(), rtol=1e-12)
+    assert tuple(state['coarse_model.views_output_linear.weight'].shape) == (4, 128)       # rgb + visibility rows (:596-603)
+    batch = {k[len(tag) + 4:]: v for k, v in g.items() if k.startswith(f'{tag}_in_')}
+    batch['iter_num'], batch['num_frames'] = 0, 3
+    if not given:      # training contract: the other views' camera centres come from the poses and the rays' view ids
+        batch['common_data'] = {'poses': batch.pop('poses')[None]}
+    table = {k[len(tag) + 5:]: v for k, v in g.items() if k.startswith(f'{tag}_rnd_')}
+    model = orc.NerfOracle(configs)
+    model.load_state_dict(state)
+    model.randoms = orc.FixedRandoms(table)
+
+    def skip(k):
+        return 'alpha' in k or 'raw_rgb' in k or 'raw_sigma' in k
+
+    model.eval()
+    with torch.no_grad():
+        out = model(batch, retraw=True, sec_views_vis=True)
+        keys = {k.split('__')[1] for k in g if k.startswith(f'{tag}_eval__')}
+        assert {k for k in out if not skip(k)} == keys
+        for k in keys:
+            torch.testing.assert_close(out[k], g[f'{tag}_eval__{k}'], **MLP_TOL, msg=lambda m, k=k: f'{k}: {m}')
+        plain = model(batch)
+        assert [len(plain), int(any('visibility2' in k for k in plain))] == g[f'{tag}_evalplain_keys'].tolist()
+    assert tuple(out['visibility2_fine'].shape) == (n, 2) and tuple(out['raw_visibility2_coarse'].shape) == (n, 64, 2, 1)
+
+    model.train()
+    out = model(batch)
+    loss = 0
+    for k in g:
+        if k.startswith(f'{tag}_cot__'):
+            loss = loss + (out[k.split('__')[1]] * g[k]).sum()
+    loss.backward()
+    for k in g:
+        if k.startswith(f'{tag}_train__'):
+            key = k.split('__')[1]
+            tol = dict(rtol=1e-4, atol=1e-5) if key.startswith('z_vals') else MLP_TOL
+            torch.testing.assert_close(out[key], g[k], **tol, msg=lambda m, key=key: f'{key}: {m}')
+    for pname, prm in model.named_parameters():
+        gv = prm.grad.flatten()[g[f'{tag}_gidx__{pname}'].long()]
+        scale = float(g[f'{tag}_gnorm__{pname}'][0]) / max(1.0, prm.numel() ** 0.5)
+        torch.testing.assert_close(gv, g[f'{tag}_gval__{pname}'], rtol=1e-3, atol=1e-4 * scale + 1e-9, msg=lambda m, p=pname: f'{p}: {m}')
+        np.testing.assert_allclose(float(prm.grad.double().norm()), float(g[f'{tag}_gnorm__{pname}'][0]), rtol=1e-4)
