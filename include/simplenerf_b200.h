@@ -66,6 +66,7 @@ enum {
 #define SNERF_FLAG_LINDISP 4u      /* sample linearly in disparity (:288-289)                    */
 #define SNERF_FLAG_SAVE_FOR_BWD 8u /* MLP forward keeps activations in the workspace             */
 #define SNERF_FLAG_PRECISE 16u     /* fp32 CUDA-core MLP instead of the bf16 tcgen05 MLP         */
+#define SNERF_FLAG_VIS_GRAD 32u    /* snerf_mlp_backward: add what snerf_visibility_backward left in the workspace */
 
 int snerf_abi_version(void);
 const char* snerf_last_error(void);
@@ -131,6 +132,27 @@ int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const* host_para
                        const float* sigma, const float* rgb, const float* d_sigma, const float* d_rgb,
                        float* const* host_grads, void* workspace, size_t workspace_bytes, int n_rays,
                        int n_samples, uint32_t flags, void* stream);
+
+/* ---- a14 / N4: secondary-view visibility head (predict_visibility=True), precise fp32 path ---------
+ * With predict_visibility the reference's views_output_linear has a fourth row (src/models/SimpleNeRF01.py:596-608):
+ *   visibility  = sigmoid(row 3 . relu(view layer))                                   (:710-713)
+ *   visibility2 = the same with the view layer re-run per OTHER view on [feature | enc_hi | PE(dir2)], dir2 the unit
+ *                 vector from that view's camera centre rays_o2[ray, v] to the sample point (:317-325, :646-649).
+ * params[SNERF_P_RGB_W] / [SNERF_P_RGB_B] then point at [4, view_width] / [4].  Both calls work on the workspace that
+ * snerf_mlp_forward(SNERF_FLAG_PRECISE | SNERF_FLAG_SAVE_FOR_BWD) of the same MLP and points left behind, plus their own
+ * (snerf_visibility_workspace_bytes).  z is NDC depth with SNERF_FLAG_NDC (converted as :319-321).
+ * Backward order within a step: snerf_visibility_backward FIRST (it adds the fourth-row and view-layer gradients to
+ * `grads` and leaves d hv / d feature in the MLP workspace), then snerf_mlp_backward(flags | SNERF_FLAG_VIS_GRAD).      */
+size_t snerf_visibility_workspace_bytes(const snerf_mlp_desc* desc, int n_rays, int n_samples, int n_other);
+int snerf_visibility_forward(const snerf_mlp_desc* desc, const float* const* host_params, const void* mlp_workspace,
+                             const float* rays_o, const float* rays_d, const float* z, const float* rays_o2,
+                             float* visibility, float* visibility2, void* workspace, size_t workspace_bytes, int n_rays,
+                             int n_samples, int n_other, uint32_t flags, void* stream);
+int snerf_visibility_backward(const snerf_mlp_desc* desc, const float* const* host_params, void* mlp_workspace,
+                              const float* rays_o, const float* rays_d, const float* z, const float* rays_o2,
+                              const float* visibility, const float* visibility2, const float* d_visibility,
+                              const float* d_visibility2, float* const* host_grads, void* workspace, size_t workspace_bytes,
+                              int n_rays, int n_samples, int n_other, uint32_t flags, void* stream);
 
 /* ---- (f) N1, one frame per call: rays of a camera pose and output post-processing -------------------
  * (DataPreprocessor01.py get_rays :351-368, get_ndc_rays :371-389, get_view_dirs :392-394, post_process_image

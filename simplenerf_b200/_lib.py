@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(PKG, 'libsimplenerf_b200.so')
 
 P_COUNT = 24
 P_HEAD_W, P_HEAD_B, P_FEAT_W, P_FEAT_B, P_VIEW_W, P_VIEW_B, P_RGB_W, P_RGB_B = 16, 17, 18, 19, 20, 21, 22, 23
-FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP, FLAG_SAVE_FOR_BWD, FLAG_PRECISE = 1, 2, 4, 8, 16
+FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP, FLAG_SAVE_FOR_BWD, FLAG_PRECISE, FLAG_VIS_GRAD = 1, 2, 4, 8, 16, 32
 
 
 class MlpDesc(C.Structure):
@@ -66,6 +66,10 @@ _SIGNATURES = {
     'snerf_reprojection_losses_forward': (C.c_int, [C.POINTER(ReprojArgs), C.c_int, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     'snerf_reprojection_losses_backward': (C.c_int, [C.POINTER(ReprojArgs), C.c_int, _fp, _fp, _fp, _fp]),
     'snerf_gather_rows': (C.c_int, [C.POINTER(GatherTable), C.c_int, _fp, C.c_int, _fp]),
+    'snerf_visibility_workspace_bytes': (C.c_size_t, [C.POINTER(MlpDesc), C.c_int, C.c_int, C.c_int]),
+    'snerf_visibility_forward': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp)] + [_fp] * 8 + [C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint32, _fp]),
+    'snerf_visibility_backward': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp)] + [_fp] * 9 + [C.POINTER(_fp), _fp, C.c_size_t,
+                                            C.c_int, C.c_int, C.c_int, C.c_uint32, _fp]),
     'snerf_tensor_selftest': (C.c_int, [C.POINTER(C.c_float), _fp]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -121,6 +121,54 @@ extern "C" int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const
                        workspace, workspace_bytes, n_rays, n_samples, flags, (cudaStream_t)stream);
 }
 
+extern "C" size_t snerf_visibility_workspace_bytes(const snerf_mlp_desc* desc, int n_rays, int n_samples, int n_other) {
+    if (validate_desc(desc) != SNERF_OK || n_rays < 0 || n_samples < 1 || n_other < 0 || desc->view_width <= 0) return 0;
+    const size_t b = simt_visibility_workspace_bytes(MlpDims(*desc), n_rays, n_samples, n_other);
+    return b < 256 ? 256 : b;
+}
+
+extern "C" int snerf_visibility_forward(const snerf_mlp_desc* desc, const float* const* host_params, const void* mlp_workspace,
+                                        const float* rays_o, const float* rays_d, const float* z, const float* rays_o2,
+                                        float* visibility, float* visibility2, void* workspace, size_t workspace_bytes,
+                                        int n_rays, int n_samples, int n_other, uint32_t flags, void* stream) {
+    int rc = validate_desc(desc);
+    if (rc != SNERF_OK) return rc;
+    rc = check_params(*desc, (const void* const*)host_params, "snerf_visibility_forward");
+    if (rc != SNERF_OK) return rc;
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_other >= 0, "snerf_visibility_forward: bad sizes");
+    if (n_rays == 0) return SNERF_OK;
+    if (!(flags & SNERF_FLAG_PRECISE)) return fail(SNERF_ERR_UNSUPPORTED, "snerf_visibility_forward: built on the precise (fp32) path only");
+    SNERF_REQUIRE(desc->view_width > 0 && desc->view_degree > 0, "snerf_visibility_forward: the MLP has no view branch");
+    SNERF_REQUIRE(mlp_workspace && rays_o && rays_d && z && visibility && workspace, "snerf_visibility_forward: null pointer");
+    SNERF_REQUIRE(n_other == 0 || (rays_o2 && visibility2), "snerf_visibility_forward: rays_o2 / visibility2 needed for %d other views", n_other);
+    return simt_visibility_forward(*desc, host_params, mlp_workspace, rays_o, rays_d, z, rays_o2, visibility, visibility2, workspace,
+                                   workspace_bytes, n_rays, n_samples, n_other, flags, (cudaStream_t)stream);
+}
+
+extern "C" int snerf_visibility_backward(const snerf_mlp_desc* desc, const float* const* host_params, void* mlp_workspace,
+                                         const float* rays_o, const float* rays_d, const float* z, const float* rays_o2,
+                                         const float* visibility, const float* visibility2, const float* d_visibility,
+                                         const float* d_visibility2, float* const* host_grads, void* workspace,
+                                         size_t workspace_bytes, int n_rays, int n_samples, int n_other, uint32_t flags,
+                                         void* stream) {
+    int rc = validate_desc(desc);
+    if (rc != SNERF_OK) return rc;
+    rc = check_params(*desc, (const void* const*)host_params, "snerf_visibility_backward(params)");
+    if (rc != SNERF_OK) return rc;
+    rc = check_params(*desc, (const void* const*)host_grads, "snerf_visibility_backward(grads)");
+    if (rc != SNERF_OK) return rc;
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_other >= 0, "snerf_visibility_backward: bad sizes");
+    if (n_rays == 0) return SNERF_OK;
+    if (!(flags & SNERF_FLAG_PRECISE)) return fail(SNERF_ERR_UNSUPPORTED, "snerf_visibility_backward: built on the precise (fp32) path only");
+    SNERF_REQUIRE(flags & SNERF_FLAG_SAVE_FOR_BWD, "snerf_visibility_backward: the forward must have run with SNERF_FLAG_SAVE_FOR_BWD");
+    SNERF_REQUIRE(desc->view_width > 0 && desc->view_degree > 0, "snerf_visibility_backward: the MLP has no view branch");
+    SNERF_REQUIRE(mlp_workspace && rays_o && rays_d && z && visibility && workspace, "snerf_visibility_backward: null pointer");
+    SNERF_REQUIRE(n_other == 0 || (rays_o2 && visibility2), "snerf_visibility_backward: rays_o2 / visibility2 needed");
+    return simt_visibility_backward(*desc, host_params, mlp_workspace, rays_o, rays_d, z, rays_o2, visibility, visibility2, d_visibility,
+                                    d_visibility2, host_grads, workspace, workspace_bytes, n_rays, n_samples, n_other, flags,
+                                    (cudaStream_t)stream);
+}
+
 extern "C" int snerf_tensor_selftest(float* host_max_err, void* stream) {
     SNERF_REQUIRE(host_max_err != nullptr, "snerf_tensor_selftest: null output");
     return tc_selftest(host_max_err, (cudaStream_t)stream);

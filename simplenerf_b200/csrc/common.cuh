@@ -80,6 +80,17 @@ int simt_backward(const snerf_mlp_desc& d, const float* const* prm, const float*
                   const float* d_sigma, const float* d_rgb, float* const* grads, void* ws, size_t ws_bytes,
                   int n_rays, int n_samples, uint32_t flags, cudaStream_t st);
 
+size_t simt_visibility_workspace_bytes(const MlpDims& m, int n_rays, int n_samples, int n_other);
+int simt_visibility_forward(const snerf_mlp_desc& d, const float* const* prm, const void* mlp_ws, const float* rays_o,
+                            const float* rays_d, const float* z, const float* rays_o2, float* visibility, float* visibility2,
+                            void* vis_ws, size_t vis_ws_bytes, int n_rays, int n_samples, int n_other, uint32_t flags,
+                            cudaStream_t st);
+int simt_visibility_backward(const snerf_mlp_desc& d, const float* const* prm, void* mlp_ws, const float* rays_o,
+                             const float* rays_d, const float* z, const float* rays_o2, const float* visibility,
+                             const float* visibility2, const float* d_visibility, const float* d_visibility2,
+                             float* const* grads, void* vis_ws, size_t vis_ws_bytes, int n_rays, int n_samples, int n_other,
+                             uint32_t flags, cudaStream_t st);
+
 // mlp_tc.cu : bf16 tcgen05 MLP (tensor path)
 size_t tc_workspace_bytes(const MlpDims& m, const snerf_mlp_desc& d, int n_rays, int n_samples, uint32_t flags);
 size_t tc_packed_bytes(const snerf_mlp_desc& d);

@@ -337,15 +337,16 @@ int simt_backward(const snerf_mlp_desc& d, const float* const* prm, const float*
                                m.view_width, ep_wgrad(), splits)));
         TRY(colsum(st, w + L.rgbraw, 3, 3, P, grads[SNERF_P_RGB_B]));
         // d hv = d_rgbraw W_rgb, masked by relu
+        const bool vis_grad = (flags & SNERF_FLAG_VIS_GRAD) != 0;   // simt_visibility_backward pre-filled dhv and dyb
         TRY((gemm<false, false>(st, Pi, m.view_width, 3, w + L.rgbraw, 3, prm[SNERF_P_RGB_W], m.view_width, w + L.dhv,
-                                m.view_width, ep_dgrad(w + L.hv, m.view_width, false))));
+                                m.view_width, ep_dgrad(w + L.hv, m.view_width, vis_grad))));
         // view layer
         TRY((gemm<true, false>(st, m.view_width, m.view_in, Pi, w + L.dhv, m.view_width, w + L.xv, L.xv_ld,
                                grads[SNERF_P_VIEW_W], m.view_in, ep_wgrad(), splits)));
         TRY(colsum(st, w + L.dhv, m.view_width, m.view_width, P, grads[SNERF_P_VIEW_B]));
         // d feature = d_hv W_view[:, :width]  (feature has no activation)
         TRY((gemm<false, false>(st, Pi, m.width, m.view_width, w + L.dhv, m.view_width, prm[SNERF_P_VIEW_W], m.view_in, dx,
-                                m.width, ep_dgrad(nullptr, 0, false))));
+                                m.width, ep_dgrad(nullptr, 0, vis_grad))));
         // feature layer
         TRY((gemm<true, false>(st, m.width, m.width, Pi, dx, m.width, h_last, ld_last, grads[SNERF_P_FEAT_W], m.width,
                                ep_wgrad(), splits)));
@@ -378,6 +379,174 @@ int simt_backward(const snerf_mlp_desc& d, const float* const* prm, const float*
         float* t = dy; dy = dx; dx = t;
     }
     (void)flags;
+    return SNERF_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Row a14 / N4: the secondary-view visibility head (predict_visibility=True), precise path only.
+// Reference: MLP ctor :596-608 (views_output_linear has a fourth row), MLP.forward :640-649 (the view branch once more per
+// other view), get_view_dependent_outputs :687-715, compute_other_view_dirs :317-325.
+// Runs on the workspace a snerf_mlp_forward(PRECISE | SAVE_FOR_BWD) of the same MLP left behind: xv = [feature | enc_hi |
+// PE(view_dir)] and hv = relu(view layer) per point.  Own workspace: xv2 [P, xv_ld], hv2 [n_other][P, view_width],
+// dv [P, 1 + n_other] (pre-sigmoid gradients), dhv2 [P, view_width].
+// ------------------------------------------------------------------------------------------------
+struct VisLayout {
+    size_t xv2, hv2, dv, dhv2, total;
+};
+
+static VisLayout vis_layout(const MlpDims& m, int n_rays, int n_samples, int n_other) {
+    VisLayout V{};
+    const size_t P = (size_t)n_rays * n_samples;
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += align_up(n < 1 ? 1 : n, 64); return o; };
+    V.xv2 = take(P * m.view_in);
+    V.hv2 = take((size_t)n_other * P * m.view_width);
+    V.dv = take(P * (1 + n_other));
+    V.dhv2 = take(P * m.view_width);
+    V.total = off;
+    return V;
+}
+
+size_t simt_visibility_workspace_bytes(const MlpDims& m, int n_rays, int n_samples, int n_other) {
+    return vis_layout(m, n_rays, n_samples, n_other).total * sizeof(float);
+}
+
+// xv2[p] = [xv[p, :view_in - venc] | PE(unit vector from the other view's camera centre to the point)]
+__global__ void __launch_bounds__(128) vis_build_input_kernel(const float* __restrict__ xv, const float* __restrict__ rays_o,
+                                                              const float* __restrict__ rays_d, const float* __restrict__ z,
+                                                              const float* __restrict__ rays_o2, float* __restrict__ xv2,
+                                                              int n_rays, int s, int n_other, int v, int xv_ld, int keep,
+                                                              int view_degree, bool ndc) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)n_rays * s) return;
+    const int ray = (int)(p / s);
+    const float ox = rays_o[ray * 3], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
+    const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+    float zz = z[p];
+    if (ndc) {                                                                                   // :319-321 (near = 1)
+        const float tn = -(1.f + oz) / dz;
+        zz = (((oz + tn * dz) / (1.f - zz + 1e-6f)) - oz) / dz;
+    }
+    const float* o2 = rays_o2 + ((size_t)ray * n_other + v) * 3;
+    float d[3] = {__fadd_rn(ox, __fmul_rn(zz, dx)) - o2[0], __fadd_rn(oy, __fmul_rn(zz, dy)) - o2[1],
+                  __fadd_rn(oz, __fmul_rn(zz, dz)) - o2[2]};                                     // :322-323
+    const float norm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);                          // :324
+    d[0] /= norm; d[1] /= norm; d[2] /= norm;
+    const float* src = xv + p * xv_ld;
+    float* dst = xv2 + p * xv_ld;
+    for (int c = 0; c < keep; ++c) dst[c] = src[c];
+    float ve[32];
+    encode3(d, view_degree, ve);
+    for (int c = 0; c < xv_ld - keep; ++c) dst[keep + c] = ve[c];
+}
+
+__global__ void vis_sigmoid_kernel(float* __restrict__ x, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = sigmoidf(x[i]);
+}
+
+// dv[p, 0] = d_vis * vis (1 - vis); dv[p, 1 + v] = d_vis2 * vis2 (1 - vis2)   (null gradients count as zero)
+__global__ void vis_head_grad_kernel(const float* __restrict__ vis, const float* __restrict__ vis2,
+                                     const float* __restrict__ d_vis, const float* __restrict__ d_vis2,
+                                     float* __restrict__ dv, long long P, int n_other) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float a = vis[p];
+    dv[p * (1 + n_other)] = d_vis ? d_vis[p] * a * (1.f - a) : 0.f;
+    for (int v = 0; v < n_other; ++v) {
+        const float b = vis2[p * n_other + v];
+        dv[p * (1 + n_other) + 1 + v] = d_vis2 ? d_vis2[p * n_other + v] * b * (1.f - b) : 0.f;
+    }
+}
+
+int simt_visibility_forward(const snerf_mlp_desc& d, const float* const* prm, const void* mlp_ws, const float* rays_o,
+                            const float* rays_d, const float* z, const float* rays_o2, float* visibility, float* visibility2,
+                            void* vis_ws, size_t vis_ws_bytes, int n_rays, int n_samples, int n_other, uint32_t flags,
+                            cudaStream_t st) {
+    const MlpDims m(d);
+    SNERF_REQUIRE(m.has_view && m.venc > 0, "visibility head: the MLP needs a view branch with view directions");
+    const SimtLayout L = simt_layout(m, n_rays, n_samples);
+    const VisLayout V = vis_layout(m, n_rays, n_samples, n_other);
+    SNERF_REQUIRE(vis_ws_bytes >= V.total * sizeof(float), "visibility_forward: workspace too small (%zu < %zu)", vis_ws_bytes,
+                  V.total * sizeof(float));
+    const long long P = (long long)n_rays * n_samples;
+    if (P == 0) return SNERF_OK;
+    const float* w = (const float*)mlp_ws;
+    float* vw = (float*)vis_ws;
+    const float* w_vis = prm[SNERF_P_RGB_W] + 3 * m.view_width;      // fourth row of views_output_linear (:710-711)
+    const float* b_vis = prm[SNERF_P_RGB_B] + 3;
+    // own view: visibility = sigmoid(hv . w_vis + b_vis)
+    TRY((gemm<false, true>(st, (int)P, 1, m.view_width, w + L.hv, m.view_width, w_vis, m.view_width, visibility, 1,
+                           ep_linear(b_vis, false))));
+    vis_sigmoid_kernel<<<(int)((P + 255) / 256), 256, 0, st>>>(visibility, P);
+    SNERF_LAUNCH_OK("vis_sigmoid_kernel");
+    for (int v = 0; v < n_other; ++v) {                                                          // :646-649
+        vis_build_input_kernel<<<(int)((P + 127) / 128), 128, 0, st>>>(w + L.xv, rays_o, rays_d, z, rays_o2, vw + V.xv2, n_rays,
+                                                                      n_samples, n_other, v, L.xv_ld, m.view_in - m.venc,
+                                                                      d.view_degree, (flags & SNERF_FLAG_NDC) != 0);
+        SNERF_LAUNCH_OK("vis_build_input_kernel");
+        float* hv2 = vw + V.hv2 + (size_t)v * P * m.view_width;
+        TRY((gemm<false, true>(st, (int)P, m.view_width, m.view_in, vw + V.xv2, L.xv_ld, prm[SNERF_P_VIEW_W], m.view_in, hv2,
+                               m.view_width, ep_linear(prm[SNERF_P_VIEW_B], true))));
+        TRY((gemm<false, true>(st, (int)P, 1, m.view_width, hv2, m.view_width, w_vis, m.view_width, visibility2 + v, n_other,
+                               ep_linear(b_vis, false))));
+    }
+    if (n_other > 0) {
+        vis_sigmoid_kernel<<<(int)((P * n_other + 255) / 256), 256, 0, st>>>(visibility2, P * n_other);
+        SNERF_LAUNCH_OK("vis_sigmoid_kernel");
+    }
+    return SNERF_OK;
+}
+
+// Must run BEFORE simt_backward(... | SNERF_FLAG_VIS_GRAD) of the same step: it leaves d hv (own view) in the MLP workspace's
+// dhv region and the other views' d feature in its dyb region, which that call then accumulates onto.
+int simt_visibility_backward(const snerf_mlp_desc& d, const float* const* prm, void* mlp_ws, const float* rays_o,
+                             const float* rays_d, const float* z, const float* rays_o2, const float* visibility,
+                             const float* visibility2, const float* d_visibility, const float* d_visibility2,
+                             float* const* grads, void* vis_ws, size_t vis_ws_bytes, int n_rays, int n_samples, int n_other,
+                             uint32_t flags, cudaStream_t st) {
+    const MlpDims m(d);
+    const SimtLayout L = simt_layout(m, n_rays, n_samples);
+    const VisLayout V = vis_layout(m, n_rays, n_samples, n_other);
+    SNERF_REQUIRE(vis_ws_bytes >= V.total * sizeof(float), "visibility_backward: workspace too small");
+    const long long P = (long long)n_rays * n_samples;
+    if (P == 0) return SNERF_OK;
+    float* w = (float*)mlp_ws;
+    float* vw = (float*)vis_ws;
+    const int Pi = (int)P, ldv = 1 + n_other;
+    const int splits = (int)max(1LL, min(512LL, P / 2048));
+    const float* w_vis = prm[SNERF_P_RGB_W] + 3 * m.view_width;
+    float* g_w_vis = grads[SNERF_P_RGB_W] + 3 * m.view_width;
+    float* g_b_vis = grads[SNERF_P_RGB_B] + 3;
+    vis_head_grad_kernel<<<(int)((P + 255) / 256), 256, 0, st>>>(visibility, visibility2, d_visibility, d_visibility2, vw + V.dv, P,
+                                                                n_other);
+    SNERF_LAUNCH_OK("vis_head_grad_kernel");
+    // own view: row-3 weight / bias gradients, and d hv left (relu-masked) for the main backward to accumulate onto
+    TRY((gemm<true, false>(st, 1, m.view_width, Pi, vw + V.dv, ldv, w + L.hv, m.view_width, g_w_vis, m.view_width, ep_wgrad(), splits)));
+    TRY(colsum(st, vw + V.dv, ldv, 1, P, g_b_vis));
+    TRY((gemm<false, false>(st, Pi, m.view_width, 1, vw + V.dv, ldv, w_vis, m.view_width, w + L.dhv, m.view_width,
+                            ep_dgrad(w + L.hv, m.view_width, false))));
+    for (int v = 0; v < n_other; ++v) {
+        const float* hv2 = vw + V.hv2 + (size_t)v * P * m.view_width;
+        const float* dv = vw + V.dv + 1 + v;
+        TRY((gemm<true, false>(st, 1, m.view_width, Pi, dv, ldv, hv2, m.view_width, g_w_vis, m.view_width, ep_wgrad(), splits)));
+        TRY(colsum(st, dv, ldv, 1, P, g_b_vis));
+        TRY((gemm<false, false>(st, Pi, m.view_width, 1, dv, ldv, w_vis, m.view_width, vw + V.dhv2, m.view_width,
+                                ep_dgrad(hv2, m.view_width, false))));
+        // view layer of this pass: its input is rebuilt (feature and enc_hi copied, the other view's direction encoded)
+        vis_build_input_kernel<<<(int)((P + 127) / 128), 128, 0, st>>>(w + L.xv, rays_o, rays_d, z, rays_o2, vw + V.xv2, n_rays,
+                                                                      n_samples, n_other, v, L.xv_ld, m.view_in - m.venc,
+                                                                      d.view_degree, (flags & SNERF_FLAG_NDC) != 0);
+        SNERF_LAUNCH_OK("vis_build_input_kernel");
+        TRY((gemm<true, false>(st, m.view_width, m.view_in, Pi, vw + V.dhv2, m.view_width, vw + V.xv2, L.xv_ld, grads[SNERF_P_VIEW_W],
+                               m.view_in, ep_wgrad(), splits)));
+        TRY(colsum(st, vw + V.dhv2, m.view_width, m.view_width, P, grads[SNERF_P_VIEW_B]));
+        // d feature of the other views, summed in the main backward's d-feature buffer
+        TRY((gemm<false, false>(st, Pi, m.width, m.view_width, vw + V.dhv2, m.view_width, prm[SNERF_P_VIEW_W], m.view_in, w + L.dyb,
+                                m.width, ep_dgrad(nullptr, 0, v > 0))));
+    }
+    if (n_other == 0) SNERF_CUDA_OK(cudaMemsetAsync(w + L.dyb, 0, (size_t)P * m.width * sizeof(float), st));
     return SNERF_OK;
 }
 

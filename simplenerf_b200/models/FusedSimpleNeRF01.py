@@ -46,9 +46,9 @@ class MlpBlock(torch.nn.Module):
     def __init__(self, mlp_cfg: dict):
         super().__init__()
         c = mlp_cfg
-        if c['predict_visibility']:
-            raise NotImplementedError('predict_visibility=True (secondary-view visibility head) is not built; '
-                                      'every shipped reference config sets it to False')
+        self.predict_visibility = bool(c['predict_visibility'])         # row a14 / N4: fourth row of the view head (:602-603)
+        if self.predict_visibility and not (c['use_view_dirs'] and c['view_dependent_rgb']):
+            raise NotImplementedError('predict_visibility=True needs use_view_dirs and view_dependent_rgb (as the reference configs pair them)')
         if c['views_net_depth'] != 1:
             raise NotImplementedError('views_net_depth != 1 is not built')
         self.width, self.depth = c['points_net_width'], c['points_net_depth']
@@ -71,7 +71,7 @@ class MlpBlock(torch.nn.Module):
         self.pts_output_linear = torch.nn.Linear(self.width, 1 if self.has_view else 4)
         if self.has_view:
             self.feature_linear = torch.nn.Linear(self.width, self.width)
-            self.views_output_linear = torch.nn.Linear(self.view_width, 3)
+            self.views_output_linear = torch.nn.Linear(self.view_width, 3 + int(self.predict_visibility))
         self.desc = MlpDesc(depth=self.depth, width=self.width, skip_layer=4, pts_degree=self.pts_degree,
                             trunk_degree=self.trunk_degree, view_degree=self.view_degree, view_width=self.view_width,
                             head_out=1 if self.has_view else 4)
@@ -238,6 +238,10 @@ class FusedSimpleNeRF(torch.nn.Module):
         for attr in _CTOR_ORDER:
             if attr in cfgs:
                 setattr(self, attr, MlpBlock(cfgs[attr]))
+        self.predict_visibility = any(getattr(self, a).predict_visibility for a in ('coarse_model', 'fine_model') if a in cfgs)   # :19-20
+        if self.predict_visibility:
+            raise NotImplementedError('predict_visibility=True (secondary-view visibility head): the kernels exist on the fp32 path '
+                                      '(snerf_visibility_*), the model wiring does not yet; every shipped reference config sets it to False')
         self.slots = [(a, pre, lvl) for a, _, pre, lvl in _SLOTS if a in cfgs]
         self.precision = mc.get('precision', 'bf16')
         if self.precision not in ('bf16', 'fp32'):

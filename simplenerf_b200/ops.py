@@ -12,7 +12,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import FLAG_LINDISP, FLAG_NDC, FLAG_PRECISE, FLAG_SAVE_FOR_BWD, FLAG_WHITE_BKGD, MlpDesc, P_COUNT  # noqa: F401
+from ._lib import FLAG_LINDISP, FLAG_NDC, FLAG_PRECISE, FLAG_SAVE_FOR_BWD, FLAG_VIS_GRAD, FLAG_WHITE_BKGD, MlpDesc, P_COUNT  # noqa: F401
 
 
 def _ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
@@ -193,6 +193,37 @@ def mlp_backward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, si
         finally:
             if split is not None:
                 lib.snerfdbg_set_backward_split_event(None)
+
+
+def visibility_forward(desc: MlpDesc, params, mlp_workspace, rays_o, rays_d, z, rays_o2, flags: int):
+    """Secondary-view visibility head on the workspace of a precise-path `mlp_forward` (row a14 / N4; reference
+    :317-325, :640-649, :687-715).  rays_o2 [N, nf-1, 3] or None.  -> visibility [N,S], visibility2 [N,S,nf-1] or None, workspace."""
+    n, s = z.shape
+    n_other = 0 if rays_o2 is None else rays_o2.shape[1]
+    rays_o2 = None if rays_o2 is None else _f32(rays_o2)
+    vis = torch.empty((n, s), device=z.device)
+    vis2 = torch.empty((n, s, n_other), device=z.device) if n_other else None
+    ws = torch.empty(_lib.load().snerf_visibility_workspace_bytes(C.byref(desc), n, s, n_other), dtype=torch.uint8, device=z.device)
+    LAUNCHES['count'] += 3 + 3 * n_other
+    _lib.check(_lib.load().snerf_visibility_forward(
+        C.byref(desc), pointer_table(params), _ptr(mlp_workspace, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(z), _ptr(rays_o2),
+        _ptr(vis), _ptr(vis2), _ptr(ws, torch.uint8), ws.numel(), n, s, n_other, flags, _stream()), 'snerf_visibility_forward')
+    return vis, vis2, ws
+
+
+def visibility_backward(desc: MlpDesc, params, mlp_workspace, rays_o, rays_d, z, rays_o2, vis, vis2, d_vis, d_vis2,
+                        grads: List[Optional[torch.Tensor]], workspace, flags: int) -> None:
+    """Run BEFORE mlp_backward(flags | FLAG_VIS_GRAD): adds the fourth-row / view-layer gradients to `grads` and leaves
+    d hv and d feature in the MLP workspace."""
+    n, s = z.shape
+    n_other = 0 if rays_o2 is None else rays_o2.shape[1]
+    rays_o2 = None if rays_o2 is None else _f32(rays_o2)
+    LAUNCHES['count'] += 4 + 7 * n_other
+    _lib.check(_lib.load().snerf_visibility_backward(
+        C.byref(desc), pointer_table(params), _ptr(mlp_workspace, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(z), _ptr(rays_o2),
+        _ptr(vis), _ptr(vis2), _ptr(None if d_vis is None else _f32(d_vis)), _ptr(None if d_vis2 is None else _f32(d_vis2)),
+        pointer_table(grads), _ptr(workspace, torch.uint8), workspace.numel(), n, s, n_other, flags, _stream()),
+        'snerf_visibility_backward')
 
 
 def tensor_selftest() -> List[float]:

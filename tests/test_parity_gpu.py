@@ -643,3 +643,66 @@ def test_frame_renderer_equals_model_on_oracle_rays():
     assert np.abs(got['image'].astype(np.int32) - want_img.astype(np.int32)).max() <= 1      # rays differ by ulps -> at most one grey level
     np.testing.assert_allclose(got['depth'], ro.post_process_depth(out['depth_fine'].cpu().numpy().reshape(r1 - r0, w)), rtol=2e-3, atol=2e-3)
     assert (got['depth_ndc'] >= 0).all() and np.isfinite(got['depth_var_ndc']).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# row a14 / N4: secondary-view visibility head (precise path), stage entry points vs the oracle's autograd
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('ndc', [False, True])
+def test_visibility_head_vs_oracle(ndc):
+    from simplenerf_b200._lib import FLAG_NDC, FLAG_PRECISE, FLAG_SAVE_FOR_BWD, FLAG_VIS_GRAD
+    from simplenerf_b200.models.FusedSimpleNeRF01 import MlpBlock
+    mlp_cfg = dict(synthetic.make_configs('vanilla')['model']['coarse_mlp'], predict_visibility=True)
+    spec = orc.MlpSpec(mlp_cfg)
+    state = orc.deterministic_state(spec.param_shapes(), 77)
+    block = MlpBlock(mlp_cfg)
+    block.load_state_dict(state)
+    block.to(DEV)
+    gen = torch.Generator().manual_seed(4)
+    n, s, nv = 37, 5, 2
+    rays_o = torch.rand((n, 3), generator=gen) - .5
+    rays_d = torch.nn.functional.normalize(torch.randn((n, 3), generator=gen), dim=-1)
+    rays_d[:, 2] = -rays_d[:, 2].abs() - .3
+    z = torch.sort(torch.rand((n, s), generator=gen) * (0.9 if ndc else 3.0), -1)[0]
+    vd = torch.nn.functional.normalize(torch.randn((n, 3), generator=gen), dim=-1)
+    rays_o2 = torch.rand((n, nv, 3), generator=gen) - .5
+    pts_o, pts_d = (torch.rand((n, 3), generator=gen) - .5, torch.rand((n, 3), generator=gen) - .5) if ndc else (rays_o, rays_d)
+    # oracle: points from the (ndc) rays, other-view directions from the metric rays (:317-325)
+    pts = (pts_o[:, None] + pts_d[:, None] * z[..., None]).reshape(-1, 3)
+    dirs2 = orc.other_view_dirs(z, rays_o, rays_d, rays_o2, ndc).reshape(-1, nv, 3)
+    params = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    out = orc.mlp_forward(spec, params, pts, vd[:, None].expand(n, s, 3).reshape(-1, 3), None, dirs2)
+    c = {k: torch.randn(out[k].shape, generator=gen) for k in ('sigma', 'rgb', 'visibility', 'visibility2')}
+    sum((out[k] * c[k]).sum() for k in c).backward()
+
+    flags = FLAG_PRECISE | FLAG_SAVE_FOR_BWD
+    table = [None if p is None else p.detach() for p in block.param_table()]
+    ws = torch.empty(ops.mlp_workspace_bytes(block.desc, n, s, flags), dtype=torch.uint8, device=DEV)
+    sigma, rgb = ops.mlp_forward(block.desc, table, None, cuda(pts_o), cuda(pts_d), cuda(vd), cuda(z), None, ws, flags)
+    vflags = flags | (FLAG_NDC if ndc else 0)
+    vis, vis2, vws = ops.visibility_forward(block.desc, table, ws, cuda(rays_o), cuda(rays_d), cuda(z), cuda(rays_o2), vflags)
+    tol = dict(rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(sigma.cpu().reshape(-1, 1), out['sigma'].detach(), **tol)
+    torch.testing.assert_close(vis.cpu().reshape(-1, 1), out['visibility'].detach(), **tol)
+    torch.testing.assert_close(vis2.cpu().reshape(-1, nv, 1), out['visibility2'].detach(), **tol)
+
+    grads = [None if p is None else torch.zeros_like(p) for p in table]
+    ops.visibility_backward(block.desc, table, ws, cuda(rays_o), cuda(rays_d), cuda(z), cuda(rays_o2), vis, vis2,
+                            cuda(c['visibility'].reshape(n, s)), cuda(c['visibility2'].reshape(n, s, nv)), grads, vws, vflags)
+    ops.mlp_backward(block.desc, table, None, cuda(pts_o), cuda(pts_d), cuda(vd), cuda(z), sigma, rgb, cuda(c['sigma'].reshape(n, s)),
+                     cuda(c['rgb'].reshape(n, s, 3)), grads, ws, flags | FLAG_VIS_GRAD)
+    names = dict(block.named_parameters())
+    by_ptr = {p.data_ptr(): k for k, p in names.items()}
+    for p, g in zip(table, grads):
+        if p is None:
+            continue
+        k = by_ptr[p.data_ptr()]
+        want = params[k].grad
+        scale = float(want.abs().max()) + 1e-12
+        assert float((g.cpu() - want).abs().max()) <= 2e-4 * scale + 1e-6, (k, float((g.cpu() - want).abs().max()), scale)
+    # without the visibility gradients the plain backward is unchanged (no flag, no pre-filled regions needed)
+    grads0 = [None if p is None else torch.zeros_like(p) for p in table]
+    sigma, rgb = ops.mlp_forward(block.desc, table, None, cuda(pts_o), cuda(pts_d), cuda(vd), cuda(z), None, ws, flags)
+    ops.mlp_backward(block.desc, table, None, cuda(pts_o), cuda(pts_d), cuda(vd), cuda(z), sigma, rgb, cuda(c['sigma'].reshape(n, s)),
+                     cuda(c['rgb'].reshape(n, s, 3)), grads0, ws, flags)
+    assert float(grads0[22][3].abs().max()) == 0.0          # fourth row of views_output_linear: untouched
