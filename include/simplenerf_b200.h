@@ -154,6 +154,15 @@ int snerf_visibility_backward(const snerf_mlp_desc* desc, const float* const* ho
                               const float* d_visibility2, float* const* host_grads, void* workspace, size_t workspace_bytes,
                               int n_rays, int n_samples, int n_other, uint32_t flags, void* stream);
 
+/* visibility2 map [n_rays, n_other] = sum_s weights[s] visibility2[s, v] / (acc + 1e-6)  (volume_rendering :479-482) and its
+ * backward: d_visibility2 [n_rays, n_samples, n_other]; d_weights [n_rays, n_samples] and d_acc [n_rays] are added by the
+ * caller to the incoming gradients of snerf_composite_backward.  n_other <= 8.                                          */
+int snerf_visibility2_composite_forward(const float* weights, const float* acc, const float* visibility2, float* visibility2_map,
+                                        int n_rays, int n_samples, int n_other, void* stream);
+int snerf_visibility2_composite_backward(const float* weights, const float* acc, const float* visibility2, const float* visibility2_map,
+                                         const float* d_visibility2_map, float* d_visibility2, float* d_weights, float* d_acc,
+                                         int n_rays, int n_samples, int n_other, void* stream);
+
 /* ---- (f) N1, one frame per call: rays of a camera pose and output post-processing -------------------
  * (DataPreprocessor01.py get_rays :351-368, get_ndc_rays :371-389, get_view_dirs :392-394, post_process_image
  * :1106-1109, post_process_depth :1112-1114; replaces the host numpy pass of create_test_data :807-895).

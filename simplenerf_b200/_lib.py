@@ -70,6 +70,8 @@ _SIGNATURES = {
     'snerf_visibility_forward': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp)] + [_fp] * 8 + [C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint32, _fp]),
     'snerf_visibility_backward': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp)] + [_fp] * 9 + [C.POINTER(_fp), _fp, C.c_size_t,
                                             C.c_int, C.c_int, C.c_int, C.c_uint32, _fp]),
+    'snerf_visibility2_composite_forward': (C.c_int, [_fp] * 4 + [C.c_int, C.c_int, C.c_int, _fp]),
+    'snerf_visibility2_composite_backward': (C.c_int, [_fp] * 8 + [C.c_int, C.c_int, C.c_int, _fp]),
     'snerf_tensor_selftest': (C.c_int, [C.POINTER(C.c_float), _fp]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -422,6 +422,56 @@ static int dispatch_composite(const CompositeArgs& a, bool backward, cudaStream_
     return fail(SNERF_ERR_UNSUPPORTED, "composite: %d samples per ray > 512", a.s);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row a14 / N4: visibility2 = sum_s w_s vis2[s, v] / (acc + 1e-6) per ray and other view (volume_rendering :479-482).
+// One warp per ray.  Backward: d vis2 = G w / (acc + 1e-6); d w = sum_v G_v vis2_v / (acc + 1e-6);
+// d acc = - sum_v G_v visibility2_v / (acc + 1e-6)  (acc = sum w: both are handed to the compositing backward).
+// ------------------------------------------------------------------------------------------------
+constexpr int kVis2MaxViews = 8;
+
+__global__ void __launch_bounds__(kCompWarps* kWarp) vis2_composite_fwd_kernel(const float* __restrict__ weights, const float* __restrict__ acc,
+                                                                              const float* __restrict__ vis2, float* __restrict__ out,
+                                                                              int n_rays, int s, int nv) {
+    const int ray = blockIdx.x * kCompWarps + threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    if (ray >= n_rays) return;
+    float sum[kVis2MaxViews] = {};
+    for (int k = lane; k < s; k += kWarp) {
+        const float w = weights[(size_t)ray * s + k];
+        for (int v = 0; v < nv; ++v) sum[v] += w * vis2[((size_t)ray * s + k) * nv + v];
+    }
+    const float inv = 1.f / (acc[ray] + 1e-6f);
+    for (int v = 0; v < nv; ++v) {
+        const float t = group_sum<kWarp>(sum[v]);
+        if (lane == 0) out[(size_t)ray * nv + v] = t * inv;
+    }
+}
+
+__global__ void __launch_bounds__(kCompWarps* kWarp) vis2_composite_bwd_kernel(const float* __restrict__ weights, const float* __restrict__ acc,
+                                                                              const float* __restrict__ vis2, const float* __restrict__ vis2_map,
+                                                                              const float* __restrict__ g_map, float* __restrict__ d_vis2,
+                                                                              float* __restrict__ d_weights, float* __restrict__ d_acc,
+                                                                              int n_rays, int s, int nv) {
+    const int ray = blockIdx.x * kCompWarps + threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    if (ray >= n_rays) return;
+    const float inv = 1.f / (acc[ray] + 1e-6f);
+    float g[kVis2MaxViews], dacc = 0.f;
+    for (int v = 0; v < nv; ++v) {
+        g[v] = g_map[(size_t)ray * nv + v] * inv;
+        dacc -= g[v] * vis2_map[(size_t)ray * nv + v];
+    }
+    if (lane == 0) d_acc[ray] = dacc;
+    for (int k = lane; k < s; k += kWarp) {
+        const size_t o = (size_t)ray * s + k;
+        const float w = weights[o];
+        float dw = 0.f;
+        for (int v = 0; v < nv; ++v) {
+            dw += g[v] * vis2[o * nv + v];
+            d_vis2[o * nv + v] = g[v] * w;
+        }
+        d_weights[o] = dw;
+    }
+}
+
 }  // namespace snerf
 
 using namespace snerf;
@@ -464,4 +514,30 @@ extern "C" int snerf_composite_backward(const float* sigma, const float* rgb, co
     a.g_weights = d_weights; a.d_sigma = d_sigma; a.d_rgb = d_rgb;
     a.n_rays = n_rays; a.s = n_samples; a.ndc = ndc; a.white = (flags & SNERF_FLAG_WHITE_BKGD) != 0;
     return dispatch_composite(a, true, (cudaStream_t)stream);
+}
+
+extern "C" int snerf_visibility2_composite_forward(const float* weights, const float* acc, const float* visibility2, float* visibility2_map,
+                                                   int n_rays, int n_samples, int n_other, void* stream) {
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_other >= 1 && n_other <= kVis2MaxViews,
+                  "snerf_visibility2_composite_forward: bad sizes (%d rays, %d samples, %d other views, max %d)", n_rays, n_samples, n_other,
+                  kVis2MaxViews);
+    if (n_rays == 0) return SNERF_OK;
+    SNERF_REQUIRE(weights && acc && visibility2 && visibility2_map, "snerf_visibility2_composite_forward: null pointer");
+    vis2_composite_fwd_kernel<<<ceil_div(n_rays, kCompWarps), kCompWarps * kWarp, 0, (cudaStream_t)stream>>>(weights, acc, visibility2, visibility2_map,
+                                                                                                         n_rays, n_samples, n_other);
+    SNERF_LAUNCH_OK("vis2_composite_fwd_kernel");
+    return SNERF_OK;
+}
+
+extern "C" int snerf_visibility2_composite_backward(const float* weights, const float* acc, const float* visibility2, const float* visibility2_map,
+                                                    const float* d_visibility2_map, float* d_visibility2, float* d_weights, float* d_acc,
+                                                    int n_rays, int n_samples, int n_other, void* stream) {
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_other >= 1 && n_other <= kVis2MaxViews, "snerf_visibility2_composite_backward: bad sizes");
+    if (n_rays == 0) return SNERF_OK;
+    SNERF_REQUIRE(weights && acc && visibility2 && visibility2_map && d_visibility2_map && d_visibility2 && d_weights && d_acc,
+                  "snerf_visibility2_composite_backward: null pointer");
+    vis2_composite_bwd_kernel<<<ceil_div(n_rays, kCompWarps), kCompWarps * kWarp, 0, (cudaStream_t)stream>>>(
+        weights, acc, visibility2, visibility2_map, d_visibility2_map, d_visibility2, d_weights, d_acc, n_rays, n_samples, n_other);
+    SNERF_LAUNCH_OK("vis2_composite_bwd_kernel");
+    return SNERF_OK;
 }

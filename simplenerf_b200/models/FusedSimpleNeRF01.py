@@ -25,7 +25,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .. import ops
-from .._lib import (FLAG_NDC, FLAG_PRECISE, FLAG_SAVE_FOR_BWD, FLAG_WHITE_BKGD, MlpDesc, P_COUNT, P_FEAT_B, P_FEAT_W,
+from .._lib import (FLAG_NDC, FLAG_PRECISE, FLAG_SAVE_FOR_BWD, FLAG_VIS_GRAD, FLAG_WHITE_BKGD, MlpDesc, P_COUNT, P_FEAT_B, P_FEAT_W,
                     P_HEAD_B, P_HEAD_W, P_RGB_B, P_RGB_W, P_VIEW_B, P_VIEW_W)
 
 _SLOTS = (   # attribute (reference :22-41), path in configs['model'], output-key prefix, level
@@ -160,7 +160,7 @@ class _RenderStream(torch.autograd.Function):
     reference :363-483).  Gradients flow to the MLP parameters only (rays, depths and noise are data)."""
 
     @staticmethod
-    def forward(ctx, block: MlpBlock, opts: dict, z, noise, rays_o, rays_d, pts_o, pts_d, view_dirs, *params):
+    def forward(ctx, block: MlpBlock, opts: dict, z, noise, rays_o, rays_d, pts_o, pts_d, view_dirs, rays_o2, *params):
         ndc, white = opts['ndc'], opts['white_bkgd']
         need_grad = opts['need_grad']
         flags = (FLAG_PRECISE if opts['precise'] else 0) | (FLAG_SAVE_FOR_BWD if need_grad else 0)
@@ -177,19 +177,36 @@ class _RenderStream(torch.autograd.Function):
         maps = ops.composite_forward(sigma, rgb, z, rays_o, rays_d, pts_d if ndc else None, ndc, white)
         keys = [k for k in ('rgb', 'acc', 'depth', 'depth_var', 'depth_ndc', 'depth_var_ndc', 'alpha', 'visibility',
                             'weights') if k in maps]
+        # row a14 / N4: secondary-view visibility head (:149-151, :379-382, :479-482, :640-649)
+        vis = vis2 = vws = None
+        vflags = flags | (FLAG_NDC if ndc else 0)
+        if block.predict_visibility:
+            vis, vis2, vws = ops.visibility_forward(block.desc, table, ws, rays_o, rays_d, z, rays_o2, vflags)
+            if vis2 is not None:
+                maps['visibility2'] = ops.visibility2_composite_forward(maps['weights'], maps['acc'], vis2)
+                keys.append('visibility2')
         ctx.keys = keys
         if need_grad:
             ctx.block, ctx.opts, ctx.flags, ctx.ws, ctx.packed = block, opts, flags, ws, packed
+            ctx.vis_state = (vis, vis2, vws, vflags, rays_o2, maps['weights'], maps['acc'], maps.get('visibility2'))
             ctx.save_for_backward(z, sigma, rgb, rays_o, rays_d, pts_o, pts_d, view_dirs, *params)
         ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(sigma, rgb)
-        return tuple(maps[k] for k in keys) + (sigma, rgb)
+        extra = tuple(t for t in (vis, vis2) if t is not None)
+        ctx.mark_non_differentiable(sigma, rgb, *extra)
+        return tuple(maps[k] for k in keys) + (sigma, rgb) + extra
 
     @staticmethod
     def backward(ctx, *gouts):
         z, sigma, rgb, rays_o, rays_d, pts_o, pts_d, view_dirs, *params = ctx.saved_tensors
         block, opts = ctx.block, ctx.opts
         grads_in = {k: g for k, g in zip(ctx.keys, gouts)}
+        vis, vis2, vws, vflags, rays_o2, weights, acc, vis2_map = ctx.vis_state
+        d_vis2 = None
+        if grads_in.get('visibility2') is not None:             # through the visibility2 map into the weights and acc
+            d_vis2, d_w, d_acc = ops.visibility2_composite_backward(weights, acc, vis2, vis2_map, grads_in['visibility2'])
+            grads_in['weights'] = d_w if grads_in.get('weights') is None else grads_in['weights'] + d_w
+            grads_in['acc'] = d_acc if grads_in.get('acc') is None else grads_in['acc'] + d_acc
+        grads_in.pop('visibility2', None)
         d_sigma, d_rgb = ops.composite_backward(sigma, rgb, z, rays_o, rays_d, pts_d if opts['ndc'] else None, opts['ndc'],
                                                 opts['white_bkgd'], grads_in)
         table: List[Optional[torch.Tensor]] = [None] * P_COUNT
@@ -209,10 +226,14 @@ class _RenderStream(torch.autograd.Function):
                 p, g = next(it)
                 table[i], gtable[i] = p, g.view_as(p)
                 out_grads.append(gtable[i])
+        bwd_flags = ctx.flags
+        if block.predict_visibility:      # first the head's own backward (it pre-fills d hv / d feature in the workspace)
+            ops.visibility_backward(block.desc, table, ctx.ws, rays_o, rays_d, z, rays_o2, vis, vis2, None, d_vis2, gtable, vws, vflags)
+            bwd_flags |= FLAG_VIS_GRAD
         ops.mlp_backward(block.desc, table, ctx.packed, pts_o, pts_d, view_dirs if block.view_degree else None, z, sigma,
-                         rgb, d_sigma, d_rgb, gtable, ctx.ws, ctx.flags)
-        ctx.ws = None
-        return (None,) * 9 + tuple(out_grads)
+                         rgb, d_sigma, d_rgb, gtable, ctx.ws, bwd_flags)
+        ctx.ws = ctx.vis_state = None
+        return (None,) * 10 + tuple(out_grads)
 
 
 class FusedSimpleNeRF(torch.nn.Module):
@@ -239,13 +260,13 @@ class FusedSimpleNeRF(torch.nn.Module):
             if attr in cfgs:
                 setattr(self, attr, MlpBlock(cfgs[attr]))
         self.predict_visibility = any(getattr(self, a).predict_visibility for a in ('coarse_model', 'fine_model') if a in cfgs)   # :19-20
-        if self.predict_visibility:
-            raise NotImplementedError('predict_visibility=True (secondary-view visibility head): the kernels exist on the fp32 path '
-                                      '(snerf_visibility_*), the model wiring does not yet; every shipped reference config sets it to False')
         self.slots = [(a, pre, lvl) for a, _, pre, lvl in _SLOTS if a in cfgs]
         self.precision = mc.get('precision', 'bf16')
         if self.precision not in ('bf16', 'fp32'):
             raise ValueError(f"configs['model']['precision'] must be 'bf16' or 'fp32', got {self.precision!r}")
+        if self.predict_visibility and self.precision != 'fp32':
+            raise NotImplementedError("predict_visibility=True (secondary-view visibility head, SURVEY row a14 / N4) is built on the "
+                                      "fp32 path only: set configs['model']['precision'] = 'fp32' (every shipped config has it False)")
         self.launch_rays = int(mc.get('launch_rays', 65536))
         self.randoms: DeviceRandoms = (ReferenceOrderRandoms(mc.get('netchunk')) if mc.get('rng', 'device') == 'reference'
                                        else DeviceRandoms())
@@ -260,10 +281,22 @@ class FusedSimpleNeRF(torch.nn.Module):
 
     def forward(self, input_batch: dict, retraw: bool = False, sec_views_vis: bool = False):
         retraw = retraw or self.training                                        # :74
+        sec_views_vis = sec_views_vis or self.training
         rays_o = input_batch['rays_o']
         if not rays_o.is_cuda:
             raise RuntimeError('FusedSimpleNeRF runs on CUDA only: move the batch to the GPU (no CPU fallback exists)')
         n = rays_o.shape[0]
+        if self.predict_visibility and sec_views_vis:                            # :119-133
+            input_batch = dict(input_batch)
+            if 'rays_o2' not in input_batch:          # the other views' camera centres, own view skipped (index plumbing only)
+                poses = input_batch['common_data']['poses']
+                poses = poses[0] if poses.dim() == 4 else poses                  # :69-73
+                image_id = input_batch['pixel_id'][:, 0].long()
+                cols = [poses[i + (i >= image_id).long()][:, :3, 3] for i in range(input_batch['num_frames'] - 1)]
+                input_batch['rays_o2'] = torch.stack(cols, dim=1)
+            input_batch['rays_o2'] = input_batch['rays_o2'].detach().float().contiguous()
+        elif 'rays_o2' in input_batch:
+            input_batch = {k: v for k, v in input_batch.items() if k != 'rays_o2'}
         parts: Dict[str, List[torch.Tensor]] = {}
         fixed = isinstance(self.randoms, FixedRandoms)
         for i in range(0, max(n, 1), self.launch_rays):                          # replaces batchify_rays :81-106
@@ -300,14 +333,19 @@ class FusedSimpleNeRF(torch.nn.Module):
         else:
             pts_o, pts_d = rays_o, rays_d                                        # :140
         view_dirs = f32(batch['view_dirs']) if block.use_view_dirs else rays_d
-        res = _RenderStream.apply(block, opts, z, noise, rays_o, rays_d, pts_o, pts_d, view_dirs, *params)
+        rays_o2 = batch.get('rays_o2') if block.predict_visibility else None
+        res = _RenderStream.apply(block, opts, z, noise, rays_o, rays_d, pts_o, pts_d, view_dirs, rays_o2, *params)
         keys = ['rgb', 'acc', 'depth', 'depth_var'] + (['depth_ndc', 'depth_var_ndc'] if self.ndc else []) + \
-               ['alpha', 'visibility', 'weights']
+               ['alpha', 'visibility', 'weights'] + (['visibility2'] if rays_o2 is not None else [])
         maps = dict(zip(keys, res[:len(keys)]))
         for k, v in maps.items():
             out[f'{prefix}{k}_{level}'] = v
         if retraw:                                                               # :166-168
-            sigma, rgb = res[-2], res[-1]
+            sigma, rgb = res[len(keys)], res[len(keys) + 1]
+            if block.predict_visibility:                                         # network outputs :710-713, :649
+                out[f'{prefix}raw_visibility_{level}'] = res[len(keys) + 2].unsqueeze(-1)
+                if rays_o2 is not None:
+                    out[f'{prefix}raw_visibility2_{level}'] = res[len(keys) + 3].unsqueeze(-1)
             out[f'{prefix}raw_sigma_{level}'] = sigma.unsqueeze(-1)
             out[f'{prefix}raw_rgb_{level}'] = rgb
             which = 'rgb_view_dependent' if block.has_view else 'rgb_view_independent'

@@ -226,6 +226,27 @@ def visibility_backward(desc: MlpDesc, params, mlp_workspace, rays_o, rays_d, z,
         'snerf_visibility_backward')
 
 
+def visibility2_composite_forward(weights, acc, vis2) -> torch.Tensor:
+    """visibility2 map [N, nf-1] = sum_s w vis2 / (acc + 1e-6)  (reference :479-482)."""
+    n, s, nv = vis2.shape
+    out = torch.empty((n, nv), device=vis2.device)
+    LAUNCHES['count'] += 1
+    _lib.check(_lib.load().snerf_visibility2_composite_forward(_ptr(weights), _ptr(acc), _ptr(vis2), _ptr(out), n, s, nv, _stream()),
+               'snerf_visibility2_composite_forward')
+    return out
+
+
+def visibility2_composite_backward(weights, acc, vis2, vis2_map, g_map):
+    """-> d_vis2 [N,S,nf-1], d_weights [N,S], d_acc [N] (the last two join the compositing backward's incoming gradients)."""
+    n, s, nv = vis2.shape
+    d_vis2, d_w, d_acc = torch.empty_like(vis2), torch.empty((n, s), device=vis2.device), torch.empty(n, device=vis2.device)
+    LAUNCHES['count'] += 1
+    _lib.check(_lib.load().snerf_visibility2_composite_backward(_ptr(weights), _ptr(acc), _ptr(vis2), _ptr(vis2_map), _ptr(_f32(g_map)),
+                                                                _ptr(d_vis2), _ptr(d_w), _ptr(d_acc), n, s, nv, _stream()),
+               'snerf_visibility2_composite_backward')
+    return d_vis2, d_w, d_acc
+
+
 def tensor_selftest() -> List[float]:
     errs = (C.c_float * 4)()
     _lib.check(_lib.load().snerf_tensor_selftest(errs, _stream()), 'snerf_tensor_selftest')

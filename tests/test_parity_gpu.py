@@ -706,3 +706,74 @@ def test_visibility_head_vs_oracle(ndc):
     ops.mlp_backward(block.desc, table, None, cuda(pts_o), cuda(pts_d), cuda(vd), cuda(z), sigma, rgb, cuda(c['sigma'].reshape(n, s)),
                      cuda(c['rgb'].reshape(n, s, 3)), grads0, ws, flags)
     assert float(grads0[22][3].abs().max()) == 0.0          # fourth row of views_output_linear: untouched
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_dropin_visibility_head_vs_reference_golden(tag):
+    """predict_visibility=True end to end on the fp32 path against the unmodified reference (tests/golden/render_visibility.npz):
+    case a = NDC with rays_o2 given, case b = metric depths with rays_o2 derived from the poses and the rays' view ids."""
+    g = gu.load('render_visibility.npz')
+    seed, n, ndc, given = [int(v) for v in g[f'{tag}_meta']]
+    configs = synthetic.make_configs('vanilla', ndc=bool(ndc))
+    for k in ('coarse_mlp', 'fine_mlp'):
+        configs['model'][k]['predict_visibility'] = True
+    with pytest.raises(NotImplementedError, match='fp32'):
+        get_model(configs, None)                                  # the tensor path does not carry the head
+    configs['model']['precision'] = 'fp32'
+    state = gu.full_state(configs, seed, True)
+    batch = {k[len(tag) + 4:]: v for k, v in g.items() if k.startswith(f'{tag}_in_')}
+    batch['iter_num'], batch['num_frames'] = 0, 3
+    if not given:
+        batch['common_data'] = {'poses': batch.pop('poses')[None]}
+    table = {k[len(tag) + 5:]: v for k, v in g.items() if k.startswith(f'{tag}_rnd_')}
+    model = get_model(configs, None)
+    model.load_state_dict(state)
+    model = model.to(DEV)
+    model.randoms = FixedRandoms(table)
+
+    def to_dev(b):
+        out = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in b.items()}
+        if 'common_data' in out:
+            out['common_data'] = {k: v.to(DEV) for k, v in out['common_data'].items()}
+        return out
+
+    def check(out, prefix):
+        keys = {k.split('__')[1] for k in g if k.startswith(f'{tag}_{prefix}__')}
+        assert keys <= set(out), keys - set(out)
+        for k in sorted(keys):
+            want, got = g[f'{tag}_{prefix}__{k}'], out[k].detach().cpu()
+            assert got.shape == want.shape, (k, got.shape, want.shape)
+            scale = max(1.0, float(want.abs().max())) if ('depth' in k or 'z_vals' in k) else 1.0
+            if k == 'z_vals_fine':      # a last-ulp difference in a coarse weight can move one resampled depth across a bin edge
+                assert float((got - want).abs().mean()) < 1e-5 * scale, (k, float((got - want).abs().mean()))
+                continue
+            tol = (5e-4 if '_fine' in k else 5e-5) * scale          # fine pass: resampled depths carry the coarse weights' rounding
+            if '_fine' in k and got.dim() >= 2 and got.shape[1] == 192:
+                # per-sample tensors of the fine pass follow their depths: compare where the depths agree
+                same = ((out['z_vals_fine'].detach().cpu() - g[f'{tag}_{prefix}__z_vals_fine']).abs() < 1e-5 * 10).all(-1)
+                got, want = got[same], want[same]
+            torch.testing.assert_close(got, want, rtol=0, atol=tol, msg=lambda m, k=k: f'{tag} {prefix} {k}: {m}')
+
+    model.eval()
+    with torch.no_grad():
+        out = model(to_dev(batch), retraw=True, sec_views_vis=True)
+        check(out, 'eval')
+        assert tuple(out['raw_visibility2_fine'].shape) == (n, 192, 2, 1)
+        plain = model(to_dev(batch))
+        assert not any('visibility2' in k for k in plain)
+    model.train()
+    out = model(to_dev(batch))
+    check(out, 'train')
+    loss = 0
+    for k in g:
+        if k.startswith(f'{tag}_cot__'):
+            loss = loss + (out[k.split('__')[1]] * g[k].to(DEV)).sum()
+    loss.backward()
+    for pname, prm in model.named_parameters():
+        if 'fine_model' in pname:
+            continue   # depends on the resampled depths
+        ref_norm = float(g[f'{tag}_gnorm__{pname}'][0])
+        got = prm.grad.flatten()[g[f'{tag}_gidx__{pname}'].long().to(DEV)].cpu()
+        np.testing.assert_allclose(float(prm.grad.double().norm()), ref_norm, rtol=2e-3, err_msg=pname)
+        torch.testing.assert_close(got, g[f'{tag}_gval__{pname}'], rtol=2e-2,
+                                   atol=2e-3 * ref_norm / max(1.0, prm.numel() ** 0.5) + 1e-9, msg=lambda m: f'{pname}: {m}')
