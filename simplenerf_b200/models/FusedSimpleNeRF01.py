@@ -191,8 +191,9 @@ class _RenderStream(torch.autograd.Function):
             ctx.vis_state = (vis, vis2, vws, vflags, rays_o2, maps['weights'], maps['acc'], maps.get('visibility2'))
             ctx.save_for_backward(z, sigma, rgb, rays_o, rays_d, pts_o, pts_d, view_dirs, *params)
         ctx.set_materialize_grads(False)
-        extra = tuple(t for t in (vis, vis2) if t is not None)
-        ctx.mark_non_differentiable(sigma, rgb, *extra)
+        extra = tuple(t for t in (vis, vis2) if t is not None)     # network outputs of the head: differentiable (VisibilityLoss01.py:29)
+        ctx.n_extra = len(extra)
+        ctx.mark_non_differentiable(sigma, rgb)
         return tuple(maps[k] for k in keys) + (sigma, rgb) + extra
 
     @staticmethod
@@ -201,9 +202,12 @@ class _RenderStream(torch.autograd.Function):
         block, opts = ctx.block, ctx.opts
         grads_in = {k: g for k, g in zip(ctx.keys, gouts)}
         vis, vis2, vws, vflags, rays_o2, weights, acc, vis2_map = ctx.vis_state
-        d_vis2 = None
+        tail = gouts[len(ctx.keys) + 2:]                          # gradients of raw visibility / raw visibility2, if any
+        d_vis = tail[0] if ctx.n_extra >= 1 else None
+        d_vis2 = tail[1] if ctx.n_extra >= 2 else None
         if grads_in.get('visibility2') is not None:             # through the visibility2 map into the weights and acc
-            d_vis2, d_w, d_acc = ops.visibility2_composite_backward(weights, acc, vis2, vis2_map, grads_in['visibility2'])
+            d_map, d_w, d_acc = ops.visibility2_composite_backward(weights, acc, vis2, vis2_map, grads_in['visibility2'])
+            d_vis2 = d_map if d_vis2 is None else d_vis2 + d_map
             grads_in['weights'] = d_w if grads_in.get('weights') is None else grads_in['weights'] + d_w
             grads_in['acc'] = d_acc if grads_in.get('acc') is None else grads_in['acc'] + d_acc
         grads_in.pop('visibility2', None)
@@ -228,7 +232,7 @@ class _RenderStream(torch.autograd.Function):
                 out_grads.append(gtable[i])
         bwd_flags = ctx.flags
         if block.predict_visibility:      # first the head's own backward (it pre-fills d hv / d feature in the workspace)
-            ops.visibility_backward(block.desc, table, ctx.ws, rays_o, rays_d, z, rays_o2, vis, vis2, None, d_vis2, gtable, vws, vflags)
+            ops.visibility_backward(block.desc, table, ctx.ws, rays_o, rays_d, z, rays_o2, vis, vis2, d_vis, d_vis2, gtable, vws, vflags)
             bwd_flags |= FLAG_VIS_GRAD
         ops.mlp_backward(block.desc, table, ctx.packed, pts_o, pts_d, view_dirs if block.view_degree else None, z, sigma,
                          rgb, d_sigma, d_rgb, gtable, ctx.ws, bwd_flags)

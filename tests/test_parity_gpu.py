@@ -777,3 +777,50 @@ def test_dropin_visibility_head_vs_reference_golden(tag):
         np.testing.assert_allclose(float(prm.grad.double().norm()), ref_norm, rtol=2e-3, err_msg=pname)
         torch.testing.assert_close(got, g[f'{tag}_gval__{pname}'], rtol=2e-2,
                                    atol=2e-3 * ref_norm / max(1.0, prm.numel() ** 0.5) + 1e-9, msg=lambda m: f'{pname}: {m}')
+
+
+def test_visibility_losses_through_the_dropin():
+    """The consumers of the head, restated from VisibilityLoss01.py:56-74 (two-sided MAE between the predicted visibility
+    and the transmittance, each side detached in turn) and VisibilityPriorLoss01.py:64-80 (mean over rays of the masked
+    sum of 1 - visibility2): their gradients through the drop-in equal those through the oracle."""
+    n = 24
+    configs = synthetic.make_configs('vanilla', ndc=True)
+    for k in ('coarse_mlp', 'fine_mlp'):
+        configs['model'][k]['predict_visibility'] = True
+    configs['model']['precision'] = 'fp32'
+    state = gu.full_state(configs, 9, True)
+    batch = synthetic.make_ray_batch('llff', n, 17)
+    gen = torch.Generator().manual_seed(6)
+    batch['rays_o2'] = torch.rand((n, 2, 3), generator=gen) - .5
+    prior = (torch.rand((n, 2), generator=gen) < 0.6).float()
+    table = {'t_rand': torch.rand((n, 64), generator=gen), 'u': torch.rand((n, 128), generator=gen)}
+    for slot in orc.model_slots(configs):
+        table[f'noise_{slot}'] = torch.randn((n * (192 if 'fine' in slot else 64), 1), generator=gen)
+
+    def losses(out, prior):
+        total = 0
+        for level in ('coarse', 'fine'):
+            pred, target = out[f'raw_visibility_{level}'][..., 0], out[f'visibility_{level}']
+            total = total + (pred - target.detach()).abs().mean(1).mean() + (pred.detach() - target).abs().mean(1).mean()
+            total = total + 0.01 * (prior * (1 - out[f'visibility2_{level}'])).sum(1).mean()
+        return total
+
+    oracle = orc.NerfOracle(configs)
+    oracle.load_state_dict(state)
+    oracle.randoms = orc.FixedRandoms(table)
+    oracle.train()
+    want = losses(oracle(batch), prior)
+    want.backward()
+    model = get_model(configs, None)
+    model.load_state_dict(state)
+    model = model.to(DEV).train()
+    model.randoms = FixedRandoms(table)
+    got = losses(model({k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}), prior.to(DEV))
+    torch.testing.assert_close(got.detach().cpu(), want.detach(), rtol=1e-4, atol=1e-6)
+    got.backward()
+    ref = dict(oracle.named_parameters())
+    for pname, prm in model.named_parameters():
+        if 'fine_model' in pname:
+            continue
+        rel = float((prm.grad.cpu() - ref[pname].grad).norm() / (ref[pname].grad.norm() + 1e-20))
+        assert rel <= 2e-3, (pname, rel)
