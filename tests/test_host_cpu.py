@@ -155,3 +155,26 @@ def test_fused_loss_computer_plumbing_without_gpu():
         FusedLossComputer(configs).compute_losses(dict(inp, iter_num=100), out)
     with pytest.raises(NotImplementedError):
         FusedLossComputer(configs).compute_losses(inp, out, return_loss_maps=True)
+
+
+def test_argument_validation_of_the_next_row_entry_points(lib):
+    """Loss, gather and visibility-head entry points reject bad arguments before any launch (no GPU needed)."""
+    streams = (_lib.LossStream * 1)()
+    assert lib.snerf_ray_losses_forward(streams, 1, 4, None, None, None, 0, None) == 1          # null pred / target
+    assert b'null' in lib.snerf_last_error()
+    assert lib.snerf_ray_losses_forward(streams, 9, 4, None, None, None, 0, None) == 1 and b'streams' in lib.snerf_last_error()
+    assert lib.snerf_ray_losses_workspace_bytes() >= 148 * 8 * 8
+    assert lib.snerf_ray_losses_backward(streams, 0, 4, None, None, None) == 1
+    args = _lib.ReprojArgs()
+    assert lib.snerf_reprojection_losses_forward(ctypes.byref(args), 4, None, None, None, None, 0, None) == 1
+    assert b'other depths' in lib.snerf_last_error()
+    tables = (_lib.GatherTable * 1)()
+    assert lib.snerf_gather_rows(tables, 1, None, 0, None) == 0                                 # empty batch: nothing to do
+    assert lib.snerf_gather_rows(tables, 1, None, 3, None) == 1
+    assert lib.snerf_gather_rows(tables, 99, None, 3, None) == 1 and b'tables' in lib.snerf_last_error()
+    good = MlpBlock(synthetic.make_configs()['model']['coarse_mlp']).desc
+    assert lib.snerf_visibility_workspace_bytes(ctypes.byref(good), 16, 64, 2) > 0
+    noview = MlpBlock(synthetic.make_configs('simplenerf')['model']['views_augmentation']['coarse_mlp']).desc
+    assert lib.snerf_visibility_workspace_bytes(ctypes.byref(noview), 16, 64, 2) == 0           # no view branch, no head
+    assert lib.snerf_visibility2_composite_forward(None, None, None, None, 4, 64, 9, None) == 1  # more than 8 other views
+    assert lib.snerf_visibility2_composite_forward(None, None, None, None, 0, 64, 2, None) == 0
