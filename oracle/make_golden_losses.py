@@ -94,6 +94,35 @@ def reprojection_golden(store):
               {k: int((store[f'{tag}_grad_{k}'] != 0).sum()) for k in out})
 
 
+PAIR_LOSSES = [dict(name='PointsAugmentationDepthLoss01', weight=0.3), dict(name='ViewsAugmentationDepthLoss01', weight=0.2),
+               dict(name='CoarseFineConsistencyLoss01', weight=0.5), dict(name='DenseDepthMSE01', weight=0.7)]
+
+
+def pair_golden(store):
+    """The plain two-sided depth losses and the dense-depth MSE.  DenseDepthMSE01 slices the fine depth with an attribute it
+    never sets (`self.num_rays`, :41): the attribute is supplied here (= the batch size) so that the module can run at all."""
+    cfg = json.load(open('/root/reference/runs/training/train1021/Configs.json'))
+    cfg['losses'] = PAIR_LOSSES
+    computer = LossComputer(cfg)
+    n, tag = 333, 'p'
+    inp, out = case(n, 31)
+    g = torch.Generator().manual_seed(32)
+    inp['dense_depth_values'] = 1 + 4 * torch.rand((n, 1), generator=g)
+    computer.losses['DenseDepthMSE01'].num_rays = n
+    res = computer.compute_losses(dict(inp), out)
+    res['TotalLoss'].backward()
+    for k, v in inp.items():
+        if isinstance(v, torch.Tensor):
+            store[f'{tag}_in_{k}'] = v.numpy()
+    for k, v in out.items():
+        store[f'{tag}_out_{k}'] = v.detach().numpy()
+        store[f'{tag}_grad_{k}'] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy()
+    for lc in PAIR_LOSSES:
+        store[f"{tag}_loss_{lc['name']}"] = np.float32(float(res[lc['name']]['loss_value'].detach()))
+    store[f'{tag}_loss_TotalLoss'] = np.float32(float(res['TotalLoss'].detach()))
+    print(tag, {k: float(v) for k, v in store.items() if k.startswith(f'{tag}_loss_')})
+
+
 def main():
     cfg = json.load(open('/root/reference/runs/training/train1021/Configs.json'))
     cfg['losses'] = [lc for lc in cfg['losses'] if 'MSE' in lc['name']]       # the six masked means of the shipped config
@@ -114,6 +143,7 @@ def main():
             store[f'{tag}_loss_{name}'] = np.float32(float(res[name]['loss_value'].detach()))
         store[f'{tag}_loss_TotalLoss'] = np.float32(float(res['TotalLoss'].detach()))
     reprojection_golden(store)
+    pair_golden(store)
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'losses.npz'), **store)
     print('wrote tests/golden/losses.npz', {k: float(v) for k, v in store.items() if k.endswith('TotalLoss')})
 

@@ -1,6 +1,8 @@
 """Host mirror of the reference's loss front end for the masked per-ray losses.
 
-`FusedLossComputer(configs).compute_losses(input_dict, output_dict)` has the contract of
+Fused: MSE01-03, SparseDepthMSE01-03, DenseDepthMSE01, PointsAugmentationDepthLoss01/02, ViewsAugmentationDepthLoss01/02,
+CoarseFineConsistencyLoss01/02 (13 of the reference's 15 loss modules; VisibilityLoss01 / VisibilityPriorLoss01 go through
+`extra_losses`).  `FusedLossComputer(configs).compute_losses(input_dict, output_dict)` has the contract of
 `loss_functions.LossComputer01.LossComputer.compute_losses` (src/loss_functions/LossComputer01.py:33-52): it returns
 `{loss_name: {'loss_value': tensor}, ..., 'TotalLoss': tensor}` and `TotalLoss.backward()` fills the gradients of the
 model outputs.  The six losses that are plain masked means -- MSE01/02/03 (MSE01.py:26-67) and SparseDepthMSE01/02/03
@@ -31,6 +33,10 @@ _DEPTH = {'SparseDepthMSE01': (None, ''), 'SparseDepthMSE02': ('points_augmentat
 _REPROJ = {'PointsAugmentationDepthLoss02': ('points_augmentation', 'points_augmentation_depth_coarse'),
            'ViewsAugmentationDepthLoss02': ('views_augmentation', 'views_augmentation_depth_coarse'),
            'CoarseFineConsistencyLoss02': (None, 'depth_fine')}
+# plain (unmasked) MSE between two model depths, gradients to BOTH sides: name -> (config sub-key or None, other depth key per level)
+_PAIR = {'PointsAugmentationDepthLoss01': ('points_augmentation', 'points_augmentation_depth_{level}'),
+         'ViewsAugmentationDepthLoss01': ('views_augmentation', 'views_augmentation_depth_{level}'),
+         'CoarseFineConsistencyLoss01': (None, None)}
 FUSED_LOSSES = tuple(_RGB) + tuple(_DEPTH)
 
 
@@ -244,6 +250,17 @@ class FusedLossComputer:
             self._tables = (key, view_tables(poses, intrinsics))
         return self._tables[1]
 
+    @staticmethod
+    def _align_mirror(owner, mirror):
+        out, j = [None] * len(owner), 0
+        for i, tag in enumerate(owner):
+            if tag is None:
+                while mirror[j] is None:
+                    j += 1
+                out[i] = mirror[j]
+                j += 1
+        return out
+
     def _reprojection_plan(self, name: str):
         """(other depth key) if the reference module would compute a coarse pair, else None (:44-51, CoarseFine :34-37)."""
         model = self.configs['model']
@@ -259,6 +276,7 @@ class FusedLossComputer:
             raise NotImplementedError('loss maps are a validation-time output; use the reference LossComputer for them')
         iter_num = input_dict['iter_num']
         preds, targets, masks, weights, owner = [], [], [], [], []
+        mirror: list = []       # per stream: None, or the weight of a gradient-only mirror stream (two-sided losses)
         reproj: Dict[tuple, list] = {}
         extra_total = 0
         loss_values: Dict[str, dict] = {}
@@ -274,6 +292,37 @@ class FusedLossComputer:
                     weights.append(weight)
                     owner.append(name)
                 if not plan:
+                    loss_values[name] = {'loss_value': torch.zeros((), device=input_dict['rays_o'].device)}
+            elif name == 'DenseDepthMSE01' and name not in self.extra_losses:
+                # masked MSE against the dense depth prior (DenseDepthMSE01.py:26-68).  The reference slices the fine depth with
+                # an attribute it never sets (`self.num_rays`, :41) and cannot run with a fine MLP; here the whole batch is used.
+                for level in ('coarse', 'fine'):
+                    if f'{level}_mlp' in self.configs['model']:
+                        preds.append(output_dict[f'depth_{level}'])
+                        targets.append(input_dict['dense_depth_values'][:, 0])
+                        masks.append(input_dict['indices_mask_nerf'])
+                        weights.append(weight)
+                        owner.append(name)
+            elif name in _PAIR and name not in self.extra_losses:
+                # mean((a - b)^2) over every ray with gradients to both depths (PointsAugmentationDepthLoss01.py:27-74,
+                # CoarseFineConsistencyLoss01.py:25-49): stream (a | b) carries the value and a's gradient, stream (b | a)
+                # carries b's gradient only (its value enters the total as v - v.detach()).
+                model = self.configs['model']
+                sub, other = _PAIR[name]
+                if sub is None:
+                    pairs = [('depth_coarse', 'depth_fine')] if ('coarse_mlp' in model and 'fine_mlp' in model) else []
+                else:
+                    pairs = [(f'depth_{lv}', other.format(level=lv)) for lv in ('coarse', 'fine')
+                             if f'{lv}_mlp' in model and f'{lv}_mlp' in model[sub]]
+                for a_key, b_key in pairs:
+                    for p_key, t_key, tag in ((a_key, b_key, name), (b_key, a_key, None)):
+                        preds.append(output_dict[p_key])
+                        targets.append(output_dict[t_key].detach())
+                        masks.append(None)
+                        weights.append(weight if tag else 0.0)
+                        owner.append(tag)
+                        mirror.append(None if tag else weight)
+                if not pairs:
                     loss_values[name] = {'loss_value': torch.zeros((), device=input_dict['rays_o'].device)}
             elif name in _REPROJ and name not in self.extra_losses:
                 other_key = self._reprojection_plan(name)
@@ -297,6 +346,7 @@ class FusedLossComputer:
                     extra_total = extra_total + weight * loss_dict['loss_value']
             elif weight != 0:
                 raise RuntimeError(f'Unknown Loss Function: {name} (not fused; pass an object for it in extra_losses)')
+        mirror_full = self._align_mirror(owner, mirror)      # stream index -> weight of a gradient-only mirror stream
         total = extra_total
         scales = None
         if self.ray_sharded:
@@ -308,12 +358,16 @@ class FusedLossComputer:
             sl = slice(i, i + _lib.LOSS_MAX_STREAMS)
             values = ray_losses(preds[sl], targets[sl], masks[sl], weights[sl])
             for j, name in enumerate(owner[sl]):        # a module with a coarse and a fine stream reports their sum (MSE01.py:35,42)
+                if name is None:                        # gradient-only mirror of a two-sided loss
+                    total = total + mirror_full[i + j] * (values[j] - values[j].detach())
+                    continue
                 prev = loss_values.get(name, {}).get('loss_value')
                 loss_values[name] = {'loss_value': values[j] if prev is None else prev + values[j]}
             if scales is None:
                 total = total + values[-1]
             else:       # per-stream weight * count scale, applied on the device
-                w = torch.stack([by_ptr[m.data_ptr()] * wt for m, wt in zip(masks[sl], weights[sl])])
+                one = torch.ones((), device=values.device)
+                w = torch.stack([(one if m is None else by_ptr[m.data_ptr()]) * wt for m, wt in zip(masks[sl], weights[sl])])
                 total = total + (values[:-1] * w).sum()
         if reproj:
             cd = input_dict['common_data']

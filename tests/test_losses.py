@@ -251,3 +251,46 @@ def test_train_step_driver_runs_the_whole_iteration():
         assert set(losses) == {lc['name'] for lc in LOSSES + REPROJ} | {'TotalLoss'}
         totals.append(float(losses['TotalLoss']))
     assert all(torch.isfinite(torch.tensor(totals))) and totals[-1] < totals[0], totals
+
+
+PAIRS = [dict(name='PointsAugmentationDepthLoss01', weight=0.3), dict(name='ViewsAugmentationDepthLoss01', weight=0.2),
+         dict(name='CoarseFineConsistencyLoss01', weight=0.5), dict(name='DenseDepthMSE01', weight=0.7)]
+PAIR_KEYS = {'PointsAugmentationDepthLoss01': ('depth_coarse', 'points_augmentation_depth_coarse'),
+             'ViewsAugmentationDepthLoss01': ('depth_coarse', 'views_augmentation_depth_coarse'),
+             'CoarseFineConsistencyLoss01': ('depth_coarse', 'depth_fine')}
+
+
+def test_two_sided_depth_losses_oracle_matches_reference():
+    """PointsAugmentationDepthLoss01.py:59-74, CoarseFineConsistencyLoss01.py:37-41: mean((a - b)^2) over every ray with
+    gradients to both sides; DenseDepthMSE01.py:56-68: the masked mean against the dense depth prior (coarse and fine)."""
+    g = gu.load('losses.npz')
+    inp, out = _case(g, 'p')
+    total = 0
+    for lc in PAIRS:
+        if lc['name'] in PAIR_KEYS:
+            a, b = (out[k] for k in PAIR_KEYS[lc['name']])
+            loss = torch.mean(torch.square(a - b))
+        else:
+            loss = sum(loss_oracle.masked_mse(out[k], inp['dense_depth_values'][:, 0], inp['indices_mask_nerf']) for k in ('depth_coarse', 'depth_fine'))
+        torch.testing.assert_close(loss.detach(), g[f"p_loss_{lc['name']}"], rtol=1e-6, atol=0)
+        total = total + lc['weight'] * loss
+    torch.testing.assert_close(total.detach(), g['p_loss_TotalLoss'], rtol=1e-6, atol=0)
+    total.backward()
+    for k, v in out.items():
+        got = v.grad if v.grad is not None else torch.zeros_like(v)
+        torch.testing.assert_close(got, g[f'p_grad_{k}'], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_fused_two_sided_depth_losses_match_reference():
+    g = gu.load('losses.npz')
+    configs = dict(synthetic.make_configs('simplenerf'), losses=[dict(lc) for lc in PAIRS])
+    inp, out = _case(g, 'p', 'cuda:0')
+    res = FusedLossComputer(configs).compute_losses(inp, out)
+    for lc in PAIRS:
+        torch.testing.assert_close(res[lc['name']]['loss_value'].detach().cpu(), g[f"p_loss_{lc['name']}"], rtol=RTOL, atol=1e-9)
+    torch.testing.assert_close(res['TotalLoss'].detach().cpu(), g['p_loss_TotalLoss'], rtol=RTOL, atol=0)
+    res['TotalLoss'].backward()
+    for k, v in out.items():
+        got = v.grad.cpu() if v.grad is not None else torch.zeros(v.shape)
+        torch.testing.assert_close(got, g[f'p_grad_{k}'], rtol=1e-5, atol=1e-9)
