@@ -194,13 +194,18 @@ int snerf_adam_step(float* const* params, const float* const* grads, float* cons
  * SparseDepthMSE01/02/03.compute_depth_loss (SparseDepthMSE01.py:58-71, one channel).  The weighted sum is
  * LossComputer.compute_losses (LossComputer01.py:33-52).  The table is a HOST array; its pointers are device pointers. */
 #define SNERF_LOSS_MAX_STREAMS 8
+#define SNERF_LOSS_SQUARED 0          /* mean over channels and masked rays of (pred - target)^2                     */
+#define SNERF_LOSS_ABSOLUTE 1         /* ... of |pred - target|        (VisibilityLoss01.compute_mae, :70-74)        */
+#define SNERF_LOSS_PRIOR_SHORTFALL 2  /* mean over masked rays of sum_c target_c (1 - pred_c)
+                                         (VisibilityPriorLoss01.compute_consistency_loss, :64-80; target = prior)   */
 typedef struct snerf_loss_stream {
     const float* pred;    /* [n_rays, channels]                                       */
     const float* target;  /* [n_rays, channels]                                       */
     const uint8_t* mask;  /* [n_rays] bool; nullable = every ray                      */
     float* grad;          /* [n_rays, channels], written by the backward call only    */
-    int32_t channels;     /* 3 (rgb) or 1 (depth); 1..4                               */
+    int32_t channels;     /* 3 (rgb), 1 (depth), nf-1 or the samples per ray; 1..1024 */
     float weight;         /* loss weight (LossComputer.get_loss_weight)               */
+    int32_t kind;         /* SNERF_LOSS_SQUARED / _ABSOLUTE / _PRIOR_SHORTFALL        */
 } snerf_loss_stream;
 size_t snerf_ray_losses_workspace_bytes(void);
 /* values[n_streams + 1]: the mean of every stream (0 when its mask is empty), then the weighted total;
@@ -209,7 +214,8 @@ size_t snerf_ray_losses_workspace_bytes(void);
 int snerf_ray_losses_forward(const snerf_loss_stream* streams, int n_streams, int n_rays, float* values,
                              int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 /* grad_values[n_streams + 1] (device): incoming gradient of `values`; stream s receives
- * (grad_values[s] + grad_values[n_streams] * weight_s) * 2 (pred - target) / (count_s * channels) on masked rays, else 0. */
+ * (grad_values[s] + grad_values[n_streams] * weight_s) * 2 (pred - target) / (count_s * channels) on masked rays, else 0
+ * (sign(pred - target) / (count_s * channels) and -target / count_s for the other two kinds).                           */
 int snerf_ray_losses_backward(const snerf_loss_stream* streams, int n_streams, int n_rays, const int32_t* counts,
                               const float* grad_values, void* stream);
 

@@ -123,6 +123,43 @@ def pair_golden(store):
     print(tag, {k: float(v) for k, v in store.items() if k.startswith(f'{tag}_loss_')})
 
 
+VIS_LOSSES = [dict(name='VisibilityLoss01', weight=0.4), dict(name='VisibilityPriorLoss01', weight=0.25)]
+
+
+def visibility_golden(store):
+    """VisibilityLoss01 / VisibilityPriorLoss01 on synthetic model outputs of the visibility head (vanilla model block)."""
+    cfg = json.load(open('/root/reference/runs/training/train1021/Configs.json'))
+    cfg['losses'] = VIS_LOSSES
+    computer = LossComputer(cfg)
+    for tag, with_prior in (('v', True), ('w', False)):
+        n = 60
+        g = torch.Generator().manual_seed(51 + int(with_prior))
+        out = {}
+        for level, s in (('coarse', 16), ('fine', 24)):
+            out[f'raw_visibility_{level}'] = torch.rand((n, s, 1), generator=g).requires_grad_()
+            out[f'visibility_{level}'] = torch.rand((n, s), generator=g).requires_grad_()
+            out[f'visibility2_{level}'] = torch.rand((n, 2), generator=g).requires_grad_()
+            out[f'raw_visibility2_{level}'] = torch.rand((n, s, 2, 1), generator=g)
+        out['raw_visibility_coarse'].data[3, 5, 0] = out['visibility_coarse'].data[3, 5]      # |0|: zero gradient on both sides
+        inp = {'iter_num': 100, 'num_frames': 3, 'rays_o': torch.zeros(n, 3), 'indices_mask_nerf': torch.rand((n,), generator=g) < 0.7}
+        if with_prior:
+            inp['visibility_prior_masks'] = (torch.rand((n, 2), generator=g) < 0.5).float()
+        res = computer.compute_losses(dict(inp), out)
+        res['TotalLoss'].backward()
+        for k, v in inp.items():
+            if isinstance(v, torch.Tensor):
+                store[f'{tag}_in_{k}'] = v.numpy()
+        for k, v in out.items():
+            if k.startswith('raw_visibility2'):
+                continue
+            store[f'{tag}_out_{k}'] = v.detach().numpy()
+            store[f'{tag}_grad_{k}'] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy()
+        for lc in VIS_LOSSES:
+            store[f"{tag}_loss_{lc['name']}"] = np.float32(float(res[lc['name']]['loss_value'].detach()))
+        store[f'{tag}_loss_TotalLoss'] = np.float32(float(res['TotalLoss'].detach()))
+        print(tag, {k: float(v) for k, v in store.items() if k.startswith(f'{tag}_loss_')})
+
+
 def main():
     cfg = json.load(open('/root/reference/runs/training/train1021/Configs.json'))
     cfg['losses'] = [lc for lc in cfg['losses'] if 'MSE' in lc['name']]       # the six masked means of the shipped config
@@ -144,6 +181,7 @@ def main():
         store[f'{tag}_loss_TotalLoss'] = np.float32(float(res['TotalLoss'].detach()))
     reprojection_golden(store)
     pair_golden(store)
+    visibility_golden(store)
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'losses.npz'), **store)
     print('wrote tests/golden/losses.npz', {k: float(v) for k, v in store.items() if k.endswith('TotalLoss')})
 

@@ -20,7 +20,10 @@ class MlpDesc(C.Structure):
 
 class LossStream(C.Structure):
     _fields_ = [('pred', C.c_void_p), ('target', C.c_void_p), ('mask', C.c_void_p), ('grad', C.c_void_p),
-                ('channels', C.c_int32), ('weight', C.c_float)]
+                ('channels', C.c_int32), ('weight', C.c_float), ('kind', C.c_int32)]
+
+
+LOSS_SQUARED, LOSS_ABSOLUTE, LOSS_PRIOR_SHORTFALL = 0, 1, 2
 
 
 class ReprojArgs(C.Structure):

@@ -27,6 +27,7 @@ struct LossTable {
     float* grad[SNERF_LOSS_MAX_STREAMS];
     float weight[SNERF_LOSS_MAX_STREAMS];
     int channels[SNERF_LOSS_MAX_STREAMS];
+    int kind[SNERF_LOSS_MAX_STREAMS];
     int n_streams;
 };
 
@@ -37,11 +38,14 @@ struct LossWorkspace {
     unsigned int ticket;
 };
 
-__device__ __forceinline__ float sq_err(const float* __restrict__ p, const float* __restrict__ t, int i, int c) {
+// per-ray contribution of one stream: squared error (MSE01.py:56-57), absolute error (VisibilityLoss01.py:70-72) or the
+// prior-weighted shortfall sum_c target_c (1 - pred_c) (VisibilityPriorLoss01.py:76-78)
+__device__ __forceinline__ float ray_term(const float* __restrict__ p, const float* __restrict__ t, int i, int c, int kind) {
     float e = 0.f;
     for (int k = 0; k < c; ++k) {
-        const float d = p[(size_t)i * c + k] - t[(size_t)i * c + k];
-        e += d * d;
+        const float pv = p[(size_t)i * c + k], tv = t[(size_t)i * c + k];
+        const float d = pv - tv;
+        e += kind == SNERF_LOSS_SQUARED ? d * d : kind == SNERF_LOSS_ABSOLUTE ? fabsf(d) : tv * (1.f - pv);
     }
     return e;
 }
@@ -59,7 +63,7 @@ __global__ void __launch_bounds__(kLossThreads) ray_losses_fwd_kernel(const __gr
         const uint8_t* m = t.mask[s];
         for (int i = blockIdx.x * kLossThreads + threadIdx.x; i < n_rays; i += gridDim.x * kLossThreads) {
             if (m == nullptr || m[i]) {
-                sum += sq_err(t.pred[s], t.target[s], i, t.channels[s]);
+                sum += ray_term(t.pred[s], t.target[s], i, t.channels[s], t.kind[s]);
                 cnt += 1;
             }
         }
@@ -91,7 +95,9 @@ __global__ void __launch_bounds__(kLossThreads) ray_losses_fwd_kernel(const __gr
             sum += __ldcg(&ws->sums[b][threadIdx.x]);
             cnt += __ldcg(&ws->counts[b][threadIdx.x]);
         }
-        const float v = cnt > 0 ? sum / ((float)cnt * (float)t.channels[threadIdx.x]) : 0.f;   // MSE01.py:58
+        // mean over channels and rays (MSE01.py:57-58); the prior-weighted sum is a mean over rays only (VisibilityPriorLoss01.py:78-79)
+        const float per_ray = t.kind[threadIdx.x] == SNERF_LOSS_PRIOR_SHORTFALL ? 1.f : (float)t.channels[threadIdx.x];
+        const float v = cnt > 0 ? sum / ((float)cnt * per_ray) : 0.f;
         values[threadIdx.x] = v;
         counts[threadIdx.x] = cnt;
         s_sum[0][threadIdx.x] = v * t.weight[threadIdx.x];
@@ -112,7 +118,9 @@ __global__ void __launch_bounds__(kLossThreads) ray_losses_bwd_kernel(const __gr
     for (int s = 0; s < t.n_streams; ++s) {
         const int c = t.channels[s], cnt = counts[s];
         const float coeff = g_values[s] + g_total * t.weight[s];
-        const float scale = cnt > 0 ? coeff * 2.f / ((float)cnt * (float)c) : 0.f;
+        const int kind = t.kind[s];
+        const float per_ray = kind == SNERF_LOSS_PRIOR_SHORTFALL ? 1.f : (float)c;
+        const float scale = cnt > 0 ? coeff / ((float)cnt * per_ray) : 0.f;
         const uint8_t* m = t.mask[s];
         const float* p = t.pred[s];
         const float* tg = t.target[s];
@@ -121,7 +129,11 @@ __global__ void __launch_bounds__(kLossThreads) ray_losses_bwd_kernel(const __gr
             const bool on = m == nullptr || m[i];
             for (int k = 0; k < c; ++k) {
                 const size_t o = (size_t)i * c + k;
-                g[o] = on ? scale * (p[o] - tg[o]) : 0.f;
+                const float d = p[o] - tg[o];
+                const float dv = kind == SNERF_LOSS_SQUARED ? 2.f * d
+                               : kind == SNERF_LOSS_ABSOLUTE ? (d > 0.f ? 1.f : d < 0.f ? -1.f : 0.f)     // torch.abs: sign, 0 at 0
+                                                            : -tg[o];
+                g[o] = on ? scale * dv : 0.f;
             }
         }
     }
@@ -317,10 +329,13 @@ static int fill_table(LossTable& t, const snerf_loss_stream* streams, int n_stre
     for (int s = 0; s < n_streams; ++s) {
         SNERF_REQUIRE(streams[s].pred && streams[s].target, "%s: stream %d has a null pointer", who, s);
         SNERF_REQUIRE(!need_grad || streams[s].grad, "%s: stream %d has no gradient buffer", who, s);
-        SNERF_REQUIRE(streams[s].channels >= 1 && streams[s].channels <= 4, "%s: stream %d has %d channels (1..4)", who, s,
+        SNERF_REQUIRE(streams[s].channels >= 1 && streams[s].channels <= 1024, "%s: stream %d has %d channels (1..1024)", who, s,
                       streams[s].channels);
+        SNERF_REQUIRE(streams[s].kind >= SNERF_LOSS_SQUARED && streams[s].kind <= SNERF_LOSS_PRIOR_SHORTFALL, "%s: stream %d has kind %d",
+                      who, s, streams[s].kind);
         t.pred[s] = streams[s].pred; t.target[s] = streams[s].target; t.mask[s] = streams[s].mask;
         t.grad[s] = streams[s].grad; t.weight[s] = streams[s].weight; t.channels[s] = streams[s].channels;
+        t.kind[s] = streams[s].kind;
     }
     return SNERF_OK;
 }

@@ -1,8 +1,7 @@
 """Host mirror of the reference's loss front end for the masked per-ray losses.
 
 Fused: MSE01-03, SparseDepthMSE01-03, DenseDepthMSE01, PointsAugmentationDepthLoss01/02, ViewsAugmentationDepthLoss01/02,
-CoarseFineConsistencyLoss01/02 (13 of the reference's 15 loss modules; VisibilityLoss01 / VisibilityPriorLoss01 go through
-`extra_losses`).  `FusedLossComputer(configs).compute_losses(input_dict, output_dict)` has the contract of
+CoarseFineConsistencyLoss01/02, VisibilityLoss01, VisibilityPriorLoss01 -- all 15 loss modules of the reference.  `FusedLossComputer(configs).compute_losses(input_dict, output_dict)` has the contract of
 `loss_functions.LossComputer01.LossComputer.compute_losses` (src/loss_functions/LossComputer01.py:33-52): it returns
 `{loss_name: {'loss_value': tensor}, ..., 'TotalLoss': tensor}` and `TotalLoss.backward()` fills the gradients of the
 model outputs.  The six losses that are plain masked means -- MSE01/02/03 (MSE01.py:26-67) and SparseDepthMSE01/02/03
@@ -76,7 +75,7 @@ class _RayLosses(torch.autograd.Function):
     """values[n+1] = per-stream masked means, then their weighted sum; preds are differentiable."""
 
     @staticmethod
-    def forward(ctx, targets, masks, weights, workspace, *preds):
+    def forward(ctx, targets, masks, weights, kinds, workspace, *preds):
         n_streams, n_rays = len(preds), preds[0].shape[0]
         dev = preds[0].device
         table = (_lib.LossStream * n_streams)()
@@ -94,7 +93,7 @@ class _RayLosses(torch.autograd.Function):
             table[s].pred, table[s].target = ops._ptr(p32), ops._ptr(t32)
             table[s].mask = ops._ptr(m8, torch.uint8)
             table[s].grad = None
-            table[s].channels, table[s].weight = p32.shape[1], float(w)
+            table[s].channels, table[s].weight, table[s].kind = p32.shape[1], float(w), int(kinds[s])
         values = torch.empty(n_streams + 1, device=dev, dtype=torch.float32)
         counts = torch.empty(n_streams, device=dev, dtype=torch.int32)
         ops.LAUNCHES['count'] += 1
@@ -102,6 +101,7 @@ class _RayLosses(torch.autograd.Function):
                                                         ops._ptr(workspace, torch.uint8), workspace.numel(), ops._stream()),
                    'snerf_ray_losses_forward')
         ctx.keep, ctx.counts, ctx.weights, ctx.shapes = keep, counts, [float(w) for w in weights], [p.shape for p in preds]
+        ctx.kinds = [int(k) for k in kinds]
         return values
 
     @staticmethod
@@ -113,11 +113,11 @@ class _RayLosses(torch.autograd.Function):
             g = torch.empty_like(p32)
             grads.append(g)
             table[s].pred, table[s].target, table[s].mask = ops._ptr(p32), ops._ptr(t32), ops._ptr(m8, torch.uint8)
-            table[s].grad, table[s].channels, table[s].weight = ops._ptr(g), p32.shape[1], ctx.weights[s]
+            table[s].grad, table[s].channels, table[s].weight, table[s].kind = ops._ptr(g), p32.shape[1], ctx.weights[s], ctx.kinds[s]
         ops.LAUNCHES['count'] += 1
         _lib.check(_lib.load().snerf_ray_losses_backward(table, n_streams, n_rays, ops._ptr(ctx.counts, torch.int32),
                                                          ops._ptr(ops._f32(g_values)), ops._stream()), 'snerf_ray_losses_backward')
-        return (None, None, None, None) + tuple(g.reshape(shape) for g, shape in zip(grads, ctx.shapes))
+        return (None,) * 5 + tuple(g.reshape(shape) for g, shape in zip(grads, ctx.shapes))
 
 
 class _ReprojectionLosses(torch.autograd.Function):
@@ -222,13 +222,15 @@ def _workspace(dev: torch.device) -> torch.Tensor:
 
 
 def ray_losses(preds: Sequence[torch.Tensor], targets: Sequence[torch.Tensor], masks: Sequence[Optional[torch.Tensor]],
-               weights: Sequence[float]) -> torch.Tensor:
-    """values[len(preds) + 1]: masked mean squared error of every stream, then sum_s weights[s] * values[s]."""
+               weights: Sequence[float], kinds: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """values[len(preds) + 1]: masked mean of every stream, then sum_s weights[s] * values[s].  kinds[s]: _lib.LOSS_SQUARED
+    (default: squared error), LOSS_ABSOLUTE (absolute error) or LOSS_PRIOR_SHORTFALL (sum_c target_c (1 - pred_c) per ray)."""
     if not 1 <= len(preds) <= _lib.LOSS_MAX_STREAMS:
         raise RuntimeError(f'{len(preds)} loss streams (1..{_lib.LOSS_MAX_STREAMS} per call)')
     if not preds[0].is_cuda:
         raise RuntimeError('simplenerf_b200 kernels need CUDA tensors (no CPU fallback exists)')
-    return _RayLosses.apply(list(targets), list(masks), list(weights), _workspace(preds[0].device), *preds)
+    kinds = [_lib.LOSS_SQUARED] * len(preds) if kinds is None else list(kinds)
+    return _RayLosses.apply(list(targets), list(masks), list(weights), kinds, _workspace(preds[0].device), *preds)
 
 
 class FusedLossComputer:
@@ -276,6 +278,7 @@ class FusedLossComputer:
             raise NotImplementedError('loss maps are a validation-time output; use the reference LossComputer for them')
         iter_num = input_dict['iter_num']
         preds, targets, masks, weights, owner = [], [], [], [], []
+        kinds: Dict[int, int] = {}     # stream index -> kind, for the streams that are not squared errors
         mirror: list = []       # per stream: None, or the weight of a gradient-only mirror stream (two-sided losses)
         reproj: Dict[tuple, list] = {}
         extra_total = 0
@@ -293,6 +296,34 @@ class FusedLossComputer:
                     owner.append(name)
                 if not plan:
                     loss_values[name] = {'loss_value': torch.zeros((), device=input_dict['rays_o'].device)}
+            elif name == 'VisibilityLoss01' and name not in self.extra_losses:
+                # two-sided MAE between the predicted visibility and the transmittance, each side detached in turn
+                # (VisibilityLoss01.py:26-74): stream (pred | T) moves the head, stream (T | pred) moves sigma; no ray mask
+                for level in ('coarse', 'fine'):
+                    if f'{level}_mlp' in self.configs['model']:
+                        a, b = output_dict[f'raw_visibility_{level}'][..., 0], output_dict[f'visibility_{level}']
+                        for p_t, t_t in ((a, b), (b, a)):
+                            kinds[len(preds)] = _lib.LOSS_ABSOLUTE
+                            preds.append(p_t)
+                            targets.append(t_t.detach())
+                            masks.append(None)
+                            weights.append(weight)
+                            owner.append(name)
+            elif name == 'VisibilityPriorLoss01' and name not in self.extra_losses:
+                # mean over the NeRF rays of sum_v prior_v (1 - visibility2_v)  (VisibilityPriorLoss01.py:25-80)
+                model = self.configs['model']
+                levels = [lv for lv in ('coarse', 'fine') if f'{lv}_mlp' in model]
+                if any(f'raw_visibility2_{lv}' not in output_dict for lv in levels):         # :29-31: the module returns None
+                    continue
+                prior = input_dict.get('visibility_prior_masks', input_dict.get('visibility_prior_weights'))
+                for lv in levels:
+                    pred = output_dict[f'visibility2_{lv}']
+                    kinds[len(preds)] = _lib.LOSS_PRIOR_SHORTFALL
+                    preds.append(pred)
+                    targets.append(torch.ones_like(pred).detach() if prior is None else prior.to(pred.dtype))
+                    masks.append(input_dict['indices_mask_nerf'])
+                    weights.append(weight)
+                    owner.append(name)
             elif name == 'DenseDepthMSE01' and name not in self.extra_losses:
                 # masked MSE against the dense depth prior (DenseDepthMSE01.py:26-68).  The reference slices the fine depth with
                 # an attribute it never sets (`self.num_rays`, :41) and cannot run with a fine MLP; here the whole batch is used.
@@ -356,7 +387,8 @@ class FusedLossComputer:
             by_ptr = {m.data_ptr(): scales[k] for k, m in named.items()}
         for i in range(0, len(preds), _lib.LOSS_MAX_STREAMS):
             sl = slice(i, i + _lib.LOSS_MAX_STREAMS)
-            values = ray_losses(preds[sl], targets[sl], masks[sl], weights[sl])
+            values = ray_losses(preds[sl], targets[sl], masks[sl], weights[sl],
+                                [kinds.get(i + j, _lib.LOSS_SQUARED) for j in range(len(preds[sl]))])
             for j, name in enumerate(owner[sl]):        # a module with a coarse and a fine stream reports their sum (MSE01.py:35,42)
                 if name is None:                        # gradient-only mirror of a two-sided loss
                     total = total + mirror_full[i + j] * (values[j] - values[j].detach())

@@ -141,7 +141,7 @@ def test_fused_loss_computer_plumbing_without_gpu():
     weight is not 0; CPU tensors are refused before any kernel is reached."""
     from simplenerf_b200.loss_functions import FusedLossComputer
     configs = dict(synthetic.make_configs('simplenerf'),
-                   losses=[{'name': 'VisibilityPriorLoss01', 'iter_weights': {'0': 0, '100': 0.5}}])
+                   losses=[{'name': 'SomeOtherLoss01', 'iter_weights': {'0': 0, '100': 0.5}}])
 
     class Extra:
         def compute_loss(self, input_dict, output_dict, return_loss_maps=False):
@@ -149,8 +149,8 @@ def test_fused_loss_computer_plumbing_without_gpu():
 
     inp, out = {'iter_num': 50, 'rays_o': torch.zeros(2, 3)}, {'x': torch.tensor(3.0)}
     assert float(FusedLossComputer(configs).compute_losses(inp, out)['TotalLoss']) == 0             # weight 0: skipped
-    got = FusedLossComputer(configs, extra_losses={'VisibilityPriorLoss01': Extra()}).compute_losses(dict(inp, iter_num=100), out)
-    assert float(got['TotalLoss']) == 3.0 and float(got['VisibilityPriorLoss01']['loss_value']) == 6.0
+    got = FusedLossComputer(configs, extra_losses={'SomeOtherLoss01': Extra()}).compute_losses(dict(inp, iter_num=100), out)
+    assert float(got['TotalLoss']) == 3.0 and float(got['SomeOtherLoss01']['loss_value']) == 6.0
     with pytest.raises(RuntimeError, match='Unknown Loss Function'):
         FusedLossComputer(configs).compute_losses(dict(inp, iter_num=100), out)
     with pytest.raises(NotImplementedError):

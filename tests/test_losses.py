@@ -75,7 +75,7 @@ def test_stream_plan_follows_the_reference_modules():
 
 
 def test_unknown_loss_raises_and_cpu_tensors_are_refused():
-    configs = dict(_configs(), losses=LOSSES + [dict(name='VisibilityPriorLoss01', iter_weights={'0': 0, '10000': 0.1})])
+    configs = dict(_configs(), losses=LOSSES + [dict(name='SomeOtherLoss01', iter_weights={'0': 0, '10000': 0.1})])
     g = gu.load('losses.npz')
     inp, out = _case(g, 'b')
     with pytest.raises(RuntimeError, match='CUDA'):
@@ -294,3 +294,53 @@ def test_fused_two_sided_depth_losses_match_reference():
     for k, v in out.items():
         got = v.grad.cpu() if v.grad is not None else torch.zeros(v.shape)
         torch.testing.assert_close(got, g[f'p_grad_{k}'], rtol=1e-5, atol=1e-9)
+
+
+VIS = [dict(name='VisibilityLoss01', weight=0.4), dict(name='VisibilityPriorLoss01', weight=0.25)]
+
+
+def _vis_case(g, tag, device='cpu'):
+    inp, out = _case(g, tag, device)
+    inp['num_frames'] = 3
+    for level in ('coarse', 'fine'):      # VisibilityPriorLoss01.py:29-31 only looks for the key
+        out[f'raw_visibility2_{level}'] = torch.zeros(1, device=device)
+    return inp, out
+
+
+@pytest.mark.parametrize('tag', ['v', 'w'])
+def test_visibility_losses_oracle_matches_reference(tag):
+    """VisibilityLoss01.py:56-74 (two-sided MAE, each side detached in turn) and VisibilityPriorLoss01.py:64-80 (mean over the
+    NeRF rays of sum_v prior_v (1 - visibility2_v); prior = ones when the batch carries none, :38-41)."""
+    g = gu.load('losses.npz')
+    inp, out = _vis_case(g, tag)
+    prior = inp.get('visibility_prior_masks', torch.ones(inp['rays_o'].shape[0], 2))
+    mae = sum((out[f'raw_visibility_{lv}'][..., 0] - out[f'visibility_{lv}'].detach()).abs().mean(1).mean() +
+              (out[f'raw_visibility_{lv}'][..., 0].detach() - out[f'visibility_{lv}']).abs().mean(1).mean() for lv in ('coarse', 'fine'))
+    m = inp['indices_mask_nerf']
+    pri = sum((prior[m] * (1 - out[f'visibility2_{lv}'][m])).sum(1).mean() for lv in ('coarse', 'fine'))
+    torch.testing.assert_close(mae.detach(), g[f'{tag}_loss_VisibilityLoss01'], rtol=1e-6, atol=0)
+    torch.testing.assert_close(pri.detach(), g[f'{tag}_loss_VisibilityPriorLoss01'], rtol=1e-6, atol=0)
+    (0.4 * mae + 0.25 * pri).backward()
+    for k, v in out.items():
+        if f'{tag}_grad_{k}' in g:
+            torch.testing.assert_close(v.grad if v.grad is not None else torch.zeros_like(v), g[f'{tag}_grad_{k}'], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['v', 'w'])
+def test_fused_visibility_losses_match_reference(tag):
+    g = gu.load('losses.npz')
+    configs = dict(synthetic.make_configs('vanilla'), losses=[dict(lc) for lc in VIS])
+    inp, out = _vis_case(g, tag, 'cuda:0')
+    res = FusedLossComputer(configs).compute_losses(inp, out)
+    for lc in VIS:
+        torch.testing.assert_close(res[lc['name']]['loss_value'].detach().cpu(), g[f"{tag}_loss_{lc['name']}"], rtol=RTOL, atol=1e-9)
+    torch.testing.assert_close(res['TotalLoss'].detach().cpu(), g[f'{tag}_loss_TotalLoss'], rtol=RTOL, atol=0)
+    res['TotalLoss'].backward()
+    for k, v in out.items():
+        if f'{tag}_grad_{k}' in g:
+            got = v.grad.cpu() if v.grad is not None else torch.zeros(v.shape)
+            torch.testing.assert_close(got, g[f'{tag}_grad_{k}'], rtol=1e-5, atol=1e-9)
+    # without the head's outputs the prior loss is skipped like the reference's `return None`
+    del out['raw_visibility2_fine']
+    assert 'VisibilityPriorLoss01' not in FusedLossComputer(configs).compute_losses(inp, out)
