@@ -1,6 +1,6 @@
 """Per-parameter gradient error of the bf16 tensor path and the fp32 precise path vs CPU autograd."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
 from oracle import nerf_oracle as orc

@@ -1,6 +1,6 @@
 """bf16 tensor-path MLP forward vs the fp32 precise path on the same device (quick numerics probe)."""
 import sys, os, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
 from oracle import nerf_oracle as orc

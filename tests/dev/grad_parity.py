@@ -1,6 +1,6 @@
 """Gradient parity of the drop-in (bf16 tensor path) against the fp32 CPU oracle under a coherent training loss."""
 import sys, os, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
 import golden_util as gu

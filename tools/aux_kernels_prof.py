@@ -1,7 +1,7 @@
 """One launch of every non-MLP kernel of the path (samplers, compositing, losses, batch gather) for an ncu capture:
    ncu --set full -k "regex:sample_|composite_|ray_losses|reproj_|gather_rows" python tools/aux_kernels_prof.py"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from simplenerf_b200 import ops
 from simplenerf_b200.batching import gather_rows
@@ -30,8 +30,9 @@ preds = [r(m, 3).requires_grad_() for _ in range(4)] + [r(m).requires_grad_() fo
 mask = r(m) < 0.75
 vals = ray_losses(preds, [r(m, 3)] * 4 + [r(m)] * 4, [mask] * 4 + [~mask] * 4, [1.0] * 4 + [0.1] * 4)
 vals[-1].backward()
-import golden_util as gu
-f = gu.load('losses.npz')
+import numpy as np
+with np.load(os.path.join(ROOT, 'tests', 'golden', 'losses.npz')) as _f:      # inputs only: a fixture file, no oracle code
+    f = {k: torch.from_numpy(_f[k]) for k in _f.files if k.startswith('r_')}
 inp = {k[5:]: v.to(DEV) for k, v in f.items() if k.startswith('r_in_')}
 cd = {k[9:]: v.to(DEV) for k, v in f.items() if k.startswith('r_common_')}
 out = {k[6:]: v.to(DEV).requires_grad_() for k, v in f.items() if k.startswith('r_out_')}
