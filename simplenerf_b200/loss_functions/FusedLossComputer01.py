@@ -247,9 +247,12 @@ class FusedLossComputer:
         self._tables = None                                      # (key, per-view tables) of the last poses seen
 
     def _view_tables(self, poses, intrinsics):
-        key = (poses.data_ptr(), poses._version, intrinsics.data_ptr(), intrinsics._version, tuple(poses.shape))
+        """Per-view tables, recomputed only when the poses / intrinsics change.  The key is the tensors' storage, offset, shape
+        and version counter; the cache holds the tensors themselves, so their storage cannot be freed and handed to
+        different data under the same address while the entry lives."""
+        key = tuple((t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), t._version) for t in (poses, intrinsics))
         if self._tables is None or self._tables[0] != key:
-            self._tables = (key, view_tables(poses, intrinsics))
+            self._tables = (key, view_tables(poses, intrinsics), (poses, intrinsics))
         return self._tables[1]
 
     @staticmethod
