@@ -88,7 +88,7 @@ class HostBatchStager:
     copy stream, double buffered, so the copy of batch i+1 travels under the kernels of batch i.
 
         stager = HostBatchStager(example_batch, device)          # layout from an example (keys, shapes, dtypes)
-        host = stager.host_views(slot)                            # dict of pinned views: fill them in place (or `stage` copies)
+        stager.wait_host(slot); host = stager.host_views(slot)    # dict of pinned views: fill them in place (or `stage` copies)
         stager.submit(slot)                                       # async copy on the copy stream
         batch = stager.device_batch(slot)                         # the compute stream waits for that copy only
         ...                                                       # run the step on `batch`
@@ -110,6 +110,7 @@ class HostBatchStager:
         self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(slots)]
         self.copy_stream = torch.cuda.Stream(self.device)
         self.copied = [torch.cuda.Event() for _ in range(slots)]
+        self.submitted = [False] * slots      # a host -> device copy out of the slot's pinned buffer has been enqueued
         self.free = [None] * slots            # event after the last kernel that read the slot
 
     def _views(self, buf: torch.Tensor) -> Dict:
@@ -118,11 +119,19 @@ class HostBatchStager:
             out[k] = buf[off:off + nbytes].view(dtype).view(shape)
         return out
 
+    def wait_host(self, slot: int) -> None:
+        """Block the host until the last copy OUT of the slot's pinned buffer has finished: the host runs ahead of the device,
+        and overwriting the buffer earlier would change the data of a copy that is still queued."""
+        if self.submitted[slot]:
+            self.copied[slot].synchronize()
+
     def host_views(self, slot: int) -> Dict:
+        """Pinned views to fill in place; call `wait_host(slot)` first when the slot has been submitted before."""
         return self._views(self.host[slot])
 
     def stage(self, slot: int, batch: Dict) -> None:
         """Copy a host batch into the slot's pinned buffer (skip when the loader fills `host_views` directly) and submit."""
+        self.wait_host(slot)
         views = self.host_views(slot)
         for k, _, _, _, _ in self.layout:
             views[k].copy_(batch[k])
@@ -134,6 +143,7 @@ class HostBatchStager:
                 self.copy_stream.wait_event(self.free[slot])
             self.dev[slot].copy_(self.host[slot], non_blocking=True)
             self.copied[slot].record(self.copy_stream)
+        self.submitted[slot] = True
 
     def device_batch(self, slot: int) -> Dict:
         torch.cuda.current_stream(self.device).wait_event(self.copied[slot])
