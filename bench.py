@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 RAYS_PER_GPU = 4096
 # DRAM bytes of the three MLP kernels per 4096-ray step (dram__bytes_read.sum + dram__bytes_write.sum, summed over the 12
-# launches of one step): profiles/r1_final_ncu_full_summary.md.  Algorithmic figure: forward
+# launches of one step): profiles/r1_final3_ncu_full_summary.md.  Algorithmic figure: forward
 # 5.0 + dgrad 5.25 + wgrad 10.8 KB/point x 1 572 864 points = 33.1 GB.
 MLP_DRAM_BYTES_PER_STEP = 31.39e9
 # algorithmic GB per step and kernel: main / fine / pts-aug MLPs keep 9.5 panels x 512 B per point (4.75 KB) + 0.25 KB of
@@ -390,7 +390,7 @@ def run_ours(args):
             'roofline': {'bound': 'tensor', 'kernel': 'tc_forward_kernel + tc_dgrad_kernel + tc_wgrad_kernel (all 4 MLPs)',
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
                          'traffic': MLP_DRAM_BYTES_PER_STEP, 'peak_source': pk['source'],
-                         'traffic_note': 'DRAM bytes per step of the same three kernels (12 launches), ncu --set full, profiles/r1_final_ncu_full_summary.md',
+                         'traffic_note': 'DRAM bytes per step of the same three kernels (12 launches), ncu --set full, profiles/r1_final3_ncu_full_summary.md',
                          # the training step moves 31.5 GB through HBM for 5.3 TFLOP: it sits between the two roofs
                          'hbm': {'achieved': MLP_DRAM_BYTES_PER_STEP / (mlp_total * 1e-3) / 1e9, 'peak': pk['hbm'], 'unit': 'GB/s',
                                  'frac': MLP_DRAM_BYTES_PER_STEP / (mlp_total * 1e-3) / 1e9 / pk['hbm']},
