@@ -34,12 +34,18 @@ def _mask8(m: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return m.contiguous().view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8).contiguous()
 
 
-def gather_rows(entries, indices: torch.Tensor) -> None:
-    """entries: list of (src [M, ...], dst [N, ...], mask [N] or None); dst[i] = src[indices[i]] where the mask holds, else -1."""
+def gather_rows(entries, indices: torch.Tensor, check_bounds: bool = False) -> None:
+    """entries: list of (src [M, ...], dst [N, ...], mask [N] or None); dst[i] = src[indices[i]] where the mask holds, else -1.
+    check_bounds: validate 0 <= indices < M for every table first (one device synchronisation; the kernel itself does not check)."""
     n = indices.shape[0]
     if not indices.is_cuda:
         raise RuntimeError('simplenerf_b200 kernels need CUDA tensors (no CPU fallback exists)')
     indices = indices.to(torch.int64).contiguous()
+    if check_bounds and n:
+        lo, hi = int(indices.min()), int(indices.max())
+        rows = min(src.shape[0] for src, _, _ in entries)
+        if lo < 0 or hi >= rows:
+            raise IndexError(f'gather_rows: indices span [{lo}, {hi}] but the smallest source table has {rows} rows')
     lib = _lib.load()
     for i in range(0, len(entries), _lib.GATHER_MAX_TABLES):
         part = entries[i:i + _lib.GATHER_MAX_TABLES]
@@ -112,6 +118,7 @@ class HostBatchStager:
         self.copied = [torch.cuda.Event() for _ in range(slots)]
         self.submitted = [False] * slots      # a host -> device copy out of the slot's pinned buffer has been enqueued
         self.free = [None] * slots            # event after the last kernel that read the slot
+        self.handed_out = [False] * slots     # device_batch(slot) was called and release(slot) has not been yet
 
     def _views(self, buf: torch.Tensor) -> Dict:
         out = dict(self.passthrough)
@@ -138,6 +145,10 @@ class HostBatchStager:
         self.submit(slot)
 
     def submit(self, slot: int) -> None:
+        if self.handed_out[slot]:
+            # the caller forgot release(slot): everything it has enqueued so far on the compute stream may still read the
+            # slot's device buffer, so order the copy after all of it (conservative) instead of racing
+            self.release(slot)
         with torch.cuda.stream(self.copy_stream):
             if self.free[slot] is not None:
                 self.copy_stream.wait_event(self.free[slot])
@@ -146,13 +157,17 @@ class HostBatchStager:
         self.submitted[slot] = True
 
     def device_batch(self, slot: int) -> Dict:
+        if not self.submitted[slot]:
+            raise RuntimeError(f'HostBatchStager.device_batch({slot}): nothing has been submitted to this slot')
         torch.cuda.current_stream(self.device).wait_event(self.copied[slot])
+        self.handed_out[slot] = True
         return self._views(self.dev[slot])
 
     def release(self, slot: int) -> None:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self.free[slot] = ev
+        self.handed_out[slot] = False
 
     @property
     def bytes_per_batch(self) -> int:

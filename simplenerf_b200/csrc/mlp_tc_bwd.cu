@@ -45,10 +45,11 @@ struct BwdParams {
     const uint8_t* packed;
     const uint8_t* act;
     const uint8_t* bits;          // ReLU sign bits written by the forward kernel (kBitsTileBytes per tile)
-    uint8_t* dy;
+    RingCtl ring;                 // destination of the gradient panels
     const float *sigma, *rgb, *d_sigma, *d_rgb, *w_rgb;
     long long n_points;
     int n_tiles, n_steps, has_view;
+    int n_pairs;                  // CTA pairs running the chain
     uint32_t tile_stash_bytes;
     TcStep steps[kMaxSteps];
 };
@@ -68,9 +69,7 @@ struct BwdBars {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_constant__ BwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
+__device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, const int pair_index) {
     BwdBars* bars = (BwdBars*)(smem + kBOffBars);
     float* s_wrgb = (float*)(smem + kBOffConst);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -99,10 +98,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    const int n_pairs = (int)gridDim.x / 2, pi = (int)blockIdx.x / 2;
+    // Group g of pair pi = super tiles 2 (g n_pairs + pi) and + 1 in slots 0 / 1: the four tiles a pair has in flight are
+    // consecutive, and tiles are produced in (roughly) increasing order over the whole launch -- the order in which the
+    // wgrad CTAs consume them, which is what lets a small ring make progress.  Every pair runs the
+    // same number of whole groups; tiles >= n_tiles are dummies.
+    const int n_pairs = p.n_pairs, pi = pair_index;
     const int n_super = (p.n_tiles + 1) / 2;
-    const int my_super = (n_super + n_pairs - 1) / n_pairs;     // uniform over pairs; tiles >= n_tiles are dummies
-    auto tile_of = [&](int i) { return 2 * (pi + i * n_pairs) + (int)rank; };
+    const int my_super = 2 * ((n_super + 2 * n_pairs - 1) / (2 * n_pairs));
+    auto tile_of = [&](int i) { return 2 * (2 * ((i >> 1) * n_pairs + pi) + (i & 1)) + (int)rank; };
     const int pv = p.has_view ? 1 : 0;
     const int n_events = p.n_steps + pv;                        // stash events per tile and slot
 
@@ -333,19 +336,46 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
             }
         }
     } else if (warp == kWarpStash) {
-        // ======================= stash writer: every gradient panel -> HBM for the wgrad kernel =======================
+        // ======================= stash writer: every gradient panel -> the ring read by the wgrad CTAs =======================
+        // Entry tile % cap of the slot's ring; before overwriting an entry its previous tile must have been copied out by
+        // every consumer, and a tile is announced (ready flag) once its bulk store has COMPLETED -- checked one event late
+        // (wait_group 1), so that the store's latency hides under the next job.
         if (lane == 0) {
+            const RingCtl& ring = p.ring;
+            uint32_t* pend_flag = nullptr;
+            uint32_t pend_val = 0;
+            auto flush = [&]() {
+                if (pend_flag) { fence_proxy_async_all(); st_release_gpu(pend_flag, pend_val); pend_flag = nullptr; }
+            };
+            auto emit = [&](const int tile, const int slot, const uint8_t* src, const uint32_t bytes) {
+                const uint32_t e = (uint32_t)tile % ring.cap;
+                if (ring.use_flags && (uint32_t)tile >= ring.cap) {
+                    const uint32_t want = (uint32_t)tile - ring.cap + 1u;
+                    for (int k = 0; k < ring.n_consumers[slot]; ++k) {
+                        const uint32_t* f = ring.consumed + ((size_t)k * kDySlots + slot) * ring.cap + e;
+                        if (!flag_reached(f, want)) {
+                            if (pend_flag) { bulk_wait_all<0>(); flush(); }     // never sit on an unannounced tile while waiting
+                            flag_wait_ge(f, want);
+                        }
+                    }
+                    fence_proxy_async_all();
+                }
+                bulk_s2g(ring.base + ring_slot_off(slot, ring.cap) + (size_t)e * ring_entry_bytes(slot), src, bytes);
+                bulk_commit();
+                bulk_wait_read<0>();
+                if (ring.use_flags) {
+                    if (pend_flag) { bulk_wait_all<1>(); flush(); }
+                    pend_flag = ring.ready + (size_t)slot * ring.cap + e;
+                    pend_val = (uint32_t)tile + 1u;
+                }
+            };
             for (int g = 0; 2 * g < my_super; ++g) {
                 const bool two = 2 * g + 1 < my_super;
                 if (pv) {
                     for (int x = 0; x < (two ? 2 : 1); ++x) {
                         const int tile = tile_of(2 * g + x);
                         mbar_wait(&bars->pro_local[x], g & 1);
-                        if (tile < p.n_tiles) {
-                            bulk_s2g(p.dy + (size_t)tile * p.tile_stash_bytes + (size_t)9 * 65536, smem + kBOffH + x * 65536, 2 * kPanelBytes);
-                            bulk_commit();
-                            bulk_wait_read<0>();
-                        }
+                        if (tile < p.n_tiles) emit(tile, 9, smem + kBOffH + x * 65536, 2 * kPanelBytes);
                         mbar_arrive(&bars->stash_done[x]);
                     }
                 }
@@ -354,16 +384,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
                         const uint32_t jx = (uint32_t)(g * p.n_steps + s);
                         const int tile = tile_of(2 * g + x);
                         mbar_wait(&bars->stash_ready[x], jx & 1);
-                        if (tile < p.n_tiles) {
-                            bulk_s2g(p.dy + (size_t)tile * p.tile_stash_bytes + (size_t)p.steps[s].slot * 65536, smem + kBOffH + x * 65536, 4 * kPanelBytes);
-                            bulk_commit();
-                            bulk_wait_read<0>();
-                        }
+                        if (tile < p.n_tiles) emit(tile, p.steps[s].slot, smem + kBOffH + x * 65536, 4 * kPanelBytes);
                         mbar_arrive(&bars->stash_done[x]);
                         if (s == p.n_steps - 1) mbar_arrive(&bars->slot_free[x]);
                     }
             }
             bulk_wait_all<0>();
+            flush();
         }
     }
     __syncwarp();
@@ -371,6 +398,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_c
     __syncthreads();
     cluster_sync_all();
     if (warp == kWarpMma) tmem_dealloc2<512>(tmem);
+}
+
+// the chain alone (two-kernel form)
+__global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_constant__ BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    dgrad_role(p, smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u), (int)blockIdx.x / 2);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
 }
 
 // =================================================================================================
@@ -397,7 +430,7 @@ struct WgJob {
     uint8_t n_segs;
     uint16_t aux_off;             // byte offset / 1024 of the computed panels inside a stage
     uint8_t with_head;            // MMA job whose B operand is h8: the reducer warps also form dW_head = d head_pre^T h8
-    uint8_t pad;
+    uint8_t ring_k;               // which of the dY slot's consumers this job is (index into RingCtl::consumed)
     int16_t cta0, n_cta;          // CTAs [cta0, cta0 + n_cta) own this job; CTA cta0 + i takes tiles i, i + n_cta, ...
     float* dw;
     float* db;
@@ -406,7 +439,9 @@ struct WgJob {
 };
 
 struct WgParams {
-    const uint8_t *act, *dy;
+    const uint8_t* act;
+    RingCtl ring;                 // source of the gradient panels
+    int n_clusters, spread;       // fused launch: total clusters; spread != 0 interleaves chain pairs and weight-gradient clusters
     const float *rays_o, *rays_d, *view_dirs, *z, *sigma, *rgb, *d_sigma, *d_rgb;
     long long n_points;
     int n_samples, n_tiles, n_jobs, pts_degree, view_degree, head_out;
@@ -429,9 +464,7 @@ __device__ __forceinline__ float bf16_at(const uint8_t* panel_base, int r, int c
     return __uint_as_float((uint32_t)bits << 16);
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
+__device__ __forceinline__ void wgrad_role(const WgParams& p, uint8_t* smem, const int cta) {
     WgBars* bars = (WgBars*)(smem + kWgOffBars);
     float* s_dh = (float*)(smem + kWgOffDh);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -456,9 +489,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     // this CTA owns and is flushed once (fp32 reductions), so the flush traffic is one matrix per CTA
     int jb = -1;
     for (int j = 0; j < p.n_jobs; ++j)
-        if ((int)blockIdx.x >= p.jobs[j].cta0 && (int)blockIdx.x < p.jobs[j].cta0 + p.jobs[j].n_cta) jb = j;
+        if (cta >= p.jobs[j].cta0 && cta < p.jobs[j].cta0 + p.jobs[j].n_cta) jb = j;
     const WgJob& job = p.jobs[jb < 0 ? 0 : jb];
-    const int part = (int)blockIdx.x - job.cta0, nparts = job.n_cta;
+    const int part = cta - job.cta0, nparts = job.n_cta;
+    const RingCtl& ring = p.ring;
     const long long t_start = clock64();
     const int my_tiles = (jb < 0 || part >= p.n_tiles) ? 0 : (p.n_tiles - part + nparts - 1) / nparts;
     const int n_stages = my_tiles * 2;
@@ -466,18 +500,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     if (warp == 0) {
         // ======================= loader: stashed panels -> smem stages =======================
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(job.a_panels + job.b_panels) * kHalfPanel;
+            const int n_a = (p.debug & 64) ? 0 : job.a_panels, n_b = (p.debug & 32) ? 0 : job.b_panels;    // debug bits 5 / 6: skip the B / A copies
+            const uint32_t bytes = (uint32_t)(n_a + n_b) * kHalfPanel;
             for (int sg = 0; sg < n_stages; ++sg) {
                 const int tile = part + (sg >> 1) * nparts, half = sg & 1;
                 const uint32_t stage = sg % kWgStages, round = sg / kWgStages;
                 if (round > 0) mbar_wait_sleep(&bars->empty[stage], (round - 1) & 1, 32);
                 uint8_t* dst = smem + stage * kWgStageBytes;
-                mbar_arrive_expect_tx(&bars->full[stage], bytes);
+                const uint32_t e = (uint32_t)tile % ring.cap;
+                if (job.a_panels && ring.use_flags && half == 0) {       // the dgrad pair has finished writing this tile's panels
+                    flag_wait_ge(ring.ready + (size_t)job.a_slot * ring.cap + e, (uint32_t)tile + 1u);
+                    fence_proxy_async_all();
+                }
+                if (bytes) mbar_arrive_expect_tx(&bars->full[stage], bytes); else mbar_arrive(&bars->full[stage]);
                 const size_t toff = (size_t)tile * p.tile_stash_bytes + (size_t)half * kHalfPanel;
-                for (int j = 0; j < job.a_panels; ++j)
-                    bulk_g2s(dst + j * kHalfPanel, p.dy + toff + (size_t)job.a_slot * 65536 + j * kPanelBytes, kHalfPanel,
-                             &bars->full[stage]);
-                for (int j = 0; j < job.b_panels; ++j)
+                const uint8_t* dy = ring.base + ring_slot_off(job.a_slot, ring.cap) + (size_t)e * ring_entry_bytes(job.a_slot) + (size_t)half * kHalfPanel;
+                for (int j = 0; j < n_a; ++j)
+                    bulk_g2s(dst + j * kHalfPanel, dy + j * kPanelBytes, kHalfPanel, &bars->full[stage]);
+                for (int j = 0; j < n_b; ++j)
                     bulk_g2s(dst + 32768 + j * kHalfPanel, p.act + toff + (size_t)job.b_slot * 65536 + j * kPanelBytes,
                              kHalfPanel, &bars->full[stage]);
             }
@@ -492,6 +532,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             for (int sg = 0; sg < n_stages; ++sg) {
                 const uint32_t stage = sg % kWgStages;
                 mbar_wait(&bars->full[stage], (sg / kWgStages) & 1);
+                if (job.a_panels && ring.use_flags && (sg & 1)) {        // both halves of the tile are in shared memory: the ring entry may be reused
+                    const int tile = part + (sg >> 1) * nparts;
+                    st_release_gpu(ring.consumed + ((size_t)job.ring_k * kDySlots + job.a_slot) * ring.cap + (uint32_t)tile % ring.cap,
+                                   (uint32_t)tile + 1u);
+                }
                 if (job.kind != 0) { mbar_arrive(&bars->empty[stage]); continue; }
                 if (aux) mbar_wait(&bars->aux_ready[stage], (sg / kWgStages) & 1);
                 tc_fence_after();
@@ -671,7 +716,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                 tc_fence_before();
             }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 12 && warp < 16) {     // (the fused launch has 23 warps: the rest idle through the weight-gradient role)
         // ======================= encoders: recomputed encoding operands =======================
         const int e = (warp - 12) * 32 + lane;
         const int r = e >> 1, hf = e & 1;
@@ -738,8 +783,35 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (p.trace && threadIdx.x == 0) { p.trace[2 * blockIdx.x] = jb; p.trace[2 * blockIdx.x + 1] = clock64() - t_start; }
+    if (p.trace && threadIdx.x == 0) { p.trace[2 * cta] = jb; p.trace[2 * cta + 1] = clock64() - t_start; }
     if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// the weight-gradient jobs alone (two-kernel form)
+__global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    wgrad_role(p, smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u), (int)blockIdx.x);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
+}
+
+// Fused form: ONE launch in which CTA pairs [0, n_pairs) run the dgrad chain and the remaining CTAs run the weight-gradient
+// jobs on the gradient panels the pairs publish through the ring -- producer and consumer are co-resident by construction
+// (one CTA per SM, grid <= SM count), so the hand-off cannot starve, also when a profiler serialises kernels.
+constexpr uint32_t kFusedSmem = kBwdSmem > kWgSmem ? kBwdSmem : kWgSmem;
+__global__ void __launch_bounds__(kBwdThreads, 1) tc_backward_kernel(const __grid_constant__ BwdParams bp, const __grid_constant__ WgParams wp) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // role of a cluster: chain pairs first, or spread evenly over the launch (the clusters of a launch are dealt round-robin
+    // to the GPCs, so spreading gives every GPC both kinds of traffic)
+    const int c = (int)blockIdx.x / 2, nc = wp.n_clusters;
+    const int before = wp.spread ? (int)((long long)c * bp.n_pairs / nc) : (c < bp.n_pairs ? c : bp.n_pairs);
+    const bool chain = wp.spread ? (int)((long long)(c + 1) * bp.n_pairs / nc) > before : c < bp.n_pairs;
+    if (chain) {
+        if (wp.debug & 16) return;                        // debug bit 4: weight-gradient jobs alone (timing experiments)
+        dgrad_role(bp, smem, before);
+    } else {
+        if (wp.debug & 8) return;                         // debug bit 3: chain alone
+        wgrad_role(wp, smem, 2 * (c - before) + ((int)blockIdx.x & 1));
+    }
 }
 
 static long long* g_wg_trace = nullptr;
@@ -767,27 +839,47 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
     SNERF_REQUIRE(ws_bytes >= w.total, "mlp_backward: workspace too small (%zu < %zu)", ws_bytes, w.total);
     uint8_t* wsb = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     const long long P = (long long)n_rays * n_samples;
-    const int grid = w.n_tiles < num_sms() ? w.n_tiles : num_sms();
+    const bool fused = bwd_fused();
+    // fused: the chain gets bwd_dgrad_pairs() CTA pairs (fewer for small inputs), the weight-gradient jobs the other SMs
+    const int n_super = (w.n_tiles + 1) / 2;
+    int n_pairs = fused ? bwd_dgrad_pairs() : num_sms() / 2;
+    if (n_pairs > (n_super + 1) / 2) n_pairs = (n_super + 1) / 2;
+    if (fused && 2 * n_pairs > num_sms() - 16) n_pairs = (num_sms() - 16) / 2;
+    const int wg_ctas = fused ? (num_sms() - 2 * n_pairs) / 2 * 2 : num_sms();
+
+    RingCtl ring{};
+    ring.base = wsb + w.dy;
+    ring.ready = (uint32_t*)(wsb + w.flags);
+    ring.consumed = ring.ready + (size_t)kDySlots * w.ring_cap;
+    ring.cap = w.ring_cap;
+    ring.use_flags = fused ? 1 : 0;
 
     // ---- (1) dgrad chain ----
     BwdParams bp{};
-    bp.packed = (const uint8_t*)packed; bp.act = wsb + w.act; bp.dy = wsb + w.dy; bp.bits = wsb + w.bits;
+    bp.packed = (const uint8_t*)packed; bp.act = wsb + w.act; bp.bits = wsb + w.bits;
     bp.sigma = sigma; bp.rgb = rgb; bp.d_sigma = d_sigma; bp.d_rgb = d_rgb;
     bp.w_rgb = m.has_view ? prm[SNERF_P_RGB_W] : nullptr;
     bp.n_points = P; bp.n_tiles = w.n_tiles; bp.n_steps = pl.n_bwd; bp.has_view = m.has_view ? 1 : 0;
+    bp.n_pairs = n_pairs;
     bp.tile_stash_bytes = pl.tile_stash_bytes;
     for (int s = 0; s < pl.n_bwd; ++s) bp.steps[s] = pl.bwd[s];
     static bool attr = false;
     if (!attr) {
         SNERF_CUDA_OK(cudaFuncSetAttribute(tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
         SNERF_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
         attr = true;
     }
-    SNERF_CUDA_OK(launch_clustered(tc_dgrad_kernel, pair_grid(w.n_tiles), kBwdThreads, kBwdSmem, st, bp));
 
     // ---- (2) wgrad ----
     WgParams wp{};
-    wp.act = wsb + w.act; wp.dy = wsb + w.dy;
+    wp.act = wsb + w.act;
+    wp.n_clusters = n_pairs + wg_ctas / 2;
+    {
+        static int spread = -1;
+        if (spread < 0) { const char* e = getenv("SNERF_BWD_SPREAD"); spread = e ? atoi(e) : 1; }
+        wp.spread = spread;
+    }
     wp.rays_o = rays_o; wp.rays_d = rays_d; wp.view_dirs = view_dirs; wp.z = z;
     wp.sigma = sigma; wp.rgb = rgb; wp.d_sigma = d_sigma; wp.d_rgb = d_rgb;
     wp.n_points = P; wp.n_samples = n_samples; wp.n_tiles = w.n_tiles; wp.pts_degree = d.pts_degree;
@@ -848,9 +940,16 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         wp.jobs[nj++] = h;
     }
     wp.n_jobs = nj;
-    // CTAs per job in proportion to the bytes the job streams per tile (the kernel is HBM-bound)
+    // ring consumers: a dY slot is read by one job, the skip layer's by two (hidden part and encoding part)
+    for (int j = 0; j < nj; ++j)
+        if (wp.jobs[j].kind == 0 && wp.jobs[j].a_panels) wp.jobs[j].ring_k = ring.n_consumers[wp.jobs[j].a_slot]++;
+    for (int sl = 0; sl < kDySlots; ++sl)
+        SNERF_REQUIRE(ring.n_consumers[sl] <= kRingConsumers, "mlp_backward: too many consumers of gradient slot %d", sl);
+    bp.ring = ring;
+    wp.ring = ring;
+    // CTAs per job in proportion to the measured cost of the job per tile
     {
-        const int G = num_sms();
+        const int G = wg_ctas;
         double cost[kMaxJobs], total = 0.0;
         for (int j = 0; j < nj; ++j) {
             const WgJob& jb = wp.jobs[j];
@@ -885,7 +984,23 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         int c0 = 0;
         for (int j = 0; j < nj; ++j) { wp.jobs[j].cta0 = (int16_t)c0; wp.jobs[j].n_cta = (int16_t)n[j]; c0 += n[j]; }
     }
-    (void)grid;
+    if (fused) {
+        if (wp.debug & 24) { bp.ring.use_flags = 0; wp.ring.use_flags = 0; }     // one role alone: no hand-off (results are garbage)
+        SNERF_CUDA_OK(cudaMemsetAsync(ring.ready, 0, (size_t)(1 + kRingConsumers) * kDySlots * ring.cap * sizeof(uint32_t), st));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * n_pairs + wg_ctas));
+        cfg.blockDim = dim3((unsigned)kBwdThreads);
+        cfg.dynamicSmemBytes = kFusedSmem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        SNERF_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_backward_kernel, bp, wp));
+        return SNERF_OK;
+    }
+    SNERF_CUDA_OK(launch_clustered(tc_dgrad_kernel, 2 * n_pairs, kBwdThreads, kBwdSmem, st, bp));
     if (g_split_event) cudaEventRecord(g_split_event, st);
     tc_wgrad_kernel<<<num_sms(), kWgThreads, kWgSmem, st>>>(wp);
     SNERF_LAUNCH_OK("tc_wgrad_kernel");

@@ -123,6 +123,34 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- flags in global memory: hand-offs between CTAs of one kernel (dgrad producers -> wgrad consumers) ----
+// The data moves through the async proxy (bulk copies), the flags through the generic proxy: the writer orders
+// "bulk store complete" -> fence.proxy.async -> st.release.gpu, the reader ld.acquire.gpu -> fence.proxy.async -> bulk load.
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ bool flag_reached(const uint32_t* p, uint32_t v) { return (int32_t)(ld_acquire_gpu(p) - v) >= 0; }
+// bounded wait until *p >= v (the flags only grow within a launch); a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void flag_wait_ge(const uint32_t* p, uint32_t v) {
+    if (flag_reached(p, v)) return;
+    const long long t0 = clock64();
+    int spins = 0;
+    while (!flag_reached(p, v)) {
+        if (++spins > 64) __nanosleep(64);
+        if (clock64() - t0 > 8000000000LL) {
+            printf("simplenerf_b200: flag wait timed out (block %d thread %d want %u have %u)\n", blockIdx.x, threadIdx.x, v,
+                   ld_acquire_gpu(p));
+            __trap();
+        }
+    }
+}
+
 // ---- thread-block clusters --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;

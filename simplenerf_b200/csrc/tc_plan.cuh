@@ -2,6 +2,8 @@
 // dgrad chain), the layout of the packed bf16 weight image, the activation / gradient stash and the workspace.
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace snerf {
@@ -188,9 +190,56 @@ constexpr uint32_t kBitsSlotBytes = 4096;                 // sign bits of one 12
 constexpr uint32_t kBitsTileBytes = 8 * kBitsSlotBytes;   // trunk layers 0..7
 
 struct TcWorkspace {
-    size_t view_bias, act, dy, bits, total;
+    size_t view_bias, act, dy, bits, flags, total;
     int n_tiles;
+    uint32_t ring_cap;
 };
+
+// ---- gradient ring (backward): dY panels travel from the dgrad CTA pairs to the wgrad CTAs of the SAME launch ----
+// One ring per dY stash slot (trunk layers 0..7, feature = 8, view layer = 9), `cap` entries each; tile t of a slot lives
+// in entry t % cap.  Slot 9 holds 2 panels (32 KB) per tile, the others 4 (64 KB).
+// SNERF_BWD_RING=0 (default): two launches, dgrad then wgrad, ring = all tiles (the gradients travel through HBM).
+// SNERF_BWD_RING=n > 0: ONE launch with both roles co-resident and an n-entry ring that stays in L2 -- correct and
+// tested, but measured slower (profiles/r2_fused_backward.md: the weight-gradient CTAs are bound by their own
+// load -> MMA -> release latency per 64-point stage, not by HBM, so halving their number costs more than the saved traffic).
+constexpr int kDySlots = 10;
+constexpr int kRingConsumers = 2;     // at most two wgrad jobs read one dY slot (skip layer: hidden part and encoding part)
+struct RingCtl {
+    uint8_t* base;
+    uint32_t* ready;       // [kDySlots][cap]: tile + 1 once the tile's panels of that slot are in the ring
+    uint32_t* consumed;    // [kRingConsumers][kDySlots][cap]: tile + 1 once that consumer has copied the entry out
+    uint32_t cap;
+    int use_flags;         // 0: two-kernel form, no hand-off inside the launch
+    uint8_t n_consumers[kDySlots];
+};
+__host__ __device__ __forceinline__ uint32_t ring_entry_bytes(int slot) { return slot == 9 ? 2u * kPanelBytes : 4u * kPanelBytes; }
+__host__ __device__ __forceinline__ size_t ring_slot_off(int slot, uint32_t cap) { return (size_t)slot * cap * (4u * kPanelBytes); }
+
+static inline int bwd_ring_tiles() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SNERF_BWD_RING");
+        v = e ? atoi(e) : 0;
+        if (v < 0) v = 0;
+        if (v > 0 && v < 8) v = 8;     // >= 4 entries are needed for progress; keep a margin
+    }
+    return v;
+}
+static inline bool bwd_fused() { return bwd_ring_tiles() != 0; }
+static inline uint32_t bwd_ring_cap(int n_tiles) {
+    const int r = bwd_ring_tiles();
+    return (uint32_t)((r == 0 || r >= n_tiles) ? (n_tiles > 0 ? n_tiles : 1) : r);
+}
+// dgrad CTA pairs of the fused launch (the remaining SMs run the wgrad jobs)
+static inline int bwd_dgrad_pairs() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SNERF_BWD_DGRAD_PAIRS");
+        v = e ? atoi(e) : 43;
+        if (v < 1) v = 1;
+    }
+    return v;
+}
 
 // Sign bits of post-ReLU bf16 activations (the ReLU masks of the backward pass).  A 16-column unit is 8 packed pairs;
 // pair p.lo / p.hi nonzero is bit 15 / 31 of (pair + 0x7FFF7FFF) -- the values are non-negative, so no carry crosses the
@@ -231,10 +280,13 @@ static inline TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n
     if (flags & SNERF_FLAG_SAVE_FOR_BWD) {
         w.act = off;
         off += (size_t)w.n_tiles * pl.tile_stash_bytes;
+        w.ring_cap = bwd_ring_cap(w.n_tiles);
         w.dy = off;
-        off += (size_t)w.n_tiles * pl.tile_stash_bytes;
+        off += (size_t)w.ring_cap * (m.has_view ? 9 * 65536 + 32768 : 8 * 65536);
         w.bits = off;
         off += (size_t)w.n_tiles * kBitsTileBytes;
+        w.flags = off;
+        off += align_up((size_t)(1 + kRingConsumers) * kDySlots * w.ring_cap * sizeof(uint32_t), 1024);
     }
     w.total = off + 1024;
     return w;

@@ -23,14 +23,24 @@ def shard_rays(batch: Dict, rank: int, world: int) -> Dict:
     return {k: (v[lo:hi] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == n else v) for k, v in batch.items()}
 
 
-def mask_count_weights(masks: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
+ALL_RAYS = '__all__'     # pseudo mask of mask_count_weights: every ray of the shard (mask-less mean losses)
+
+
+def mask_count_weights(masks: Dict[str, torch.Tensor], group=None, n_rays: int = None) -> Dict[str, torch.Tensor]:
     """the reference's losses are means over MASKED subsets of the whole batch (MSE01.py:53-59,
     SparseDepthMSE01.py:58-63), computed on the gathered outputs of all replicas.  With one process per GPU every rank takes
     the mean over its own masked rays; scaling the rank's loss of a mask by  n_rank * world / n_global  makes the AVERAGE
     of the ranks' gradients (what the gradient exchange computes) equal the gradient of the global masked mean.  One
-    all-reduce of len(masks) counts per step; every scale is 1 when there is one rank.  -> mask name -> 0-dim tensor."""
+    all-reduce of len(masks) counts per step; every scale is 1 when there is one rank.  -> mask name -> 0-dim tensor.
+    `n_rays` (the shard's ray count) adds the entry ALL_RAYS for losses that average over every ray: with unequal shards
+    their per-rank means need the same n_rank * world / n_global weight."""
     names = sorted(masks)
-    local = torch.stack([masks[k].sum().to(torch.float32) for k in names])
+    device = masks[names[0]].device if names else None
+    counts = [masks[k].sum().to(torch.float32) for k in names]
+    if n_rays is not None:
+        names = names + [ALL_RAYS]
+        counts.append(torch.tensor(float(n_rays), device=device))
+    local = torch.stack(counts)
     active = dist.is_initialized() and dist.get_world_size(group) > 1
     if not active:
         return {k: torch.ones((), device=local.device) for k in names}
@@ -115,6 +125,7 @@ class GradientExchange:
         self._seen: List[int] = []
         self._handles: list = []
         self._done: set = set()
+        self.armed = True        # False while a step's earlier sub-batches accumulate into the buckets (see `arm`)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
 
     def _active(self) -> bool:
@@ -129,7 +140,16 @@ class GradientExchange:
             self._handles.append(dist.all_reduce(buf, op=dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM, group=self.group,
                                                  async_op=True))
 
+    def arm(self, final: bool) -> None:
+        """Gradient accumulation (src/Trainer01.py:84-101 runs `sub_batch_size` slices and calls backward on each): the
+        buckets are complete only after the LAST backward of the step.  Call `arm(False)` before every earlier backward
+        and `arm(True)` before the last one; the hooks launch collectives only while armed, everything else is exchanged
+        by `finish`.  With one backward per step nothing has to be called (armed by default)."""
+        self.armed = bool(final)
+
     def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if not self.armed:
+            return
         b = self.bucket_of.get(id(p))
         if b is None:
             return
@@ -167,6 +187,7 @@ class GradientExchange:
                     self.bucket_size.append(len(ps))
         self._seen = [0] * len(self.bucket_size)
         self._handles, self._done = [], set()
+        self.armed = True
 
     def close(self) -> None:
         for h in self._hooks:

@@ -386,23 +386,25 @@ class FusedLossComputer:
         if self.ray_sharded:
             from ..distributed import mask_count_weights
             named = {k: input_dict[k] for k in ('indices_mask_nerf', 'indices_mask_sparse_depth') if input_dict.get(k) is not None}
-            scales = mask_count_weights(named, self.group)
+            from ..distributed import ALL_RAYS
+            scales = mask_count_weights(named, self.group, n_rays=input_dict['rays_o'].shape[0])
             by_ptr = {m.data_ptr(): scales[k] for k, m in named.items()}
+            all_rays = scales[ALL_RAYS]          # mask-less means (pair losses, VisibilityLoss01): weight of the shard's ray count
         for i in range(0, len(preds), _lib.LOSS_MAX_STREAMS):
             sl = slice(i, i + _lib.LOSS_MAX_STREAMS)
             values = ray_losses(preds[sl], targets[sl], masks[sl], weights[sl],
                                 [kinds.get(i + j, _lib.LOSS_SQUARED) for j in range(len(preds[sl]))])
             for j, name in enumerate(owner[sl]):        # a module with a coarse and a fine stream reports their sum (MSE01.py:35,42)
                 if name is None:                        # gradient-only mirror of a two-sided loss
-                    total = total + mirror_full[i + j] * (values[j] - values[j].detach())
+                    mw = mirror_full[i + j] if scales is None else mirror_full[i + j] * all_rays
+                    total = total + mw * (values[j] - values[j].detach())
                     continue
                 prev = loss_values.get(name, {}).get('loss_value')
                 loss_values[name] = {'loss_value': values[j] if prev is None else prev + values[j]}
             if scales is None:
                 total = total + values[-1]
             else:       # per-stream weight * count scale, applied on the device
-                one = torch.ones((), device=values.device)
-                w = torch.stack([(one if m is None else by_ptr[m.data_ptr()]) * wt for m, wt in zip(masks[sl], weights[sl])])
+                w = torch.stack([(all_rays if m is None else by_ptr[m.data_ptr()]) * wt for m, wt in zip(masks[sl], weights[sl])])
                 total = total + (values[:-1] * w).sum()
         if reproj:
             cd = input_dict['common_data']

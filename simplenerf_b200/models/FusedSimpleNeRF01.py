@@ -198,6 +198,11 @@ class _RenderStream(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *gouts):
+        with torch.cuda.device(ctx.saved_tensors[0].device):       # autograd's thread may sit on another device
+            return _RenderStream._backward(ctx, *gouts)
+
+    @staticmethod
+    def _backward(ctx, *gouts):
         z, sigma, rgb, rays_o, rays_d, pts_o, pts_d, view_dirs, *params = ctx.saved_tensors
         block, opts = ctx.block, ctx.opts
         grads_in = {k: g for k, g in zip(ctx.keys, gouts)}
@@ -289,6 +294,11 @@ class FusedSimpleNeRF(torch.nn.Module):
         rays_o = input_batch['rays_o']
         if not rays_o.is_cuda:
             raise RuntimeError('FusedSimpleNeRF runs on CUDA only: move the batch to the GPU (no CPU fallback exists)')
+        with torch.cuda.device(rays_o.device):      # kernels go to the current device's stream: make it the batch's ('device': [k] configs)
+            return self._forward(input_batch, retraw, sec_views_vis)
+
+    def _forward(self, input_batch: dict, retraw: bool, sec_views_vis: bool):
+        rays_o = input_batch['rays_o']
         n = rays_o.shape[0]
         if self.predict_visibility and sec_views_vis:                            # :119-133
             input_batch = dict(input_batch)

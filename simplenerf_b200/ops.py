@@ -22,6 +22,11 @@ def _ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
         raise RuntimeError('simplenerf_b200 kernels need CUDA tensors (no CPU fallback exists)')
     if t.dtype != dtype or not t.is_contiguous():
         raise RuntimeError(f'expected a contiguous {dtype} tensor, got {t.dtype}, contiguous={t.is_contiguous()}')
+    if t.device.index != torch.cuda.current_device():
+        # the launch goes to the CURRENT device's stream (_stream): a tensor of another device would hand the kernel a
+        # foreign pointer.  The drop-in's forward / backward select the batch's device; direct callers must do the same.
+        raise RuntimeError(f'tensor lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}: '
+                           'wrap the call in `with torch.cuda.device(tensor.device):`')
     return t.data_ptr()
 
 

@@ -57,14 +57,60 @@ class FusedAdam:
                                            float(group['eps']), self.step_count, stream), 'snerf_adam_step')
             ops.LAUNCHES['count'] += 1
 
+    # ---- checkpoints: the torch.optim.Adam layout, so that src/Trainer01.py:352-381 can save with either optimizer and
+    # resume with the other ({'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [{..., 'params': [i, ...]}]}) ----
     def state_dict(self) -> dict:
-        return {'step': self.step_count, 'exp_avg': [t.clone() for t in self.exp_avg], 'exp_avg_sq': [t.clone() for t in self.exp_avg_sq],
-                'param_groups': [{k: v for k, v in self.param_groups[0].items() if k != 'params'}]}
+        return to_torch_adam_state(self.step_count, self.exp_avg, self.exp_avg_sq, self.param_groups[0])
 
     def load_state_dict(self, state: dict) -> None:
-        self.step_count = int(state['step'])
-        for dst, src in zip(self.exp_avg, state['exp_avg']):
-            dst.copy_(src)
-        for dst, src in zip(self.exp_avg_sq, state['exp_avg_sq']):
-            dst.copy_(src)
-        self.param_groups[0].update(state['param_groups'][0])
+        step, exp_avg, exp_avg_sq, group = from_adam_state(state, len(self.params))
+        self.step_count = step
+        for dst, src in zip(self.exp_avg, exp_avg):
+            dst.zero_() if src is None else dst.copy_(src)
+        for dst, src in zip(self.exp_avg_sq, exp_avg_sq):
+            dst.zero_() if src is None else dst.copy_(src)
+        self.param_groups[0].update({k: v for k, v in group.items() if k in ('lr', 'betas', 'eps')})
+        self.param_groups[0]['betas'] = tuple(self.param_groups[0]['betas'])
+
+
+def _torch_adam_group_defaults() -> dict:
+    """The param_group keys of torch.optim.Adam in the running torch version (its load_state_dict REPLACES the group dict,
+    so every key its step() reads has to be present)."""
+    g = dict(torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))]).state_dict()['param_groups'][0])
+    g.pop('params', None)
+    return g
+
+
+def to_torch_adam_state(step_count: int, exp_avg, exp_avg_sq, group: dict) -> dict:
+    """State of `FusedAdam` in the layout of torch.optim.Adam.state_dict() (one param group, no weight decay, no amsgrad:
+    src/Trainer01.py:516).  torch keeps no state for parameters that were never stepped; neither does this."""
+    pg = _torch_adam_group_defaults()
+    pg.update(lr=float(group['lr']), betas=tuple(group['betas']), eps=float(group['eps']))
+    pg['params'] = list(range(len(exp_avg)))
+    state = {}
+    if step_count > 0:
+        for i, (m, v) in enumerate(zip(exp_avg, exp_avg_sq)):
+            state[i] = {'step': torch.tensor(float(step_count)), 'exp_avg': m.detach().clone(), 'exp_avg_sq': v.detach().clone()}
+    return {'state': state, 'param_groups': [pg]}
+
+
+def from_adam_state(state: dict, n_params: int):
+    """-> (step, exp_avg list, exp_avg_sq list, group dict) from a torch.optim.Adam state_dict or from the flat layout this
+    class wrote in round 1 ({'step', 'exp_avg': [...], 'exp_avg_sq': [...], 'param_groups'}).  Entries are None for
+    parameters without state."""
+    group = dict(state['param_groups'][0])
+    if 'state' not in state:                                   # round-1 layout
+        return int(state['step']), list(state['exp_avg']), list(state['exp_avg_sq']), group
+    ids = group.get('params', list(range(n_params)))
+    if len(state['param_groups']) != 1 or len(ids) != n_params:
+        raise ValueError(f"optimizer state has {len(state['param_groups'])} group(s) / {len(ids)} parameters, expected 1 / {n_params}")
+    exp_avg, exp_avg_sq, steps = [], [], []
+    for pid in ids:
+        st = state['state'].get(pid)
+        exp_avg.append(None if st is None else st['exp_avg'])
+        exp_avg_sq.append(None if st is None else st['exp_avg_sq'])
+        if st is not None:
+            steps.append(int(float(st['step'])))
+    if steps and min(steps) != max(steps):
+        raise ValueError('FusedAdam keeps one step count: the per-parameter steps of this checkpoint differ')
+    return (steps[0] if steps else 0), exp_avg, exp_avg_sq, group

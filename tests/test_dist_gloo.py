@@ -207,3 +207,72 @@ def test_count_weighted_masked_means_equal_the_global_mean():
     want.backward()
     torch.testing.assert_close(ret['loss'], want.detach(), rtol=1e-6, atol=0)
     torch.testing.assert_close(ret['grad'], p.grad, rtol=1e-5, atol=1e-9)
+
+
+# ---- gradient accumulation over sub-batches (Trainer01.py:84-101) under the overlapped exchange ----
+def _accumulate_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    blocks = [[torch.nn.Parameter(torch.ones(s)) for s in ((4, 3), (5,))], [torch.nn.Parameter(torch.ones(s)) for s in ((2, 2), (1,), (6,))]]
+    params = [p for blk in blocks for p in blk]
+    ex = GradientExchange(params, weight=0.5)
+    got = []
+    n_sub = 3
+    for step in range(3):
+        for p in params:
+            p.grad = None
+        hooked_early = 0
+        for k in range(n_sub):                 # every sub-batch accumulates into the same flat buckets
+            ex.arm(k == n_sub - 1)
+            x = torch.tensor(float(rank + 1 + step + 10 * k))
+            (_BucketFn.apply(x, *blocks[0]) + _BucketFn.apply(x, *blocks[1])).backward()
+            if k < n_sub - 1:
+                hooked_early += len(ex._handles)
+        hooked = len(ex._handles)
+        ex.finish()
+        got.append((hooked_early, hooked, [p.grad.clone() for p in params]))
+    ex.close()
+    if rank == 0:
+        ret['accumulate'] = got
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_with_sub_batches_equals_single_process():
+    """The buckets may be exchanged only in the LAST backward of a step: earlier sub-batches accumulate into them."""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_accumulate_worker, args=(2, port, ret), nprocs=2, join=True)
+    for step, (hooked_early, hooked, grads) in enumerate(ret['accumulate']):
+        assert hooked_early == 0                              # nothing is launched before the last sub-batch
+        assert hooked == (0 if step == 0 else 2)
+        want = 0.5 * sum((1 + step + 10 * k) + (2 + step + 10 * k) for k in range(3))
+        for g in grads:
+            torch.testing.assert_close(g, torch.full_like(g, want))
+
+
+def test_train_step_pieces_are_the_references_sub_batches_split_over_the_ranks():
+    """every rank runs the same number of backward passes, also when shards are unequal."""
+    from simplenerf_b200.trainer import RayShardedTrainStep
+    for n, sub, world in ((4098, 1024, 2), (4099, 1024, 2), (4096, 2048, 8), (11, 4, 3), (4096, 4096, 1)):
+        per_rank = []
+        for rank in range(world):
+            step = RayShardedTrainStep.__new__(RayShardedTrainStep)
+            step.rank, step.world = rank, world
+            per_rank.append(step._pieces(n, sub, shard=True))
+        assert len({len(p) for p in per_rank}) == 1                      # same count everywhere
+        covered = sorted(span for p in per_rank for span in p)
+        assert covered[0][0] == 0 and covered[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))   # a partition of the batch
+        for k in range(len(per_rank[0])):                                # piece k of every rank lies in the reference's sub-batch k
+            assert all(k * sub <= p[k][0] < p[k][1] <= min(n, (k + 1) * sub) for p in per_rank)
+    lone = RayShardedTrainStep.__new__(RayShardedTrainStep)          # a sub-batch with fewer rays than ranks cannot be split: loud, not a hang
+    lone.rank, lone.world = 1, 2
+    try:
+        lone._pieces(4097, 1024, shard=True)
+    except ValueError as exc:
+        assert 'cannot be split' in str(exc)
+    else:
+        raise AssertionError('expected a ValueError')

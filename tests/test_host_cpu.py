@@ -178,3 +178,41 @@ def test_argument_validation_of_the_next_row_entry_points(lib):
     assert lib.snerf_visibility_workspace_bytes(ctypes.byref(noview), 16, 64, 2) == 0           # no view branch, no head
     assert lib.snerf_visibility2_composite_forward(None, None, None, None, 4, 64, 9, None) == 1  # more than 8 other views
     assert lib.snerf_visibility2_composite_forward(None, None, None, None, 0, 64, 2, None) == 0
+
+
+def test_fused_adam_state_has_the_torch_adam_layout_both_ways():
+    """Trainer01.py:352-381 saves optimizer.state_dict() and resumes with load_state_dict(); a checkpoint
+    written with torch.optim.Adam must load into FusedAdam and the other way round."""
+    from simplenerf_b200.optim import from_adam_state, to_torch_adam_state
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(s)) for s in ((4, 3), (5,), (2, 2))]
+    ref = torch.optim.Adam(params, lr=5e-4, betas=(0.9, 0.999))
+    for _ in range(3):
+        for p in params:
+            p.grad = torch.randn_like(p)
+        ref.step()
+    sd = ref.state_dict()
+    step, m, v, group = from_adam_state(sd, len(params))                        # torch -> ours
+    assert step == 3 and group['lr'] == 5e-4
+    for i, p in enumerate(params):
+        torch.testing.assert_close(m[i], ref.state[p]['exp_avg'])
+        torch.testing.assert_close(v[i], ref.state[p]['exp_avg_sq'])
+    ours = to_torch_adam_state(step, m, v, {'lr': 1e-4, 'betas': (0.9, 0.999), 'eps': 1e-8})   # ours -> torch
+    assert set(ours['param_groups'][0]) == set(sd['param_groups'][0])
+    fresh = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    other = torch.optim.Adam(fresh, lr=5e-4)
+    other.load_state_dict(ours)
+    assert other.param_groups[0]['lr'] == 1e-4
+    for p, q in zip(params, fresh):                                              # and the next update is the same update
+        p.grad = torch.ones_like(p)
+        q.grad = torch.ones_like(q)
+    ref.param_groups[0]['lr'] = 1e-4
+    ref.step()
+    other.step()
+    for p, q in zip(params, fresh):
+        torch.testing.assert_close(p, q)
+    # the flat layout round 1 wrote still loads
+    step2, m2, _, _ = from_adam_state({'step': 7, 'exp_avg': m, 'exp_avg_sq': v, 'param_groups': [{'lr': 1.0}]}, len(params))
+    assert step2 == 7 and m2[0] is m[0]
+    # never-stepped optimizer: torch keeps no state
+    assert to_torch_adam_state(0, m, v, {'lr': 1e-4, 'betas': (0.9, 0.999), 'eps': 1e-8})['state'] == {}
