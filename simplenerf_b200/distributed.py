@@ -17,6 +17,11 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     return min(n, rank * per), min(n, (rank + 1) * per)
 
 
+def balanced_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of n units for `rank`, sizes differing by at most one (no rank is empty while n >= world)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
 def shard_rays(batch: Dict, rank: int, world: int) -> Dict:
     n = batch['rays_o'].shape[0]
     lo, hi = shard_bounds(n, rank, world)

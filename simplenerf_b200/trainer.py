@@ -16,7 +16,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
-from .distributed import GradientExchange, shard_bounds
+from .distributed import GradientExchange, balanced_bounds
 
 
 class RayShardedTrainStep:
@@ -39,7 +39,7 @@ class RayShardedTrainStep:
         if shard:
             pieces = []
             for start in range(0, n, sub):
-                lo, hi = shard_bounds(min(n, start + sub) - start, self.rank, self.world)
+                lo, hi = balanced_bounds(min(n, start + sub) - start, self.rank, self.world)
                 if hi <= lo:
                     raise ValueError(f'sub-batch of {min(n, start + sub) - start} rays cannot be split over {self.world} ranks')
                 pieces.append((start + lo, start + hi))
