@@ -269,7 +269,7 @@ def test_train_step_pieces_are_the_references_sub_batches_split_over_the_ranks()
         for k in range(len(per_rank[0])):                                # piece k of every rank lies in the reference's sub-batch k
             assert all(k * sub <= p[k][0] < p[k][1] <= min(n, (k + 1) * sub) for p in per_rank)
     lone = RayShardedTrainStep.__new__(RayShardedTrainStep)          # a sub-batch with fewer rays than ranks cannot be split: loud, not a hang
-    lone.rank, lone.world = 1, 2
+    lone.rank, lone.world = 0, 2
     try:
         lone._pieces(4097, 1024, shard=True)
     except ValueError as exc:
