@@ -13,8 +13,13 @@ all-reduced over NCCL every step.  Metric: train rays/s over all GPUs.
 Our arm   : the drop-in model (simplenerf_b200.models.FusedSimpleNeRF01, bf16 tcgen05 path) -- `value` with
             the batch resident in HBM, `e2e` with the batch in pinned host memory copied every step and the
             loss read back.
-Reference : `--impl reference` times the reference algorithm's CPU restatement (oracle/, "port": the
-            reference is pure Python/torch and /root/reference does not exist on the GPU box) on the host cores.
+Reference : `--impl reference` times the UNMODIFIED reference -- its own Trainer01.train_one_iter on the same C2
+            step (DataPreprocessor01 batch, SimpleNeRF01, LossComputer01 with the nine shipped losses, Adam) -- on the host
+            cores, from the copy `__graft_entry__.build()` stages under baseline/_ref (kind "reference"); when that copy is
+            absent it falls back to the CPU restatement in oracle/ (kind "port").
+Beside the headline the line carries: `roofline` (MLP kernels against the bf16 tensor peak, per-kernel HBM fractions),
+`cpu_baseline`, `render` (ms per 1008x756 frame), `c5` (compositing / resampling sweep against the HBM roof),
+`trainer` (the drop-in behind the reference's own Trainer01 on this GPU, and the reference model itself on this GPU).
 """
 from __future__ import annotations
 
@@ -29,10 +34,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RAYS_PER_GPU = 4096
-# DRAM bytes of the three MLP kernels per 4096-ray step (dram__bytes_read.sum + dram__bytes_write.sum, summed over the 12
-# launches of one step): profiles/r1_final3_ncu_full_summary.md.  Algorithmic figure: forward
-# 5.0 + dgrad 5.25 + wgrad 10.8 KB/point x 1 572 864 points = 33.1 GB.
-MLP_DRAM_BYTES_PER_STEP = 31.39e9
+
+
+def measured_traffic():
+    """DRAM bytes of the three MLP kernels per 4096-ray step (dram__bytes_read.sum + dram__bytes_write.sum over the 12 launches
+    of one step, ncu --set full): kept in profiles/mlp_dram_traffic.json next to the capture it was read from, so that the
+    number changes when the profile does.  Algorithmic figure: 33.1 GB."""
+    path = os.path.join(ROOT, 'profiles', 'mlp_dram_traffic.json')
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d['bytes_per_step']), f"{d['source']} ({d['how']})"
+    except (OSError, KeyError, ValueError):
+        return None, 'profiles/mlp_dram_traffic.json missing'
 # algorithmic GB per step and kernel: main / fine / pts-aug MLPs keep 9.5 panels x 512 B per point (4.75 KB) + 0.25 KB of
 # sign bits, views-aug 8 panels (4 KB); 4096 rays x (64 + 64 + 192) points with view layers + 4096 x 64 without.
 _P_VIEW, _P_NOVIEW = 4096 * (64 + 64 + 192), 4096 * 64
@@ -52,7 +66,7 @@ def peaks():
         with open(path) as f:
             d = json.load(f)
         return dict(tflops=d.get('bf16_tflops_sustained', d['bf16_tflops']), tflops_burst=d['bf16_tflops'],
-                    hbm=d['hbm_gbs'], source='measured (MEASURED_PEAKS.json, sustained bf16)')
+                    hbm=d['hbm_gbs'], source='measured (MEASURED_PEAKS.json: burst bf16 = best of 10 matmuls, sustained = 4 s back to back)')
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
 
 
@@ -159,30 +173,100 @@ def cpu_training_pass(n_rays: int, sub_batch: int, threads: int):
     return run
 
 
+def reference_step_runner(threads: int):
+    """-> (run, kind, sample): run() performs ONE full C2 training step of the reference on the host cores and returns seconds.
+    Unmodified reference when staged (baseline/_ref), else the oracle port."""
+    import torch
+    from baseline import ref_harness as rh
+    torch.set_num_threads(threads)
+    if rh.available():
+        trainer, _ = rh.build_trainer('SimpleNeRF01', device=[0], resolution=(756, 1008), num_rays=2048, sparse_rays=2048,
+                                      sub_batch_size=2048)
+        if next(trainer.model.parameters()).is_cuda:
+            raise RuntimeError('the CPU arm must run with the GPUs hidden (CUDA_VISIBLE_DEVICES="")')
+        it = [20000]
+
+        def run():
+            t0 = time.perf_counter()
+            trainer.train_one_iter(it[0])
+            it[0] += 1
+            return time.perf_counter() - t0
+        return run, 'reference', ('one full C2 step per step: the unmodified Trainer01.train_one_iter (src/Trainer01.py:61-107) on a synthetic '
+                                  '3-view 756x1008 scene -- 2048 image + 2048 sparse-depth rays as 2 sub-batches of 2048, SimpleNeRF01 (4 MLPs), '
+                                  'LossComputer01 with the 9 shipped losses, Adam -- from baseline/_ref, fp32, all host threads')
+    run = cpu_training_pass(4096, 2048, threads)
+    return run, 'port', ('one full 4096-ray step per step as 2 sub-batches of 2048 (fwd+bwd, 4 MLPs): oracle/nerf_oracle.py on the host '
+                         '(baseline/_ref not staged)')
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    os.environ['CUDA_VISIBLE_DEVICES'] = ''          # the reference picks the GPU by itself when it sees one (CommonUtils01.py:15-27)
     import torch
     threads = os.cpu_count() or 1
-    sample = 512
-    run = cpu_training_pass(sample, sample, threads)
+    run, kind, sample = reference_step_runner(threads)
     for _ in range(args.warmup):
         run()
     times = [run() for _ in range(args.steps)]
     total = sum(times)
-    value = sample * args.steps / total
+    value = RAYS_PER_GPU * args.steps / total
     line = {
         'impl': 'reference', 'metric': 'train rays/s (64+128 samples, fwd+bwd)', 'value': value, 'unit': 'rays/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args.gpus),
-        'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                         'sample': f'{sample} rays of the same workload per step (fwd+bwd, 4 MLPs), oracle/nerf_oracle.py on the host'},
+        'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(quick: bool):
+    """The reference arm on the host cores, in a child process with the GPUs hidden: 1 warm-up + 2 timed full steps (~15-25 s)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1' if quick else '2', '--warmup', '0' if quick else '1']
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE')}
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    for ln in reversed(res.stdout.strip().splitlines()):
+        if ln.startswith('{'):
+            return json.loads(ln)['cpu_baseline']
+    return {'value': None, 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'failed', 'sample': (res.stderr or res.stdout)[-300:]}
+
+
+def trainer_context(steps: int, warmup: int):
+    """N=1 context numbers through the reference's own Trainer01.train_one_iter on THIS GPU (full C2 step incl. the reference's
+    batch assembly and its per-loss .item() synchronisations): (a) the unmodified reference model -- what a user of the
+    reference runs today; (b) the same with ONE string changed (model name -> FusedSimpleNeRF01); (c) also FusedLossComputer +
+    FusedAdam.  None when the reference copy is not staged."""
+    import torch
+    from baseline import ref_harness as rh
+    if not rh.available():
+        return None
+    from simplenerf_b200.loss_functions.FusedLossComputer01 import FusedLossComputer
+    from simplenerf_b200.optim import FusedAdam
+    scene = dict(device=[torch.cuda.current_device()], resolution=(756, 1008), num_rays=2048, sparse_rays=2048, sub_batch_size=2048)
+    out = {'note': 'rays/s of Trainer01.train_one_iter on one B200, wall clock with a device synchronize on both sides; 4096 rays per step'}
+    variants = (('reference_gpu', 'SimpleNeRF01', {}, {}),
+                ('dropin_one_string', 'FusedSimpleNeRF01', {'precision': 'bf16'}, {}),
+                ('dropin_fused_losses_adam', 'FusedSimpleNeRF01', {'precision': 'bf16'},
+                 dict(loss_computer_factory=FusedLossComputer, optimizer_factory=lambda ps: FusedAdam(ps, lr=5e-4, betas=(0.9, 0.999)))))
+    for key, name, extra, factories in variants:
+        trainer, _ = rh.build_trainer(name, model_extra=extra or None, **scene, **factories)
+        for i in range(warmup):
+            trainer.train_one_iter(20000 + i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            trainer.train_one_iter(20100 + i)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        out[key] = {'value': RAYS_PER_GPU / dt, 'unit': 'rays/s', 'ms_per_step': 1e3 * dt, 'steps': steps}
+        del trainer
+        torch.cuda.empty_cache()
+    return out
 
 
 def workload_config(n_gpus: int):
@@ -262,9 +346,7 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    # warm-up: the W requested steps, and at least 25 in total -- a fresh box needs a few hundred ms of load before clocks,
-    # allocator pools and the NCCL channels settle (the first timed steps of a cold process measured 3-5 % slow)
-    n_warm = max(args.warmup, 25)
+    n_warm = args.warmup        # exactly the W untimed steps the caller asked for
     for _ in range(n_warm):
         step(resident)
 
@@ -344,7 +426,7 @@ def run_ours(args):
         frame = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in frame.items()}
         with torch.no_grad():
             vmodel(frame)
-            ms_frame = timed(lambda: vmodel(frame), 2) / 2
+            ms_frame = timed(lambda: vmodel(frame), args.frames) / args.frames
         # the same frame through the one-call renderer: pose on the host -> device ray generation -> render ->
         # device post-processing -> uint8 image and depth maps in pinned host memory, all inside the timed region
         from simplenerf_b200.render import FrameRenderer
@@ -354,28 +436,35 @@ def run_ours(args):
         import numpy as np
         pose = np.eye(4, dtype=np.float32)
         fr.render(pose)
-        ms_frame_e2e = timed(lambda: fr.render(pose), 2) / 2
+        ms_frame_e2e = timed(lambda: fr.render(pose), args.frames) / args.frames
         d2h = (r1 - r0) * w * (3 + 4 * 4)
-        render = {'ms_per_frame': ms_frame, 'rays_per_s': h * w / (ms_frame * 1e-3), 'resolution': [h, w],
-                  'tensor_frac_of_peak': h * w * RENDER_FLOP_PER_RAY / (ms_frame * 1e-3) / (peaks()['tflops'] * 1e12 * world),
+        render = {'ms_per_frame': ms_frame, 'rays_per_s': h * w / (ms_frame * 1e-3), 'resolution': [h, w], 'frames_timed': args.frames,
+                  'tensor_frac_of_burst_peak': h * w * RENDER_FLOP_PER_RAY / (ms_frame * 1e-3) / (peaks()['tflops_burst'] * 1e12 * world),
+                  'tensor_frac_of_sustained_peak': h * w * RENDER_FLOP_PER_RAY / (ms_frame * 1e-3) / (peaks()['tflops'] * 1e12 * world),
                   'sharding': f'{world} row bands, no collective',
                   'e2e': {'ms_per_frame': ms_frame_e2e, 'h2d_bytes_per_frame': 48 + 36, 'd2h_bytes_per_frame': d2h,
                           'note': 'FrameRenderer.render(pose): rays generated on the device, uint8 image + 4 depth maps copied to pinned host memory'}}
 
-    # ---- cpu baseline (rank 0, N=1 only): the oracle on the host cores, one full C2 step ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        run = cpu_training_pass(4096 if not args.quick_cpu else 256, 2048, threads)
-        t = run()
-        cpu = {'value': (4096 if not args.quick_cpu else 256) / t, 'unit': 'rays/s', 'cores': threads, 'kind': 'port',
-               'sample': 'one full 4096-ray step as 2 sub-batches of 2048 (Trainer01 sub_batch_size), fwd+bwd, no warm-up' if not args.quick_cpu
-               else '256 rays fwd+bwd'}
+    # ---- N=1 extras (rank 0): C5 sweep, the drop-in behind the reference's Trainer01, the reference's CPU path ----
+    c5 = trainer_ctx = cpu = None
+    if rank == 0 and world == 1:
+        if not args.no_c5:
+            from tools import scan_microbench
+            rows = scan_microbench.run(iters=5)
+            c5 = {'unit': 'GB/s', 'peak': peaks()['hbm'], 'target_frac': 0.70,
+                  'bytes': 'algorithmic bytes per ray (SURVEY.md 8d): composite fwd 20S+68 (24S+68 with weights), bwd 36S+48, sample_pdf+merge 1792 (1280 with the linspace row), stratified 8S',
+                  'rows': [{'kernel': r['kernel'], 'S': r['S'], 'log2_rays': r['rays'].bit_length() - 1, 'us': round(r['seconds'] * 1e6, 1),
+                            'gbs': round(r['gbs']), 'frac': round(r['frac'], 3)} for r in rows]}
+        if not args.no_trainer:
+            trainer_ctx = trainer_context(steps=5, warmup=2)
+        if not args.no_cpu:
+            cpu = cpu_baseline_subprocess(args.quick_cpu)
 
     if rank == 0:
         pk = peaks()
         mlp_total = mlp_ms['mlp_forward'] + mlp_ms['mlp_backward']
         achieved = n * TRAIN_FLOP_PER_RAY / (mlp_total * 1e-3) / 1e12
+        traffic, traffic_note = measured_traffic()
         line = {
             'metric': 'train rays/s (64+128 samples, fwd+bwd)', 'value': value, 'unit': 'rays/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': n_warm, 'ms_per_step': ms_step, 'higher_is_better': True,
@@ -388,12 +477,15 @@ def run_ours(args):
             'host_enqueue_ms_per_step': host_enqueue_ms,
             'clocks': clocks.summary(),
             'roofline': {'bound': 'tensor', 'kernel': 'tc_forward_kernel + tc_dgrad_kernel + tc_wgrad_kernel (all 4 MLPs)',
-                         'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
-                         'traffic': MLP_DRAM_BYTES_PER_STEP, 'peak_source': pk['source'],
-                         'traffic_note': 'DRAM bytes per step of the same three kernels (12 launches), ncu --set full, profiles/r1_final3_ncu_full_summary.md',
-                         # the training step moves 31.5 GB through HBM for 5.3 TFLOP: it sits between the two roofs
-                         'hbm': {'achieved': MLP_DRAM_BYTES_PER_STEP / (mlp_total * 1e-3) / 1e9, 'peak': pk['hbm'], 'unit': 'GB/s',
-                                 'frac': MLP_DRAM_BYTES_PER_STEP / (mlp_total * 1e-3) / 1e9 / pk['hbm']},
+                         # `peak` is the BURST figure (the timed region is short and runs above the clock the sustained figure was
+                         # measured at); the fraction of the sustained figure is given beside it
+                         'achieved': achieved, 'peak': pk['tflops_burst'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops_burst'],
+                         'frac_of_sustained_peak': achieved / pk['tflops'], 'sustained_peak': pk['tflops'],
+                         'traffic': traffic, 'peak_source': pk['source'],
+                         'traffic_note': 'DRAM bytes per step of the same three kernels (12 launches): ' + traffic_note,
+                         # the training step moves ~31 GB through HBM for 5.3 TFLOP: it sits between the two roofs
+                         'hbm': None if traffic is None else {'achieved': traffic / (mlp_total * 1e-3) / 1e9, 'peak': pk['hbm'], 'unit': 'GB/s',
+                                                              'frac': traffic / (mlp_total * 1e-3) / 1e9 / pk['hbm']},
                          # per kernel, against the roof that bounds it in training: ALGORITHMIC bytes (DESIGN.md section 4:
                          # KB per point x 1 572 864 points of a step; views-aug has no view layer) / live CUDA-event time
                          'kernels': {k: {'bound': 'hbm', 'ms_per_step': mlp_ms[t], 'algorithmic_gb': gb,
@@ -404,11 +496,13 @@ def run_ours(args):
                                                       ('tc_wgrad_kernel', 'wgrad', ALG_GB['wgrad'])) if mlp_ms.get(t)},
                          'ms_per_step': {'mlp_forward': mlp_ms['mlp_forward'], 'mlp_backward': mlp_ms['mlp_backward'],
                                          'other': ms_step - mlp_total},
-                         'frac_forward': n * 2 * 220_348_416 / (mlp_ms['mlp_forward'] * 1e-3) / 1e12 / pk['tflops'],
-                         'frac_backward': n * 2 * 428_236_800 / (mlp_ms['mlp_backward'] * 1e-3) / 1e12 / pk['tflops'],
-                         'step_frac_of_peak': n * TRAIN_FLOP_PER_RAY / (ms_step * 1e-3) / 1e12 / pk['tflops']},
+                         'frac_forward': n * 2 * 220_348_416 / (mlp_ms['mlp_forward'] * 1e-3) / 1e12 / pk['tflops_burst'],
+                         'frac_backward': n * 2 * 428_236_800 / (mlp_ms['mlp_backward'] * 1e-3) / 1e12 / pk['tflops_burst'],
+                         'step_frac_of_peak': n * TRAIN_FLOP_PER_RAY / (ms_step * 1e-3) / 1e12 / pk['tflops_burst']},
             'cpu_baseline': cpu,
             'render': render,
+            'c5': c5,
+            'trainer': trainer_ctx,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -422,6 +516,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-render', action='store_true')
+    ap.add_argument('--frames', type=int, default=10, help='frames timed for the render metric')
+    ap.add_argument('--no-c5', action='store_true', help='skip the compositing / resampling sweep (N=1 only)')
+    ap.add_argument('--no-trainer', action='store_true', help='skip the runs behind the reference Trainer01 (N=1 only)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--quick-cpu', action='store_true')
     ap.add_argument('--torch-loss', action='store_true', help='eager torch loss (8 masked means, ~80 launches) instead of snerf_ray_losses_*')

@@ -18,13 +18,30 @@ _MAX = 64
 class FusedAdam:
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        for p in self.params:
-            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
-                raise ValueError('FusedAdam needs contiguous fp32 CUDA parameters (there is no CPU fallback)')
         self.param_groups = [{'params': self.params, 'lr': lr, 'betas': tuple(betas), 'eps': eps}]
-        self.exp_avg = [torch.zeros_like(p) for p in self.params]
-        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        # Like torch.optim.Adam the state is created lazily: the reference builds its optimizer BEFORE the model moves to the
+        # device (src/Trainer01.py:516 then :58), so at construction time the parameters may still live on the CPU.
+        self._exp_avg: List[torch.Tensor] = []
+        self._exp_avg_sq: List[torch.Tensor] = []
         self.step_count = 0
+
+    def _state(self):
+        if not self._exp_avg or any(m.device != p.device for m, p in zip(self._exp_avg, self.params)):
+            for p in self.params:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise ValueError('FusedAdam needs contiguous fp32 CUDA parameters (there is no CPU fallback)')
+            old_m, old_v = self._exp_avg, self._exp_avg_sq
+            self._exp_avg = [torch.zeros_like(p) if not old_m else old_m[i].to(p.device) for i, p in enumerate(self.params)]
+            self._exp_avg_sq = [torch.zeros_like(p) if not old_v else old_v[i].to(p.device) for i, p in enumerate(self.params)]
+        return self._exp_avg, self._exp_avg_sq
+
+    @property
+    def exp_avg(self) -> List[torch.Tensor]:
+        return self._state()[0]
+
+    @property
+    def exp_avg_sq(self) -> List[torch.Tensor]:
+        return self._state()[1]
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self.params:
@@ -60,6 +77,8 @@ class FusedAdam:
     # ---- checkpoints: the torch.optim.Adam layout, so that src/Trainer01.py:352-381 can save with either optimizer and
     # resume with the other ({'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [{..., 'params': [i, ...]}]}) ----
     def state_dict(self) -> dict:
+        if self.step_count == 0 and not self._exp_avg:        # never stepped: no state yet (the parameters may still be on the CPU)
+            return to_torch_adam_state(0, self.params, self.params, self.param_groups[0])
         return to_torch_adam_state(self.step_count, self.exp_avg, self.exp_avg_sq, self.param_groups[0])
 
     def load_state_dict(self, state: dict) -> None:
