@@ -273,6 +273,11 @@ typedef struct snerf_gather_table {
 } snerf_gather_table;
 int snerf_gather_rows(const snerf_gather_table* tables, int n_tables, const int64_t* indices, int n_rows, void* stream);
 
+/* Measurement hook of snerf_mlp_backward on the tensor path (two-launch form): `event` is a cudaEvent_t that the next calls
+ * record on their launch stream BETWEEN the dgrad chain kernel and the wgrad kernel, so that a caller timing the call with
+ * its own events can split the two (bench.py's per-kernel roofline lines).  NULL (the default) disables it.  Process-global.  */
+void snerf_set_backward_split_event(void* event);
+
 /* Self-test of the tcgen05 GEMM building blocks against a CUDA-core GEMM (used by tests).
  * Returns SNERF_OK and writes the max abs error of each mode to host_max_err[4].               */
 int snerf_tensor_selftest(float* host_max_err, void* stream);

@@ -7,6 +7,9 @@ import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, 'libsimplenerf_b200.so')
+# the same sources + the probe kernels and the snerfdbg_* entry points (compiled with -DSNERF_DEBUG by `build.py --debug`); the
+# developer tools under tools/ select it with SNERF_B200_DEBUG_LIB=1, the product never loads it
+LIB_DBG_PATH = os.path.join(PKG, 'libsimplenerf_b200_dbg.so')
 
 P_COUNT = 24
 P_HEAD_W, P_HEAD_B, P_FEAT_W, P_FEAT_B, P_VIEW_W, P_VIEW_B, P_RGB_W, P_RGB_B = 16, 17, 18, 19, 20, 21, 22, 23
@@ -76,6 +79,7 @@ _SIGNATURES = {
     'snerf_visibility2_composite_forward': (C.c_int, [_fp] * 4 + [C.c_int, C.c_int, C.c_int, _fp]),
     'snerf_visibility2_composite_backward': (C.c_int, [_fp] * 8 + [C.c_int, C.c_int, C.c_int, _fp]),
     'snerf_tensor_selftest': (C.c_int, [C.POINTER(C.c_float), _fp]),
+    'snerf_set_backward_split_event': (None, [_fp]),
 }
 EXPORTS = tuple(_SIGNATURES)
 _lib = None
@@ -84,10 +88,11 @@ _lib = None
 def load() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f'{LIB_PATH} is missing: build it with `python -m simplenerf_b200.build` '
+        path = LIB_DBG_PATH if os.environ.get('SNERF_B200_DEBUG_LIB') == '1' else LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError(f'{path} is missing: build it with `python -m simplenerf_b200.build` '
                                '(there is no CPU or PyTorch fallback for this path)')
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args

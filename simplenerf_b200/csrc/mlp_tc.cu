@@ -718,6 +718,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     return SNERF_OK;
 }
 
+#ifdef SNERF_DEBUG   // probe kernels and debug entry points live in libsimplenerf_b200_dbg.so only (build.py --debug)
 // ------------------------------------------------------------------------------------------------
 // Descriptor probe: runs a host-specified list of tcgen05.mma instructions on host-provided operand
 // images and returns the accumulator (tools/tc_probe.py).
@@ -793,6 +794,8 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint8_t* __restrict
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+#endif  // SNERF_DEBUG
+
 int tc_selftest(float* host_max_err, cudaStream_t) {
     for (int i = 0; i < 4; ++i) host_max_err[i] = -1.f;
     return fail(SNERF_ERR_UNSUPPORTED, "use tools/tc_probe.py");
@@ -803,6 +806,7 @@ int tc_selftest(float* host_max_err, cudaStream_t) {
 using namespace snerf;
 extern "C" int snerf_has_tensor_path(void) { return 1; }
 
+#ifdef SNERF_DEBUG
 extern "C" void snerfdbg_set_trace(long long* device_buffer_512) { snerf::g_trace = device_buffer_512; }
 extern "C" void snerfdbg_set_fwd_debug(int bits) { snerf::g_fwd_debug = bits; }
 extern "C" void snerfdbg_set_probe_pattern(int chunk, int waits) {
@@ -822,3 +826,4 @@ extern "C" int snerfdbg_probe(const void* a_img, uint32_t a_bytes, const void* b
     SNERF_LAUNCH_OK("tc_probe_kernel");
     return SNERF_OK;
 }
+#endif  // SNERF_DEBUG

@@ -1009,7 +1009,9 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
 
 }  // namespace snerf
 
+// measurement hook (include/simplenerf_b200.h): a cudaEvent_t recorded on the launch stream between the dgrad and the wgrad launch
+extern "C" void snerf_set_backward_split_event(void* event) { snerf::g_split_event = (cudaEvent_t)event; }
+#ifdef SNERF_DEBUG
 extern "C" void snerfdbg_set_wgrad_trace(long long* device_buffer) { snerf::g_wg_trace = device_buffer; }
-// measurement hook (not part of the public ABI): a cudaEvent_t recorded on the launch stream between dgrad and wgrad; null disables
-extern "C" void snerfdbg_set_backward_split_event(void* event) { snerf::g_split_event = (cudaEvent_t)event; }
 extern "C" void snerfdbg_set_wgrad_debug(int bits) { snerf::g_wg_debug = bits; }
+#endif  // SNERF_DEBUG

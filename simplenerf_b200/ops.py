@@ -188,8 +188,7 @@ def mlp_backward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, si
         split = getattr(tm, 'split_event', None)        # bench.py: an event recorded between the dgrad and the wgrad launch
         lib = _lib.load()
         if split is not None:
-            lib.snerfdbg_set_backward_split_event.argtypes = [C.c_void_p]
-            lib.snerfdbg_set_backward_split_event(split.cuda_event)
+            lib.snerf_set_backward_split_event(split.cuda_event)
         try:
             _lib.check(lib.snerf_mlp_backward(
                 C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
@@ -197,7 +196,7 @@ def mlp_backward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, si
                 workspace.numel(), n, s, flags, _stream()), 'snerf_mlp_backward')
         finally:
             if split is not None:
-                lib.snerfdbg_set_backward_split_event(None)
+                lib.snerf_set_backward_split_event(None)
 
 
 def visibility_forward(desc: MlpDesc, params, mlp_workspace, rays_o, rays_d, z, rays_o2, flags: int):

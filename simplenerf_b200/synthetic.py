@@ -141,3 +141,10 @@ def deterministic_state(shapes: Dict[str, tuple], seed: int) -> Dict[str, torch.
         bound = 1.0 / np.sqrt(fan_in)
         state[name] = torch.from_numpy(rng.uniform(-bound, bound, size=shape).astype(np.float32))
     return state
+
+
+def trained_scale_state(state: Dict[str, torch.Tensor], gain: float = 6.0 ** 0.5) -> Dict[str, torch.Tensor]:
+    """Weights of trained magnitude for parity fixtures: nn.Linear's default init U(-1/sqrt(fan_in), 1/sqrt(fan_in)) has a third of
+    the variance that keeps a ReLU trunk's signal alive, so random-init outputs are nearly constant (rgb within 0.02 of 0.5).
+    Every weight matrix times sqrt(6) is He-scaled: rgb then spans (0, 1) and sigma is O(1-10).  Biases are kept."""
+    return {k: (v * gain if k.endswith('weight') else v.clone()) for k, v in state.items()}

@@ -170,3 +170,34 @@ def test_visibility_head_oracle_matches_reference(tag):
         scale = float(g[f'{tag}_gnorm__{pname}'][0]) / max(1.0, prm.numel() ** 0.5)
         torch.testing.assert_close(gv, g[f'{tag}_gval__{pname}'], rtol=1e-3, atol=1e-4 * scale + 1e-9, msg=lambda m, p=pname: f'{p}: {m}')
         np.testing.assert_allclose(float(prm.grad.double().norm()), float(g[f'{tag}_gnorm__{pname}'][0]), rtol=1e-4)
+
+
+def test_mlp_trained_scale_matches_reference():
+    """The trained-scale fixture (oracle/make_golden_trained.py, unmodified reference MLP with He-scaled weights): the oracle
+    restatement reproduces it, the signal is wide enough for a relative tolerance to mean something, and the bf16 emulation
+    stays within the bound the GPU test uses while a dropped K chunk does not."""
+    from oracle.bf16_emulation import mlp_forward_bf16
+    g = gu.load('mlp_trained.npz')
+    configs = synthetic.make_configs('simplenerf')
+    for slot, mlp_cfg in orc.model_slots(configs).items():
+        if slot == 'fine_model':
+            continue
+        spec = orc.MlpSpec(mlp_cfg)
+        state = synthetic.trained_scale_state(orc.deterministic_state(spec.param_shapes(), int(g[f'{slot}_seed'][0])))
+        np.testing.assert_allclose(gu.checksum(state), g[f'{slot}_checksum'].numpy(), rtol=1e-12)
+        assert float(g[f'{slot}_eval_rgb'].std()) > 0.08 and float(g[f'{slot}_eval_sigma'].mean()) > 0.3
+        for training in (False, True):
+            tag = f"{slot}_{'train' if training else 'eval'}"
+            noise = g['noise'] if training else None
+            out = orc.mlp_forward(spec, state, g['pts'], g['view_dirs'], noise)
+            emu = mlp_forward_bf16(spec, state, g['pts'], g['view_dirs'], noise)
+            for k in ('sigma', 'rgb'):
+                want = g[f'{tag}_{k}']
+                torch.testing.assert_close(out[k].reshape(want.shape), want, rtol=2e-4, atol=2e-5)
+                err = emu[k].reshape(want.shape) - want
+                assert float(err.pow(2).mean().sqrt()) <= 0.03 * float(want.std()), (tag, k)
+        broken = {k: v.clone() for k, v in state.items()}
+        broken['pts_linears.3.weight'][:, 64:128] = 0
+        out = orc.mlp_forward(spec, broken, g['pts'], g['view_dirs'], None)
+        want = g[f'{slot}_eval_rgb']
+        assert float((out['rgb'].reshape(want.shape) - want).pow(2).mean().sqrt()) > 0.15 * float(want.std())

@@ -352,8 +352,23 @@ def test_fused_adam_matches_torch_adam():
         b.step()
         for p, q in zip(ours, theirs):
             torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-6, atol=1e-7)
+    # checkpoints travel both ways (src/Trainer01.py:352-381 saves optimizer.state_dict() and resumes with load_state_dict)
     state = a.state_dict()
-    assert state['step'] == 6 and len(state['exp_avg']) == len(shapes)
+    assert set(state) == {'state', 'param_groups'} and len(state['state']) == len(shapes) and float(state['state'][0]['step']) == 6
+    assert set(state['param_groups'][0]) == set(b.state_dict()['param_groups'][0])
+    ours2 = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    theirs2 = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    a2, b2 = FusedAdam(ours2, lr=1.0), torch.optim.Adam(theirs2, lr=1.0)
+    a2.load_state_dict(b.state_dict())          # written by torch.optim.Adam, resumed by FusedAdam
+    b2.load_state_dict(a.state_dict())          # written by FusedAdam, resumed by torch.optim.Adam
+    assert a2.param_groups[0]['lr'] == 1e-3 and b2.param_groups[0]['lr'] == 1e-3 and a2.step_count == 6
+    for p, q in zip(ours2, theirs2):
+        p.grad = cuda(torch.randn(p.shape, generator=gen))
+        q.grad = p.grad.clone()
+    a2.step()
+    b2.step()
+    for p, q in zip(ours2, theirs2):
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-6, atol=1e-7)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 """Probe of the cta_group::2 (CTA pair) MMA: D[256 x N] = A[256 x 64] B[N x 64]^T with exact small integers.
 Checks the operand / accumulator split between the two CTAs that the chain kernels assume, and times 256 pair MMAs."""
+import os as _os; _os.environ['SNERF_B200_DEBUG_LIB'] = '1'   # snerfdbg_* entry points live in libsimplenerf_b200_dbg.so (build.py --debug)
 import ctypes as C, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)

@@ -1,6 +1,7 @@
 """Round 2: where does the fused backward launch spend its time?  Times the whole launch, the dgrad chain alone and the
 weight-gradient jobs alone (debug bits 8 / 16), the latter also without MMAs (2), without reducer work (4) and without both (6),
 and prints the per-job cycle counts of the weight-gradient CTAs.  Run under SNERF_BWD_RING / SNERF_BWD_DGRAD_PAIRS settings."""
+import os as _os; _os.environ['SNERF_B200_DEBUG_LIB'] = '1'   # snerfdbg_* entry points live in libsimplenerf_b200_dbg.so (build.py --debug)
 import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

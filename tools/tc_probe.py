@@ -1,6 +1,7 @@
 """Probe of the tcgen05 shared-memory / instruction descriptors used by simplenerf_b200/csrc/mlp_tc.cu.
 Runs small exact-integer GEMMs through the debug entry `snerfdbg_probe` and compares with numpy.
 Usage (on a B200):  python tools/tc_probe.py"""
+import os as _os; _os.environ['SNERF_B200_DEBUG_LIB'] = '1'   # snerfdbg_* entry points live in libsimplenerf_b200_dbg.so (build.py --debug)
 import ctypes as C
 import os
 import sys

@@ -1,4 +1,5 @@
 """Swizzled bf16 panel images for the descriptor probes."""
+import os as _os; _os.environ['SNERF_B200_DEBUG_LIB'] = '1'   # snerfdbg_* entry points live in libsimplenerf_b200_dbg.so (build.py --debug)
 import numpy as np
 
 

@@ -1,4 +1,5 @@
 """TMEM -> register read throughput (tcgen05.ld) per SM: shapes, warp counts, with / without concurrent MMAs."""
+import os as _os; _os.environ['SNERF_B200_DEBUG_LIB'] = '1'   # snerfdbg_* entry points live in libsimplenerf_b200_dbg.so (build.py --debug)
 import ctypes as C, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)

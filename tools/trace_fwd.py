@@ -1,5 +1,6 @@
 """Timeline of one tile of the forward chain kernel (CTA 0, third tile): clock64 stamps of the MMA issuer and of one
 epilogue warp.  Debug tool for the pipeline analysis in profiles/."""
+import os as _os; _os.environ['SNERF_B200_DEBUG_LIB'] = '1'   # snerfdbg_* entry points live in libsimplenerf_b200_dbg.so (build.py --debug)
 import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,5 +1,6 @@
 """Per-job time of the wgrad kernel (one job per CTA): prints, for every job, the CTAs it got and their cycle counts.
 Debug tool for the static CTA allocation in tc_backward()."""
+import os as _os; _os.environ['SNERF_B200_DEBUG_LIB'] = '1'   # snerfdbg_* entry points live in libsimplenerf_b200_dbg.so (build.py --debug)
 import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
