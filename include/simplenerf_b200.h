@@ -219,6 +219,11 @@ int snerf_ray_losses_forward(const snerf_loss_stream* streams, int n_streams, in
 int snerf_ray_losses_backward(const snerf_loss_stream* streams, int n_streams, int n_rays, const int32_t* counts,
                               const float* grad_values, void* stream);
 
+/* Per-ray loss maps of the same streams (validation: src/Trainer01.py:195-196 passes return_loss_maps, :252-259 saves them):
+ * stream s writes [n_rays] floats through its `grad` pointer (used as the OUTPUT here): the ray's error averaged over its
+ * channels -- the `loss_maps` entry of compute_mse (MSE01.py:56, :63-66) -- and 0 on masked-out rays.                     */
+int snerf_ray_loss_maps(const snerf_loss_stream* streams, int n_streams, int n_rays, void* stream);
+
 /* Patch-reprojection depth losses: compute_loss_nerf of PointsAugmentationDepthLoss02 / ViewsAugmentationDepthLoss02 /
  * CoarseFineConsistencyLoss02 (src/loss_functions/PointsAugmentationDepthLoss02.py:98-176, identical in the three
  * modules; reprojection: src/utils/CommonUtils01.py:45-72).  One call compares ONE main depth with up to 4 other

@@ -69,6 +69,7 @@ _SIGNATURES = {
     'snerf_ray_losses_workspace_bytes': (C.c_size_t, []),
     'snerf_ray_losses_forward': (C.c_int, [C.POINTER(LossStream), C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     'snerf_ray_losses_backward': (C.c_int, [C.POINTER(LossStream), C.c_int, C.c_int, _fp, _fp, _fp]),
+    'snerf_ray_loss_maps': (C.c_int, [C.POINTER(LossStream), C.c_int, C.c_int, _fp]),
     'snerf_reprojection_losses_forward': (C.c_int, [C.POINTER(ReprojArgs), C.c_int, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     'snerf_reprojection_losses_backward': (C.c_int, [C.POINTER(ReprojArgs), C.c_int, _fp, _fp, _fp, _fp]),
     'snerf_gather_rows': (C.c_int, [C.POINTER(GatherTable), C.c_int, _fp, C.c_int, _fp]),

@@ -361,6 +361,28 @@ extern "C" int snerf_ray_losses_forward(const snerf_loss_stream* streams, int n_
     return SNERF_OK;
 }
 
+// per-ray loss maps (validation images, src/Trainer01.py:195-196, :252-259): maps[s][i] = the ray's term divided by its channel
+// count -- what compute_mse / compute_depth_loss return as `loss_maps` before averaging over rays (MSE01.py:56, :63-66)
+__global__ void __launch_bounds__(kLossThreads) ray_loss_maps_kernel(const __grid_constant__ LossTable t, int n_rays) {
+    for (int i = blockIdx.x * kLossThreads + threadIdx.x; i < n_rays; i += gridDim.x * kLossThreads)
+        for (int s = 0; s < t.n_streams; ++s) {
+            const bool in = t.mask[s] == nullptr || t.mask[s][i];
+            const float per_ray = t.kind[s] == SNERF_LOSS_PRIOR_SHORTFALL ? 1.f : (float)t.channels[s];
+            t.grad[s][i] = in ? ray_term(t.pred[s], t.target[s], i, t.channels[s], t.kind[s]) / per_ray : 0.f;
+        }
+}
+
+extern "C" int snerf_ray_loss_maps(const snerf_loss_stream* streams, int n_streams, int n_rays, void* stream) {
+    SNERF_REQUIRE(n_rays >= 0, "snerf_ray_loss_maps: bad ray count %d", n_rays);
+    LossTable t{};
+    if (int rc = fill_table(t, streams, n_streams, true, "snerf_ray_loss_maps")) return rc;
+    if (n_rays == 0) return SNERF_OK;
+    const int blocks = min(4 * kLossMaxBlocks, ceil_div(n_rays, kLossThreads));
+    ray_loss_maps_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(t, n_rays);
+    SNERF_LAUNCH_OK("ray_loss_maps_kernel");
+    return SNERF_OK;
+}
+
 extern "C" int snerf_ray_losses_backward(const snerf_loss_stream* streams, int n_streams, int n_rays, const int32_t* counts,
                                          const float* grad_values, void* stream) {
     SNERF_REQUIRE(n_rays >= 0, "snerf_ray_losses_backward: bad ray count %d", n_rays);

