@@ -153,8 +153,9 @@ def test_fused_loss_computer_plumbing_without_gpu():
     assert float(got['TotalLoss']) == 3.0 and float(got['SomeOtherLoss01']['loss_value']) == 6.0
     with pytest.raises(RuntimeError, match='Unknown Loss Function'):
         FusedLossComputer(configs).compute_losses(dict(inp, iter_num=100), out)
-    with pytest.raises(NotImplementedError):
-        FusedLossComputer(configs).compute_losses(inp, out, return_loss_maps=True)
+    # return_loss_maps (validation): every reported loss carries a `loss_maps` dict; extra losses keep theirs (none here)
+    got = FusedLossComputer(configs, extra_losses={'SomeOtherLoss01': Extra()}).compute_losses(dict(inp, iter_num=100), out, return_loss_maps=True)
+    assert got['SomeOtherLoss01']['loss_maps'] == {} and float(got['TotalLoss']) == 3.0
 
 
 def test_argument_validation_of_the_next_row_entry_points(lib):
