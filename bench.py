@@ -304,7 +304,7 @@ def run_ours(args):
     opt = (torch.optim.Adam(model.parameters(), lr=5e-4, betas=(0.9, 0.999), fused=True) if args.torch_adam
            else FusedAdam(model.parameters(), lr=5e-4, betas=(0.9, 0.999)))    # Trainer01.py:516, one launch
     params = [p for p in model.parameters()]
-    exchange = GradientExchange(params, weight=1.0 / world) if world > 1 else None
+    exchange = GradientExchange(params, weight=1.0 / world, overlap=args.exchange == 'overlap') if world > 1 else None
     n = RAYS_PER_GPU
     host = synthetic.make_ray_batch('llff', n, 1021 + rank)
     g = torch.Generator().manual_seed(3 + rank)
@@ -521,6 +521,8 @@ def main():
     ap.add_argument('--no-trainer', action='store_true', help='skip the runs behind the reference Trainer01 (N=1 only)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--quick-cpu', action='store_true')
+    ap.add_argument('--exchange', default='after', choices=['after', 'overlap'],
+                    help='gradient all-reduce: one coalesced launch after the backward pass (default) or per bucket from autograd hooks while it runs')
     ap.add_argument('--torch-loss', action='store_true', help='eager torch loss (8 masked means, ~80 launches) instead of snerf_ray_losses_*')
     ap.add_argument('--torch-adam', action='store_true', help='torch.optim.Adam(fused=True) instead of simplenerf_b200.optim.FusedAdam')
     args = ap.parse_args()

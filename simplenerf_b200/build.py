@@ -12,7 +12,7 @@ LIB_DBG = os.path.join(PKG, 'libsimplenerf_b200_dbg.so')
 SOURCES = ['api.cu', 'sampling.cu', 'composite.cu', 'mlp_simt.cu', 'mlp_tc.cu', 'mlp_tc_bwd.cu', 'adam.cu', 'raygen.cu', 'losses.cu', 'gather.cu']
 # developer library: the product sources compiled with -DSNERF_DEBUG (snerfdbg_* entry points: clock64 traces, stage
 # switches, descriptor probe) plus the stand-alone probe kernels -- kept out of the product library
-DEBUG_SOURCES = SOURCES + ['tmem_bench.cu', 'pair_probe.cu']
+DEBUG_SOURCES = SOURCES + ['tmem_bench.cu', 'pair_probe.cu', 'store_probe.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 

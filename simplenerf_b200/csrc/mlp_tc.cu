@@ -643,20 +643,36 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
         }
     } else if (warp == kWarpStash) {
         // ======================= stash writer (training) =======================
+        // One SM moves at most ~32 bytes per clock to global memory (tools/store_probe.py: 31.6 B/clk with two stores in
+        // flight, 25.8 when every store is waited for before the next is issued), and a training forward needs 64 KB per job =
+        // ~22 B/clk at the pace of the eval kernel: the store path is the resource to keep busy.  The writer therefore keeps
+        // TWO bulk stores in flight: the slot's panels are released (stash_done) when the NEXT store has been issued and the
+        // previous one has finished reading shared memory.  The two slots alternate, so the released slot is never the one
+        // the next store needs; with a single active slot (last, odd group) every store is waited for at once.
         if (save && lane == 0) {
-            SNERF_FOR_EACH_JOB(my_super, p.n_steps) {
-                const TcStep& st = p.steps[s];
-                const uint32_t jx = (uint32_t)(g * p.n_steps + s);
-                const int tile = tile_of(2 * g + x);
-                mbar_wait_sleep(&bars->stash_ready[x], jx & 1, 64);
-                if (tile < p.n_tiles) {
-                    bulk_s2g(p.stash + (size_t)tile * p.tile_stash_bytes + (size_t)st.slot * 65536, smem + kOffH + x * 65536,
-                             (uint32_t)(st.n_rows / 64) * kPanelBytes);
-                    bulk_commit();
-                    bulk_wait_read<0>();
-                }
-                mbar_arrive(&bars->stash_done[x]);
+            int pending = -1;                                  // slot whose store may still be reading its panels
+            for (int g = 0; 2 * g < my_super; ++g) {
+                const bool two = 2 * g + 1 < my_super;
+                for (int s = 0; s < p.n_steps; ++s)
+                    for (int x = 0; x < (two ? 2 : 1); ++x) {
+                        const TcStep& st = p.steps[s];
+                        const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+                        const int tile = tile_of(2 * g + x);
+                        mbar_wait_sleep(&bars->stash_ready[x], jx & 1, 64);
+                        if (tile < p.n_tiles) {
+                            bulk_s2g(p.stash + (size_t)tile * p.tile_stash_bytes + (size_t)st.slot * 65536, smem + kOffH + x * 65536,
+                                     (uint32_t)(st.n_rows / 64) * kPanelBytes);
+                            bulk_commit();
+                            if (pending >= 0) { bulk_wait_read<1>(); mbar_arrive(&bars->stash_done[pending]); pending = -1; }
+                            if (two) pending = x;
+                            else { bulk_wait_read<0>(); mbar_arrive(&bars->stash_done[x]); }
+                        } else {
+                            if (pending >= 0) { bulk_wait_read<0>(); mbar_arrive(&bars->stash_done[pending]); pending = -1; }
+                            mbar_arrive(&bars->stash_done[x]);
+                        }
+                    }
             }
+            if (pending >= 0) { bulk_wait_read<0>(); mbar_arrive(&bars->stash_done[pending]); }
             bulk_wait_all<0>();
         }
     }

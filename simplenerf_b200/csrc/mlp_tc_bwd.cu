@@ -362,33 +362,52 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
                 }
                 bulk_s2g(ring.base + ring_slot_off(slot, ring.cap) + (size_t)e * ring_entry_bytes(slot), src, bytes);
                 bulk_commit();
-                bulk_wait_read<0>();
                 if (ring.use_flags) {
                     if (pend_flag) { bulk_wait_all<1>(); flush(); }
                     pend_flag = ring.ready + (size_t)slot * ring.cap + e;
                     pend_val = (uint32_t)tile + 1u;
                 }
             };
+            // Two stores in flight (see the forward kernel's stash writer: one SM stores ~32 B/clk at best, 26 when every
+            // store is waited for): a slot's panels are released once the NEXT store -- always the other slot's -- has been
+            // issued and this one has finished reading shared memory.
+            int pending = -1;
+            bool pending_free = false;
+            auto release = [&](const bool keep_newest) {
+                if (pending < 0) return;
+                if (keep_newest) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                mbar_arrive(&bars->stash_done[pending]);
+                if (pending_free) mbar_arrive(&bars->slot_free[pending]);
+                pending = -1;
+                pending_free = false;
+            };
+            auto event = [&](const int x, const int tile, const int slot, const uint32_t bytes, const bool last_of_tile) {
+                if (tile < p.n_tiles) {
+                    emit(tile, slot, smem + kBOffH + x * 65536, bytes);
+                    release(true);
+                    pending = x;
+                    pending_free = last_of_tile;
+                } else {
+                    release(false);
+                    mbar_arrive(&bars->stash_done[x]);
+                    if (last_of_tile) mbar_arrive(&bars->slot_free[x]);
+                }
+            };
             for (int g = 0; 2 * g < my_super; ++g) {
-                const bool two = 2 * g + 1 < my_super;
                 if (pv) {
-                    for (int x = 0; x < (two ? 2 : 1); ++x) {
-                        const int tile = tile_of(2 * g + x);
+                    for (int x = 0; x < 2; ++x) {
                         mbar_wait(&bars->pro_local[x], g & 1);
-                        if (tile < p.n_tiles) emit(tile, 9, smem + kBOffH + x * 65536, 2 * kPanelBytes);
-                        mbar_arrive(&bars->stash_done[x]);
+                        event(x, tile_of(2 * g + x), 9, 2 * kPanelBytes, false);
                     }
                 }
                 for (int s = 0; s < p.n_steps; ++s)
-                    for (int x = 0; x < (two ? 2 : 1); ++x) {
+                    for (int x = 0; x < 2; ++x) {
                         const uint32_t jx = (uint32_t)(g * p.n_steps + s);
-                        const int tile = tile_of(2 * g + x);
                         mbar_wait(&bars->stash_ready[x], jx & 1);
-                        if (tile < p.n_tiles) emit(tile, p.steps[s].slot, smem + kBOffH + x * 65536, 4 * kPanelBytes);
-                        mbar_arrive(&bars->stash_done[x]);
-                        if (s == p.n_steps - 1) mbar_arrive(&bars->slot_free[x]);
+                        event(x, tile_of(2 * g + x), p.steps[s].slot, 4 * kPanelBytes, s == p.n_steps - 1);
                     }
             }
+            release(false);
             bulk_wait_all<0>();
             flush();
         }

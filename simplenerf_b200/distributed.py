@@ -120,11 +120,16 @@ class GradientExchange:
         loss.backward(); exchange.finish(); optimizer.step()
 
     The first step learns which parameters share a bucket (it exchanges everything in `finish`); from the second step on
-    every complete bucket is reduced in place the moment it is ready."""
+    every complete bucket is reduced in place the moment it is ready.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], weight: float = 1.0, group=None):
+    overlap=False: nothing is launched from the hooks; `finish` reduces all buckets in ONE coalesced NCCL launch after the
+    backward pass.  The backward kernels are persistent and fill every SM, so an all-reduce that runs beside them takes SMs
+    from them for as long as it is resident (round 1, 8 GPUs: +0.24 ms of backward for a ~50 us exchange); 9 MB over
+    NVLink 5 after the backward costs less than that."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], weight: float = 1.0, group=None, overlap: bool = True):
         self.params = [p for p in params if p.requires_grad]
-        self.weight, self.group = weight, group
+        self.weight, self.group, self.overlap = weight, group, overlap
         self.bucket_of: Dict[int, int] = {}          # id(param) -> bucket index (learned)
         self.bucket_size: List[int] = []
         self._seen: List[int] = []
@@ -152,8 +157,27 @@ class GradientExchange:
         by `finish`.  With one backward per step nothing has to be called (armed by default)."""
         self.armed = bool(final)
 
+    def _reduce_many(self, bufs: List[torch.Tensor]) -> None:
+        """All buffers in one grouped launch where the backend can (NCCL), else one collective each."""
+        if self._active() and len(bufs) > 1 and dist.get_backend(self.group) == 'nccl':
+            world = dist.get_world_size(self.group)
+            use_avg = abs(self.weight * world - 1.0) < 1e-12
+            if self.weight != 1.0 and not use_avg:
+                torch._foreach_mul_(bufs, self.weight)
+            try:
+                with dist._coalescing_manager(group=self.group, async_ops=True) as cm:
+                    for b in bufs:
+                        dist.all_reduce(b, op=dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM, group=self.group)
+                self._handles.append(cm)
+                return
+            except (AttributeError, RuntimeError, ValueError):      # no coalescing in this torch build: fall through
+                if self.weight != 1.0 and not use_avg:
+                    torch._foreach_mul_(bufs, 1.0 / self.weight)
+        for b in bufs:
+            self._reduce(b)
+
     def _on_grad(self, p: torch.nn.Parameter) -> None:
-        if not self.armed:
+        if not self.armed or not self.overlap:
             return
         b = self.bucket_of.get(id(p))
         if b is None:
@@ -171,8 +195,7 @@ class GradientExchange:
         if rest:
             flats, loose = _grad_buckets(rest)
             packed = torch.cat([p.grad.reshape(-1) for p in loose]) if loose else None
-            for b in flats + ([packed] if packed is not None else []):
-                self._reduce(b)
+            self._reduce_many(flats + ([packed] if packed is not None else []))
         for h in self._handles:
             h.wait()
         if rest and packed is not None:
