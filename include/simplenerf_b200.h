@@ -123,6 +123,24 @@ int snerf_mlp_forward(const snerf_mlp_desc* desc, const float* const* host_param
                       const float* sigma_noise, float* sigma, float* rgb, void* workspace, size_t workspace_bytes,
                       int n_rays, int n_samples, uint32_t flags, void* stream);
 
+/* ---- in-kernel random numbers (production draws in the kernels that consume them) ----------------
+ * The reference draws t_rand (:299), u (:341) and the sigma noise (:670) on the CPU generator and copies them to the device.
+ * The *_rng entry points draw them where they are consumed, from Philox4x32-10 keyed by `seed`, counter = (element / 4, `offset`):
+ * element e of a draw is the same number in every kernel, and snerf_fill_random writes exactly those numbers to memory, so
+ *   snerf_sample_coarse(t_rand = fill(uniform))        == snerf_sample_coarse_rng      bit for bit,
+ *   snerf_sample_fine(u = fill(uniform), stride n_new)  == snerf_sample_fine_rng,
+ *   snerf_mlp_forward(sigma_noise = fill(normal, std))  == snerf_mlp_forward_rng        (tensor path).
+ * Use a fresh `offset` per draw.  Elements: ray * n_samples + k (coarse), ray * n_new + k (fine), point index (noise).        */
+int snerf_fill_random(float* out, long long n, int normal, float scale, uint64_t seed, uint64_t offset, void* stream);
+int snerf_sample_coarse_rng(const float* near, const float* far, const float* t_vals, uint64_t seed, uint64_t offset,
+                            float* z_out, int n_rays, int n_samples, uint32_t flags, void* stream);
+int snerf_sample_fine_rng(const float* z_coarse, const float* weights_coarse, uint64_t seed, uint64_t offset, float* z_fine,
+                          int n_rays, int s_coarse, int n_new, void* stream);
+int snerf_mlp_forward_rng(const snerf_mlp_desc* desc, const float* const* host_params, const void* packed, const float* rays_o,
+                          const float* rays_d, const float* view_dirs, const float* z, float noise_std, uint64_t seed,
+                          uint64_t offset, float* sigma, float* rgb, void* workspace, size_t workspace_bytes, int n_rays,
+                          int n_samples, uint32_t flags, void* stream);
+
 /* Backward: consumes the workspace left by a forward run with FLAG_SAVE_FOR_BWD (same desc,
  * shapes and flags).  d_sigma [P], d_rgb [P,3] are gradients w.r.t. the forward outputs.
  * host_grads: HOST array of SNERF_P_COUNT device pointers, same shapes as the parameters;

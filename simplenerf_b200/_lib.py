@@ -80,6 +80,11 @@ _SIGNATURES = {
     'snerf_visibility2_composite_forward': (C.c_int, [_fp] * 4 + [C.c_int, C.c_int, C.c_int, _fp]),
     'snerf_visibility2_composite_backward': (C.c_int, [_fp] * 8 + [C.c_int, C.c_int, C.c_int, _fp]),
     'snerf_tensor_selftest': (C.c_int, [C.POINTER(C.c_float), _fp]),
+    'snerf_fill_random': (C.c_int, [_fp, C.c_longlong, C.c_int, C.c_float, C.c_uint64, C.c_uint64, _fp]),
+    'snerf_sample_coarse_rng': (C.c_int, [_fp, _fp, _fp, C.c_uint64, C.c_uint64, _fp, C.c_int, C.c_int, C.c_uint32, _fp]),
+    'snerf_sample_fine_rng': (C.c_int, [_fp, _fp, C.c_uint64, C.c_uint64, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    'snerf_mlp_forward_rng': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp), _fp, _fp, _fp, _fp, _fp, C.c_float, C.c_uint64, C.c_uint64,
+                                        _fp, _fp, _fp, C.c_size_t, C.c_int, C.c_int, C.c_uint32, _fp]),
     'snerf_set_backward_split_event': (None, [_fp]),
 }
 EXPORTS = tuple(_SIGNATURES)

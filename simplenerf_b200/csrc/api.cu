@@ -97,6 +97,26 @@ extern "C" int snerf_mlp_forward(const snerf_mlp_desc* desc, const float* const*
                       workspace_bytes, n_rays, n_samples, flags, (cudaStream_t)stream);
 }
 
+extern "C" int snerf_mlp_forward_rng(const snerf_mlp_desc* desc, const float* const* host_params, const void* packed,
+                                     const float* rays_o, const float* rays_d, const float* view_dirs, const float* z,
+                                     float noise_std, uint64_t seed, uint64_t offset, float* sigma, float* rgb, void* workspace,
+                                     size_t workspace_bytes, int n_rays, int n_samples, uint32_t flags, void* stream) {
+    int rc = validate_desc(desc);
+    if (rc != SNERF_OK) return rc;
+    rc = check_params(*desc, (const void* const*)host_params, "snerf_mlp_forward_rng");
+    if (rc != SNERF_OK) return rc;
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_mlp_forward_rng: bad sizes");
+    if (n_rays == 0) return SNERF_OK;
+    if (flags & SNERF_FLAG_PRECISE)
+        return fail(SNERF_ERR_UNSUPPORTED, "snerf_mlp_forward_rng: tensor path only (precise path: snerf_fill_random + snerf_mlp_forward draw the same numbers)");
+    SNERF_REQUIRE(rays_o && rays_d && z && sigma && rgb && workspace && packed, "snerf_mlp_forward_rng: null pointer");
+    SNERF_REQUIRE(desc->view_degree == 0 || view_dirs != nullptr, "snerf_mlp_forward_rng: view_dirs required by this MLP");
+    SNERF_REQUIRE((long long)n_rays * n_samples < (1LL << 31), "snerf_mlp_forward_rng: more than 2^31 points in one call");
+    const unsigned long long key[2] = {seed, offset};
+    return tc_forward(*desc, host_params, packed, rays_o, rays_d, view_dirs, z, nullptr, sigma, rgb, workspace, workspace_bytes,
+                      n_rays, n_samples, flags, (cudaStream_t)stream, key, noise_std);
+}
+
 extern "C" int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const* host_params, const void* packed,
                                   const float* rays_o, const float* rays_d, const float* view_dirs, const float* z,
                                   const float* sigma, const float* rgb, const float* d_sigma, const float* d_rgb,

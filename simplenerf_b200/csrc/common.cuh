@@ -97,7 +97,8 @@ size_t tc_packed_bytes(const snerf_mlp_desc& d);
 int tc_pack(const snerf_mlp_desc& d, const float* const* prm, void* packed, cudaStream_t st);
 int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o,
                const float* rays_d, const float* view_dirs, const float* z, const float* noise, float* sigma,
-               float* rgb, void* ws, size_t ws_bytes, int n_rays, int n_samples, uint32_t flags, cudaStream_t st);
+               float* rgb, void* ws, size_t ws_bytes, int n_rays, int n_samples, uint32_t flags, cudaStream_t st,
+               const unsigned long long* rng_seed_offset = nullptr, float noise_std = 0.f);
 int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o,
                 const float* rays_d, const float* view_dirs, const float* z, const float* sigma, const float* rgb,
                 const float* d_sigma, const float* d_rgb, float* const* grads, void* ws, size_t ws_bytes,

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_plan.cuh"
+#include "rng.cuh"
 
 namespace snerf {
 using namespace tc;
@@ -141,6 +142,9 @@ struct FwdParams {
     const float *w_head, *b_head, *w_rgb, *b_rgb;
     const float* view_bias;        // [n_rays,128]
     const float *rays_o, *rays_d, *z, *noise;
+    RngKey noise_rng;              // use_rng: sigma noise drawn in the head epilogue (element = point index) instead of read from `noise`
+    float noise_std;
+    int use_rng;
     float *sigma, *rgb;
     uint8_t* stash;                // null in eval
     uint8_t* bits;                 // (training) ReLU sign bits of the trunk activations, kBitsTileBytes per tile
@@ -575,7 +579,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
 #pragma unroll
                     for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h]);             // :704-707
                 } else {
-                    const float nz = p.noise ? p.noise[pt] : 0.f;
+                    float nz = 0.f;
+                    if (p.noise) nz = p.noise[pt];
+                    else if (p.use_rng) nz = p.noise_std * rng_pick(rng_normal4(p.noise_rng, (unsigned long long)pt >> 2), (unsigned long long)pt);
                     p.sigma[pt] = fmaxf(head[0] + nz, 0.f);                                        // :668-672
                     if (kind == EPI_RELU_HEAD4) {
 #pragma unroll
@@ -695,7 +701,7 @@ static int g_fwd_debug = 0;
 
 int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o, const float* rays_d,
                const float* view_dirs, const float* z, const float* noise, float* sigma, float* rgb, void* ws, size_t ws_bytes,
-               int n_rays, int n_samples, uint32_t flags, cudaStream_t st) {
+               int n_rays, int n_samples, uint32_t flags, cudaStream_t st, const unsigned long long* rng_seed_offset, float noise_std) {
     const MlpDims m(d);
     const TcPlan pl = build_plan(d, prm);
     const TcWorkspace w = tc_ws_layout(m, pl, n_rays, n_samples, flags);
@@ -715,6 +721,11 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     p.w_rgb = m.has_view ? prm[SNERF_P_RGB_W] : nullptr; p.b_rgb = m.has_view ? prm[SNERF_P_RGB_B] : nullptr;
     p.view_bias = (const float*)(wsb + w.view_bias);
     p.rays_o = rays_o; p.rays_d = rays_d; p.z = z; p.noise = noise; p.sigma = sigma; p.rgb = rgb;
+    if (rng_seed_offset != nullptr && noise == nullptr && noise_std != 0.f) {
+        p.noise_rng = RngKey{rng_seed_offset[0], rng_seed_offset[1]};
+        p.noise_std = noise_std;
+        p.use_rng = 1;
+    }
     p.stash = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.act : nullptr;
     p.bits = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.bits : nullptr;
     p.trace = g_trace; p.debug = g_fwd_debug;

@@ -5,6 +5,7 @@
 // Both kernels reproduce the reference's fp32 arithmetic op by op (explicit _rn intrinsics stop
 // nvcc from contracting a*b+c into FMA, which the eager CPU reference never does).
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace snerf {
 
@@ -24,22 +25,23 @@ __global__ void __launch_bounds__(256) sample_coarse_kernel(const float* __restr
                                                             const float* __restrict__ t_vals,
                                                             const float* __restrict__ t_rand,
                                                             float* __restrict__ z_out, int n_rays, int s,
-                                                            bool lindisp) {
+                                                            bool lindisp, const RngKey rng, const bool use_rng) {
     // generic path: one thread per sample
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)n_rays * s) return;
     const int ray = (int)(gid / s), k = (int)(gid % s);
     const float nr = near[ray], fr = far[ray];
     const float zk = lerp_depth(nr, fr, t_vals[k], lindisp);
-    if (t_rand == nullptr) {
+    if (t_rand == nullptr && !use_rng) {
         z_out[gid] = zk;
         return;
     }
+    const float tr = use_rng ? rng_pick(rng_uniform4(rng, (unsigned long long)gid >> 2), (unsigned long long)gid) : t_rand[gid];
     // lower = [z0, mids], upper = [mids, z_last]   (:295-297)
     float lo = zk, hi = zk;
     if (k > 0) lo = __fmul_rn(.5f, __fadd_rn(zk, lerp_depth(nr, fr, t_vals[k - 1], lindisp)));
     if (k < s - 1) hi = __fmul_rn(.5f, __fadd_rn(lerp_depth(nr, fr, t_vals[k + 1], lindisp), zk));
-    z_out[gid] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), t_rand[gid]));                      // :301
+    z_out[gid] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), tr));                               // :301
 }
 
 // s % 4 == 0: thread handles samples 4q..4q+3 of one ray; q4 = s / 4 threads per ray.  The kernel is issue-bound (ncu: 66 %
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(256) sample_coarse_vec4_kernel(const float* __
                                                                  const float* __restrict__ t_vals,
                                                                  const float* __restrict__ t_rand,
                                                                  float* __restrict__ z_out, int n_rays, int s_rt, int q4_rt,
-                                                                 bool lindisp_rt) {
+                                                                 bool lindisp_rt, const RngKey rng, const bool use_rng) {
     const int s = S_FIXED > 0 ? S_FIXED : s_rt;
     const int q4 = S_FIXED > 0 ? S_FIXED / 4 : q4_rt;
     const bool lindisp = LINDISP_RT ? lindisp_rt : false;
@@ -67,10 +69,12 @@ __global__ void __launch_bounds__(256) sample_coarse_vec4_kernel(const float* __
     zc[3] = lerp_depth(nr, fr, t4.z, lindisp);
     zc[4] = lerp_depth(nr, fr, t4.w, lindisp);
     float out[4] = {zc[1], zc[2], zc[3], zc[4]};
-    if (t_rand != nullptr) {
+    if (t_rand != nullptr || use_rng) {
         zc[0] = k0 > 0 ? lerp_depth(nr, fr, t_vals[k0 - 1], lindisp) : zc[1];
         zc[5] = k0 + 4 < s ? lerp_depth(nr, fr, t_vals[k0 + 4], lindisp) : zc[4];
-        const float4 r4 = __ldg(reinterpret_cast<const float4*>(t_rand + (size_t)ray * s + k0));
+        // in-kernel draw: element ray * s + k0 is a multiple of four, i.e. one Philox block per thread
+        const float4 r4 = use_rng ? rng_uniform4(rng, ((unsigned long long)ray * s + k0) >> 2)
+                                  : __ldg(reinterpret_cast<const float4*>(t_rand + (size_t)ray * s + k0));
         const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -91,7 +95,7 @@ constexpr int kFineWarps = 4;
 
 __global__ void __launch_bounds__(kFineWarps* kWarp)
     sample_fine_generic_kernel(const float* __restrict__ z_coarse, const float* __restrict__ w_coarse,
-                               const float* __restrict__ u, int u_stride, float* __restrict__ z_fine,
+                               const float* __restrict__ u, int u_stride, const RngKey rng, const bool use_rng, float* __restrict__ z_fine,
                                float* __restrict__ samples_dbg, float* __restrict__ cdf_dbg, int* __restrict__ below_dbg,
                                int* __restrict__ above_dbg, int n_rays, int sc, int n_new, int npad) {
     extern __shared__ float smem[];
@@ -148,9 +152,10 @@ __global__ void __launch_bounds__(kFineWarps* kWarp)
     if (cdf_dbg != nullptr)
         for (int i = lane; i < nb; i += kWarp) cdf_dbg[(size_t)ray * nb + i] = cdf[i];
 
-    const float* urow = u + (size_t)ray * u_stride;
+    const float* urow = use_rng ? nullptr : u + (size_t)ray * u_stride;
     for (int s = lane; s < n_new; s += kWarp) {
-        const float us = urow[s];
+        const unsigned long long el = (unsigned long long)ray * n_new + s;
+        const float us = use_rng ? rng_pick(rng_uniform4(rng, el >> 2), el) : urow[s];
         int lo = 0, hi = nb;   // searchsorted(right=True): first index with cdf[idx] > u
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -277,7 +282,7 @@ __device__ __forceinline__ void bitonic_sort_registers(float (&v)[NPL], int lane
 template <int NPL, int WARPS>
 __global__ void __launch_bounds__(WARPS* kWarp)
     sample_fine_fast_kernel(const float* __restrict__ z_coarse, const float* __restrict__ w_coarse,
-                            const float* __restrict__ u, int u_stride, float* __restrict__ z_fine,
+                            const float* __restrict__ u, int u_stride, const RngKey rng, const bool use_rng, float* __restrict__ z_fine,
                             float* __restrict__ samples_dbg, float* __restrict__ cdf_dbg, int* __restrict__ below_dbg,
                             int* __restrict__ above_dbg, int n_rays) {
     constexpr int NNEW = NPL * kWarp, TOT = kSc + NNEW, NB = kSc - 1;
@@ -363,7 +368,20 @@ __global__ void __launch_bounds__(WARPS* kWarp)
     Row& row = s_rows[warp][which];
     const float2 z2 = *reinterpret_cast<const float2*>(row.zc + 2 * lane);     // this lane's coarse depths 2*lane, 2*lane+1
     float us[NPL];
-    {
+    if (use_rng) {     // in-kernel draw (:341): this lane's NPL consecutive elements of the ray's row
+        const unsigned long long el = (unsigned long long)ray * NNEW + lane * NPL;
+        if constexpr (NPL % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < NPL / 4; ++i) {
+                const float4 t = rng_uniform4(rng, (el >> 2) + i);
+                us[4 * i] = t.x; us[4 * i + 1] = t.y; us[4 * i + 2] = t.z; us[4 * i + 3] = t.w;
+            }
+        } else {
+            const float4 t = rng_uniform4(rng, el >> 2);
+            us[0] = (el & 2ull) ? t.z : t.x;
+            us[1] = (el & 2ull) ? t.w : t.y;
+        }
+    } else {
         const float* urow = u + (size_t)ray * u_stride + lane * NPL;
         if constexpr (NPL % 4 == 0) {
 #pragma unroll
@@ -509,11 +527,11 @@ __global__ void __launch_bounds__(WARPS* kWarp)
 
 using namespace snerf;
 
-extern "C" int snerf_sample_coarse(const float* near, const float* far, const float* t_vals, const float* t_rand,
-                                   float* z_out, int n_rays, int n_samples, uint32_t flags, void* stream) {
-    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_sample_coarse: bad sizes (%d rays, %d samples)", n_rays, n_samples);
+static int sample_coarse_impl(const float* near, const float* far, const float* t_vals, const float* t_rand, const RngKey rng,
+                              const bool use_rng, float* z_out, int n_rays, int n_samples, uint32_t flags, void* stream, const char* who) {
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "%s: bad sizes (%d rays, %d samples)", who, n_rays, n_samples);
     if (n_rays == 0) return SNERF_OK;   // empty batch: nothing to launch (pointers may be null)
-    SNERF_REQUIRE(near && far && t_vals && z_out, "snerf_sample_coarse: null pointer");
+    SNERF_REQUIRE(near && far && t_vals && z_out, "%s: null pointer", who);
     const bool lindisp = (flags & SNERF_FLAG_LINDISP) != 0;
     const long long total = (long long)n_rays * n_samples;
     const bool aligned = ((reinterpret_cast<uintptr_t>(t_vals) | reinterpret_cast<uintptr_t>(t_rand) |
@@ -524,28 +542,38 @@ extern "C" int snerf_sample_coarse(const float* near, const float* far, const fl
         const unsigned blocks = (unsigned)((threads + 255) / 256);
         if (n_samples == 64 && !lindisp)
             sample_coarse_vec4_kernel<64, false><<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, t_vals, t_rand, z_out, n_rays,
-                                                                                         n_samples, q4, lindisp);
+                                                                                         n_samples, q4, lindisp, rng, use_rng);
         else
             sample_coarse_vec4_kernel<0, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, t_vals, t_rand, z_out, n_rays,
-                                                                                        n_samples, q4, lindisp);
+                                                                                        n_samples, q4, lindisp, rng, use_rng);
         SNERF_LAUNCH_OK("sample_coarse_vec4_kernel");
         return SNERF_OK;
     }
     const int blocks = (int)((total + 255) / 256);
-    sample_coarse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, t_vals, t_rand, z_out, n_rays, n_samples, lindisp);
+    sample_coarse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(near, far, t_vals, t_rand, z_out, n_rays, n_samples, lindisp, rng, use_rng);
     SNERF_LAUNCH_OK("sample_coarse_kernel");
     return SNERF_OK;
 }
 
-extern "C" int snerf_sample_fine(const float* z_coarse, const float* weights_coarse, const float* u, int u_stride,
-                                 float* z_fine, float* samples_dbg, float* cdf_dbg, int32_t* below_dbg,
-                                 int32_t* above_dbg, int n_rays, int s_coarse, int n_new, void* stream) {
-    SNERF_REQUIRE(n_rays >= 0 && s_coarse >= 3 && n_new >= 1, "snerf_sample_fine: bad sizes (%d rays, %d coarse, %d new)",
-                  n_rays, s_coarse, n_new);
+extern "C" int snerf_sample_coarse(const float* near, const float* far, const float* t_vals, const float* t_rand,
+                                   float* z_out, int n_rays, int n_samples, uint32_t flags, void* stream) {
+    return sample_coarse_impl(near, far, t_vals, t_rand, RngKey{0, 0}, false, z_out, n_rays, n_samples, flags, stream, "snerf_sample_coarse");
+}
+
+extern "C" int snerf_sample_coarse_rng(const float* near, const float* far, const float* t_vals, uint64_t seed, uint64_t offset,
+                                       float* z_out, int n_rays, int n_samples, uint32_t flags, void* stream) {
+    return sample_coarse_impl(near, far, t_vals, nullptr, RngKey{seed, offset}, true, z_out, n_rays, n_samples, flags, stream,
+                              "snerf_sample_coarse_rng");
+}
+
+static int sample_fine_impl(const float* z_coarse, const float* weights_coarse, const float* u, int u_stride, const RngKey rng,
+                            const bool use_rng, float* z_fine, float* samples_dbg, float* cdf_dbg, int32_t* below_dbg,
+                            int32_t* above_dbg, int n_rays, int s_coarse, int n_new, void* stream, const char* who) {
+    SNERF_REQUIRE(n_rays >= 0 && s_coarse >= 3 && n_new >= 1, "%s: bad sizes (%d rays, %d coarse, %d new)", who, n_rays, s_coarse, n_new);
     if (n_rays == 0) return SNERF_OK;
-    SNERF_REQUIRE(z_coarse && weights_coarse && u && z_fine, "snerf_sample_fine: null pointer");
-    SNERF_REQUIRE(u_stride == 0 || u_stride >= n_new, "snerf_sample_fine: u_stride %d < n_new %d", u_stride, n_new);
-    if (s_coarse + n_new > 1024) return fail(SNERF_ERR_UNSUPPORTED, "snerf_sample_fine: %d + %d samples > 1024", s_coarse, n_new);
+    SNERF_REQUIRE(z_coarse && weights_coarse && (u || use_rng) && z_fine, "%s: null pointer", who);
+    SNERF_REQUIRE(use_rng || u_stride == 0 || u_stride >= n_new, "%s: u_stride %d < n_new %d", who, u_stride, n_new);
+    if (s_coarse + n_new > 1024) return fail(SNERF_ERR_UNSUPPORTED, "%s: %d + %d samples > 1024", who, s_coarse, n_new);
     const bool aligned = ((reinterpret_cast<uintptr_t>(z_coarse) | reinterpret_cast<uintptr_t>(weights_coarse) |
                            reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(z_fine)) & 15) == 0 && u_stride % 4 == 0;
     if (s_coarse == kSc && aligned && (n_new == 64 || n_new == 128 || n_new == 256)) {
@@ -553,13 +581,13 @@ extern "C" int snerf_sample_fine(const float* z_coarse, const float* weights_coa
         // two rays per warp; the 256-sample row needs 8.5 KB of shared memory per warp, so its blocks have four warps
         if (n_new == 64)
             sample_fine_fast_kernel<2, kFastWarps><<<ceil_div(n_rays, 2 * kFastWarps), kFastWarps * kWarp, 0, st>>>(
-                z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays);
+                z_coarse, weights_coarse, u, u_stride, rng, use_rng, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays);
         else if (n_new == 128)
             sample_fine_fast_kernel<4, kFastWarps><<<ceil_div(n_rays, 2 * kFastWarps), kFastWarps * kWarp, 0, st>>>(
-                z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays);
+                z_coarse, weights_coarse, u, u_stride, rng, use_rng, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays);
         else
             sample_fine_fast_kernel<8, 4><<<ceil_div(n_rays, 2 * 4), 4 * kWarp, 0, st>>>(
-                z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays);
+                z_coarse, weights_coarse, u, u_stride, rng, use_rng, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays);
         SNERF_LAUNCH_OK("sample_fine_fast_kernel");
         return SNERF_OK;
     }
@@ -572,8 +600,40 @@ extern "C" int snerf_sample_fine(const float* z_coarse, const float* weights_coa
         attr_set = true;
     }
     sample_fine_generic_kernel<<<ceil_div(n_rays, kFineWarps), kFineWarps * kWarp, smem, (cudaStream_t)stream>>>(
-        z_coarse, weights_coarse, u, u_stride, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays, s_coarse,
+        z_coarse, weights_coarse, u, u_stride, rng, use_rng, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg, n_rays, s_coarse,
         n_new, npad);
     SNERF_LAUNCH_OK("sample_fine_generic_kernel");
+    return SNERF_OK;
+}
+
+extern "C" int snerf_sample_fine(const float* z_coarse, const float* weights_coarse, const float* u, int u_stride,
+                                 float* z_fine, float* samples_dbg, float* cdf_dbg, int32_t* below_dbg,
+                                 int32_t* above_dbg, int n_rays, int s_coarse, int n_new, void* stream) {
+    return sample_fine_impl(z_coarse, weights_coarse, u, u_stride, RngKey{0, 0}, false, z_fine, samples_dbg, cdf_dbg, below_dbg, above_dbg,
+                            n_rays, s_coarse, n_new, stream, "snerf_sample_fine");
+}
+
+extern "C" int snerf_sample_fine_rng(const float* z_coarse, const float* weights_coarse, uint64_t seed, uint64_t offset,
+                                     float* z_fine, int n_rays, int s_coarse, int n_new, void* stream) {
+    return sample_fine_impl(z_coarse, weights_coarse, nullptr, 0, RngKey{seed, offset}, true, z_fine, nullptr, nullptr, nullptr, nullptr,
+                            n_rays, s_coarse, n_new, stream, "snerf_sample_fine_rng");
+}
+
+// out[e] = scale * (uniform [0,1) or standard normal) of element e of draw (seed, offset): the numbers the *_rng entry points consume
+__global__ void __launch_bounds__(256) fill_random_kernel(float* __restrict__ out, long long n, int normal, float scale, const RngKey rng) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * b >= n) return;
+    const float4 v = normal ? rng_normal4(rng, (unsigned long long)b) : rng_uniform4(rng, (unsigned long long)b);
+    const float r[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    for (int i = 0; i < 4 && 4 * b + i < n; ++i) out[4 * b + i] = r[i];
+}
+
+extern "C" int snerf_fill_random(float* out, long long n, int normal, float scale, uint64_t seed, uint64_t offset, void* stream) {
+    SNERF_REQUIRE(n >= 0, "snerf_fill_random: bad size");
+    if (n == 0) return SNERF_OK;
+    SNERF_REQUIRE(out != nullptr, "snerf_fill_random: null pointer");
+    const long long blocks = ((n + 3) / 4 + 255) / 256;
+    fill_random_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, n, normal, scale, RngKey{seed, offset});
+    SNERF_LAUNCH_OK("fill_random_kernel");
     return SNERF_OK;
 }

@@ -14,8 +14,9 @@ fallback -- a missing library or a CPU tensor raises.
 
 Extra, optional keys read from ``configs['model']`` (absent in reference configs):
 ``precision``: ``'bf16'`` (tcgen05 tensor path, default) or ``'fp32'`` (CUDA-core precise path);
-``rng``: ``'device'`` (default: draws on the GPU) or ``'reference'`` (draws on the CPU generator in
-the reference's order, so equal seeds give equal random numbers, ``:299, :341, :670``);
+``rng``: ``'device'`` (default: the kernels that consume a random number draw it themselves -- counter-based Philox keyed by
+``torch.initial_seed()``, nothing is materialised), ``'torch'`` (torch.rand / randn tensors on the GPU) or ``'reference'`` (draws
+on the CPU generator in the reference's order, so equal seeds give equal random numbers, ``:299, :341, :670``);
 ``launch_rays``: rays per kernel launch group (default 65536; bounds workspace memory).
 """
 from __future__ import annotations
@@ -114,6 +115,31 @@ class DeviceRandoms:
 
     def sigma_noise(self, tag, p, device):
         return torch.randn(p, device=device)
+
+
+class KernelRandoms(DeviceRandoms):
+    """Production random source: every draw is an `ops.RngDraw` -- a (seed, offset) pair handed to the
+    kernel that consumes the numbers (stratified sampler, resampler, sigma-head epilogue).  The seed is torch's
+    (`torch.manual_seed` makes runs repeatable), the offset counts the draws of this model."""
+
+    def __init__(self):
+        self.seed = None
+        self.draws = 0
+
+    def _draw(self, scale: float = 1.0) -> 'ops.RngDraw':
+        if self.seed is None:
+            self.seed = torch.initial_seed()
+        self.draws += 1
+        return ops.RngDraw(self.seed, self.draws, scale)
+
+    def t_rand(self, n, s, device):
+        return self._draw()
+
+    def u(self, n, s, device):
+        return (self._draw(), s)
+
+    def sigma_noise(self, tag, p, device):
+        return self._draw()
 
 
 class ReferenceOrderRandoms(DeviceRandoms):
@@ -277,8 +303,11 @@ class FusedSimpleNeRF(torch.nn.Module):
             raise NotImplementedError("predict_visibility=True (secondary-view visibility head, SURVEY row a14 / N4) is built on the "
                                       "fp32 path only: set configs['model']['precision'] = 'fp32' (every shipped config has it False)")
         self.launch_rays = int(mc.get('launch_rays', 65536))
-        self.randoms: DeviceRandoms = (ReferenceOrderRandoms(mc.get('netchunk')) if mc.get('rng', 'device') == 'reference'
-                                       else DeviceRandoms())
+        rng = mc.get('rng', 'device')
+        if rng not in ('device', 'torch', 'reference'):
+            raise ValueError(f"configs['model']['rng'] must be 'device', 'torch' or 'reference', got {rng!r}")
+        self.randoms: DeviceRandoms = (ReferenceOrderRandoms(mc.get('netchunk')) if rng == 'reference'
+                                       else DeviceRandoms() if rng == 'torch' else KernelRandoms())
         self._const_cache: Dict[tuple, torch.Tensor] = {}
 
     # torch.linspace is evaluated on the CPU exactly as the reference does (:285, :338) and cached per device
@@ -333,8 +362,11 @@ class FusedSimpleNeRF(torch.nn.Module):
         dev = z.device
         noise = None
         if self.training and mc['raw_noise_std'] > 0.:                           # :669-671
-            noise = self.randoms.sigma_noise(attr, n * s, dev).reshape(-1).float() * mc['raw_noise_std']
-            noise = noise.contiguous()
+            noise = self.randoms.sigma_noise(attr, n * s, dev)
+            if isinstance(noise, ops.RngDraw):
+                noise.scale = float(mc['raw_noise_std'])
+            else:
+                noise = (noise.reshape(-1).float() * mc['raw_noise_std']).contiguous()
         table = block.param_table()
         params = [p for p in table if p is not None]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)

@@ -58,11 +58,34 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------
-def sample_coarse(near: torch.Tensor, far: torch.Tensor, t_vals: torch.Tensor, t_rand: Optional[torch.Tensor],
-                  lindisp: bool = False) -> torch.Tensor:
-    """get_z_vals_coarse (reference :272-302).  near/far [N,1] or [N]; t_vals [S]; t_rand [N,S] or None."""
+class RngDraw:
+    """One draw of the in-kernel generator (Philox4x32-10 keyed by `seed`, counter = (element / 4, `offset`)): passed where a
+    tensor of random numbers would go, the consuming kernel draws the numbers itself (snerf_*_rng).  `materialize` writes the
+    very same numbers to memory (snerf_fill_random) for the code paths that need a tensor."""
+
+    def __init__(self, seed: int, offset: int, scale: float = 1.0):
+        self.seed, self.offset, self.scale = int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), float(scale)
+
+    def materialize(self, shape, device, normal: bool) -> torch.Tensor:
+        out = torch.empty(shape, device=device, dtype=torch.float32)
+        LAUNCHES['count'] += 1
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.load().snerf_fill_random(_ptr(out), out.numel(), int(normal), self.scale, self.seed, self.offset, _stream()),
+                       'snerf_fill_random')
+        return out
+
+
+def sample_coarse(near: torch.Tensor, far: torch.Tensor, t_vals: torch.Tensor, t_rand, lindisp: bool = False) -> torch.Tensor:
+    """get_z_vals_coarse (reference :272-302).  near/far [N,1] or [N]; t_vals [S]; t_rand [N,S], an RngDraw (drawn in the
+    kernel) or None."""
     n, s = near.shape[0], t_vals.shape[0]
     near, far, t_vals = _f32(near).reshape(-1), _f32(far).reshape(-1), _f32(t_vals)
+    if isinstance(t_rand, RngDraw):
+        z = torch.empty((n, s), device=near.device, dtype=torch.float32)
+        LAUNCHES['count'] += 1
+        _lib.check(_lib.load().snerf_sample_coarse_rng(_ptr(near), _ptr(far), _ptr(t_vals), t_rand.seed, t_rand.offset, _ptr(z), n, s,
+                                                       FLAG_LINDISP if lindisp else 0, _stream()), 'snerf_sample_coarse_rng')
+        return z
     if t_rand is not None:
         t_rand = _f32(t_rand)
         assert tuple(t_rand.shape) == (n, s)
@@ -75,8 +98,18 @@ def sample_coarse(near: torch.Tensor, far: torch.Tensor, t_vals: torch.Tensor, t
 
 def sample_fine(z_coarse: torch.Tensor, weights_coarse: torch.Tensor, u: torch.Tensor, debug: bool = False):
     """get_z_vals_fine + sample_pdf (reference :304-361).  u: [N,n_new] random draws, or [n_new] = the
-    deterministic linspace row shared by all rays."""
+    deterministic linspace row shared by all rays, or (RngDraw, n_new): drawn in the kernel."""
     n, sc = z_coarse.shape
+    if isinstance(u, tuple) and isinstance(u[0], RngDraw):
+        draw, n_new = u
+        if debug:
+            return sample_fine(z_coarse, weights_coarse, draw.materialize((n, n_new), z_coarse.device, normal=False), debug=True)
+        z_coarse, weights_coarse = _f32(z_coarse), _f32(weights_coarse)
+        z_fine = torch.empty((n, sc + n_new), device=z_coarse.device, dtype=torch.float32)
+        LAUNCHES['count'] += 1
+        _lib.check(_lib.load().snerf_sample_fine_rng(_ptr(z_coarse), _ptr(weights_coarse), draw.seed, draw.offset, _ptr(z_fine), n, sc,
+                                                     n_new, _stream()), 'snerf_sample_fine_rng')
+        return z_fine
     z_coarse, weights_coarse, u = _f32(z_coarse), _f32(weights_coarse), _f32(u)
     n_new = u.shape[-1]
     u_stride = 0 if u.dim() == 1 else n_new
@@ -172,6 +205,16 @@ def mlp_forward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, noi
     rgb = torch.empty((n, s, 3), device=z.device)
     # tensor path: view-bias kernel (view-dependent MLPs) + the fused chain kernel; precise path: ~14 launches
     LAUNCHES['count'] += (14 if flags & FLAG_PRECISE else (2 if desc.view_width else 1))
+    if isinstance(noise, RngDraw):
+        if flags & FLAG_PRECISE:        # the fp32 path reads a tensor: the same numbers, written out first
+            noise = noise.materialize((n * s,), z.device, normal=True)
+        else:                           # tensor path: drawn in the sigma-head epilogue
+            with _timed('mlp_forward'):
+                _lib.check(_lib.load().snerf_mlp_forward_rng(
+                    C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
+                    _ptr(z), noise.scale, noise.seed, noise.offset, _ptr(sigma), _ptr(rgb), _ptr(workspace, torch.uint8),
+                    workspace.numel(), n, s, flags, _stream()), 'snerf_mlp_forward_rng')
+            return sigma, rgb
     with _timed('mlp_forward'):
         _lib.check(_lib.load().snerf_mlp_forward(
             C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(view_dirs),
