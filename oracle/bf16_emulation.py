@@ -1,9 +1,11 @@
 """Torch restatement of the ROUNDING POINTS of the bf16 tensor path (test infrastructure only).
 
 Same algorithm as ``oracle.nerf_oracle.mlp_forward`` (reference src/models/SimpleNeRF01.py:626-715) with
-bf16 rounding applied exactly where the tcgen05 kernels round: the encoded points, every hidden activation
-and the feature vector that feed a tensor-core GEMM, and the weights of those GEMMs.  Heads (sigma, rgb) and
-the view-direction part of the view layer stay fp32, as in the kernels.  Rounding is straight-through in the
+bf16 rounding applied exactly where the tcgen05 kernels round: the encoded points and every hidden activation
+that feed a tensor-core GEMM, and the weights of those GEMMs.  Heads (sigma, rgb) and the view-direction part of
+the view layer stay fp32, as in the kernels.  feature_linear has no activation (:691-697), and the kernels multiply the
+last trunk activation by the merged matrix  W_view[:, :256] @ W_feat  (formed in fp32, rounded to bf16 once; the feature
+bias reaches the view layer in fp32): the feature vector itself is never formed, so it is not rounded here either.  Rounding is straight-through in the
 backward pass, so autograd yields the gradient the kernels are expected to produce (it
 isolates kernel bugs from the unavoidable ReLU-mask flips of a bf16 forward)."""
 import torch
@@ -49,11 +51,12 @@ def mlp_forward_bf16(spec, params, pts, view_dirs, sigma_noise=None):
     if not spec.view_dep_rgb:
         out['rgb'] = out['rgb_view_independent'] = torch.sigmoid(head[..., 1:4])
         return out
-    feat = bf(bf(F.linear(x, bf(params['feature_linear.weight']))) + bf(params['feature_linear.bias']))
     wv = params['views_linears.0.weight']
     n_hi = spec.pts_enc_dim - spec.trunk_in
     venc = orc.positional_encoding(view_dirs, spec.view_degree)
-    pre = F.linear(feat, bf(wv[:, :spec.width])) + F.linear(venc, wv[:, spec.width + n_hi:], params['views_linears.0.bias'])
+    merged = bf(wv[:, :spec.width] @ params['feature_linear.weight'])
+    pre = (F.linear(x, merged) + F.linear(params['feature_linear.bias'], wv[:, :spec.width])
+           + F.linear(venc, wv[:, spec.width + n_hi:], params['views_linears.0.bias']))
     if n_hi:
         pre = pre + F.linear(e_bf[:, spec.trunk_in:], bf(wv[:, spec.width:spec.width + n_hi]))
     hv = F.relu(pre)

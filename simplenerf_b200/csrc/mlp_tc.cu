@@ -24,7 +24,9 @@
 namespace snerf {
 using namespace tc;
 
-size_t tc_packed_bytes(const snerf_mlp_desc& d) { return align_up(build_plan(d, nullptr).packed_bytes, 1024); }
+// packed image = bf16 weight chunks, then (MLPs with a view branch) the fp32 merged matrix W_vf the chunks were cut from
+static size_t packed_chunk_bytes(const snerf_mlp_desc& d) { return align_up(build_plan(d, nullptr).packed_bytes, 1024); }
+size_t tc_packed_bytes(const snerf_mlp_desc& d) { return packed_chunk_bytes(d) + (d.view_width > 0 ? kMergedWeightBytes : 0); }
 
 // ------------------------------------------------------------------------------------------------
 // weight packing: fp32 torch.nn.Linear weights -> bf16 swizzled [N x 64] chunks
@@ -59,8 +61,38 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ Pa
     }
 }
 
+// W_vf[o][k] = sum_j W_view[o][j] W_feat[j][k]   (fp32; 128 x 256 x 256): block = 8 output rows x 256 columns
+// and the feature bias seen through the view layer, bvf[o] = sum_j W_view[o][j] b_feat[j], stored behind W_vf
+__global__ void __launch_bounds__(256) tc_merge_view_feature_kernel(const float* __restrict__ w_view, int view_in,
+                                                                    const float* __restrict__ w_feat, const float* __restrict__ b_feat,
+                                                                    float* __restrict__ wvf) {
+    __shared__ float a[8][256];
+    const int o0 = blockIdx.x * 8, k = threadIdx.x;
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) a[i >> 8][i & 255] = w_view[(size_t)(o0 + (i >> 8)) * view_in + (i & 255)];
+    __syncthreads();
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < 256; ++j) {
+        const float w = w_feat[(size_t)j * 256 + k];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = fmaf(a[r][j], w, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) wvf[(size_t)(o0 + r) * 256 + k] = acc[r];
+    if (threadIdx.x < 8) {
+        float b = 0.f;
+        for (int j = 0; j < 256; ++j) b = fmaf(a[threadIdx.x][j], b_feat[j], b);
+        wvf[128 * 256 + o0 + threadIdx.x] = b;
+    }
+}
+
 int tc_pack(const snerf_mlp_desc& d, const float* const* prm, void* packed, cudaStream_t st) {
-    const TcPlan pl = build_plan(d, prm);
+    float* wvf = nullptr;
+    if (d.view_width > 0) {
+        wvf = (float*)((uint8_t*)packed + packed_chunk_bytes(d));
+        tc_merge_view_feature_kernel<<<128 / 8, 256, 0, st>>>(prm[SNERF_P_VIEW_W], MlpDims(d).view_in, prm[SNERF_P_FEAT_W], prm[SNERF_P_FEAT_B], wvf);
+        SNERF_LAUNCH_OK("tc_merge_view_feature_kernel");
+    }
+    const TcPlan pl = build_plan(d, prm, wvf);
     PackParams pp;
     pp.n = pl.n_pack;
     for (int i = 0; i < pl.n_pack; ++i) pp.c[i] = pl.pack[i];
@@ -70,11 +102,13 @@ int tc_pack(const snerf_mlp_desc& d, const float* const* prm, void* packed, cuda
 }
 
 // per-ray part of the view layer: vb[ray][o] = b_view[o] + sum_c W_view[o][col0 + c] * PE(view_dir)[c]   (:640, :695)
+//                                              + sum_j W_view[o][j] b_feat[j]   (the feature bias seen through the merged matrix)
 // One block per kRaysPerBlock rays: the encodings are computed element-parallel (accurate sin/cos: fp32 consumers), then
 // thread o keeps its weight row in registers and forms the output of every ray of the block.
 constexpr int kVbRays = 16;
 __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restrict__ view_dirs, const float* __restrict__ w_view,
-                                                           const float* __restrict__ b_view, float* __restrict__ vb, int n_rays,
+                                                           const float* __restrict__ b_view, const float* __restrict__ b_merged,
+                                                           float* __restrict__ vb, int n_rays,
                                                            int view_degree, int view_in, int col0, int venc) {
     const int ray0 = blockIdx.x * kVbRays;
     __shared__ float ve[kVbRays][32];
@@ -97,7 +131,7 @@ __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restri
     float w[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) w[c] = c < venc ? w_view[(size_t)o * view_in + col0 + c] : 0.f;
-    const float bias = b_view[o];
+    const float bias = b_view[o] + b_merged[o];
     for (int r = 0; r < kVbRays && ray0 + r < n_rays; ++r) {
         float acc = bias;
 #pragma unroll
@@ -709,14 +743,15 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     SNERF_REQUIRE(((uintptr_t)packed & 15) == 0 && ((uintptr_t)ws & 15) == 0, "mlp_forward: packed/workspace must be 16-byte aligned");
     uint8_t* wsb = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     if (m.has_view) {
-        tc_view_bias_kernel<<<(n_rays + kVbRays - 1) / kVbRays, 128, 0, st>>>(view_dirs, prm[SNERF_P_VIEW_W], prm[SNERF_P_VIEW_B], (float*)(wsb + w.view_bias),
-                                                    n_rays, d.view_degree, m.view_in, m.width + m.enc_hi, m.venc);
+        tc_view_bias_kernel<<<(n_rays + kVbRays - 1) / kVbRays, 128, 0, st>>>(view_dirs, prm[SNERF_P_VIEW_W], prm[SNERF_P_VIEW_B],
+                                                    (const float*)((const uint8_t*)packed + align_up(pl.packed_bytes, 1024)) + 128 * 256,
+                                                    (float*)(wsb + w.view_bias), n_rays, d.view_degree, m.view_in, m.width + m.enc_hi, m.venc);
         SNERF_LAUNCH_OK("tc_view_bias_kernel");
     }
     FwdParams p{};
     p.packed = (const uint8_t*)packed;
     for (int l = 0; l < 8; ++l) p.bias[l] = prm[2 * l + 1];
-    p.bias[8] = m.has_view ? prm[SNERF_P_FEAT_B] : nullptr;
+    p.bias[8] = nullptr;          // (the feature bias reaches the view layer through the per-ray bias table)
     p.w_head = prm[SNERF_P_HEAD_W]; p.b_head = prm[SNERF_P_HEAD_B];
     p.w_rgb = m.has_view ? prm[SNERF_P_RGB_W] : nullptr; p.b_rgb = m.has_view ? prm[SNERF_P_RGB_B] : nullptr;
     p.view_bias = (const float*)(wsb + w.view_bias);

@@ -6,8 +6,8 @@
 //  dgrad kernel  -- the CTA-pair machine of the forward kernel run backwards (two 256-point super tiles in flight):
 //      prologue warps : d rgb_pre = d rgb * rgb (1-rgb), d sigma_pre = d sigma * [sigma>0],
 //                       dY_v = (d rgb_pre W_rgb) * [hv>0]            (CUDA cores, fp32)
-//      MMA chain      : d feature = dY_v W_view[:, :256];  d h8 = d feature W_feat + d head_pre W_head;
-//                       d h_l = dY_l W_l[:, hidden]  for l = 7..1    (tcgen05 cta_group::2, B = packed W^T chunks)
+//      MMA chain      : d h8 = dY_v W_vf + d head_pre W_head   (W_vf = W_view[:, :256] W_feat, the merged view branch of
+//                       tc_plan.cuh);  d h_l = dY_l W_l[:, hidden]  for l = 7..1    (tcgen05 cta_group::2, B = packed W^T chunks)
 //      epilogue warps : ReLU mask from the sign bits the forward epilogue filed, bf16, back to smem as the next A operand
 //      stash writer   : every dY panel -> HBM (raw panel image) for the wgrad kernel
 //  wgrad kernel  -- per parameter matrix dW = dY^T X over all points: both operands are read MN-major from the
@@ -290,7 +290,7 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
                 hp[x] = p.has_view ? make_uint4(pack_bf16(ds, 0.f), 0u, 0u, 0u) : make_uint4(pack_bf16(ds, gr[0]), pack_bf16(gr[1], gr[2]), 0u, 0u);
                 if (p.has_view) {
                     uint4 mk[16];
-                    const uint8_t* hv = p.act + (size_t)tile * p.tile_stash_bytes + (size_t)9 * 65536;
+                    const uint8_t* hv = p.act + (size_t)tile * p.tile_stash_bytes + (size_t)kSlotHv * 65536;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         mk[i] = tile < p.n_tiles ? __ldg(reinterpret_cast<const uint4*>(hv + (i >> 3) * kPanelBytes + swz_offset(row, i & 7)))
@@ -397,7 +397,7 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
                 if (pv) {
                     for (int x = 0; x < 2; ++x) {
                         mbar_wait(&bars->pro_local[x], g & 1);
-                        event(x, tile_of(2 * g + x), 9, 2 * kPanelBytes, false);
+                        event(x, tile_of(2 * g + x), kDySlotView, 2 * kPanelBytes, false);
                     }
                 }
                 for (int s = 0; s < p.n_steps; ++s)
@@ -833,6 +833,85 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_backward_kernel(const __gri
     }
 }
 
+// =================================================================================================
+// gradients of the two matrices behind the merged view branch (tc_plan.cuh)
+// =================================================================================================
+// With G = dY_v^T h8 [128 x 256] and s = column sums of dY_v [128] (left in the workspace by the view layer's job):
+//   dW_view[:, :256] += G W_feat^T + s b_feat^T      dW_view[:, 256:] += the job's encoding columns      db_view += s
+//   dW_feat          += W_view[:, :256]^T G          db_feat += W_view[:, :256]^T s
+// fp32 on the CUDA cores, 17 MFLOP per call: blocks 0..31 the first product (32 x 32 output tiles), 32..95 the second,
+// 96.. the copies and the two vectors.
+constexpr int kUnmergeBlocks = 32 + 64 + 5;
+__global__ void __launch_bounds__(256) tc_unmerge_grads_kernel(const float* __restrict__ merged, const float* __restrict__ w_view,
+                                                               const float* __restrict__ w_feat, const float* __restrict__ b_feat,
+                                                               float* __restrict__ dw_view, float* __restrict__ db_view,
+                                                               float* __restrict__ dw_feat, float* __restrict__ db_feat, int view_in) {
+    __shared__ float sa[32][33], sb[32][33];
+    const float* s_vec = merged + 128 * view_in;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // thread: column tx, rows ty + 8 i
+    int b = blockIdx.x;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (b < 32) {
+        const int o0 = (b >> 3) * 32, k0 = (b & 7) * 32;         // out[o][k] = sum_j G[o][j] W_feat[k][j]
+        for (int j0 = 0; j0 < 256; j0 += 32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sa[ty + 8 * i][tx] = merged[(size_t)(o0 + ty + 8 * i) * view_in + j0 + tx];
+                sb[ty + 8 * i][tx] = w_feat[(size_t)(k0 + ty + 8 * i) * 256 + j0 + tx];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float w = sb[tx][c];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(sa[ty + 8 * i][c], w, acc[i]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int o = o0 + ty + 8 * i, k = k0 + tx;
+            dw_view[(size_t)o * view_in + k] += acc[i] + s_vec[o] * b_feat[k];
+        }
+        return;
+    }
+    b -= 32;
+    if (b < 64) {
+        const int k0 = (b >> 3) * 32, j0 = (b & 7) * 32;         // out[k][j] = sum_o W_view[o][k] G[o][j]
+        for (int o0 = 0; o0 < 128; o0 += 32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sa[ty + 8 * i][tx] = w_view[(size_t)(o0 + ty + 8 * i) * view_in + k0 + tx];     // [o][k]
+                sb[ty + 8 * i][tx] = merged[(size_t)(o0 + ty + 8 * i) * view_in + j0 + tx];     // [o][j]
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float g = sb[c][tx];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(sa[c][ty + 8 * i], g, acc[i]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dw_feat[(size_t)(k0 + ty + 8 * i) * 256 + j0 + tx] += acc[i];
+        return;
+    }
+    b -= 64;
+    if (b < 4) {                                                 // the encoding columns of dW_view, rows 32 b .. 32 b + 31
+        const int extra = view_in - 256;
+        for (int i = threadIdx.x; i < 32 * extra; i += 256) {
+            const int o = 32 * b + i / extra, k = 256 + i % extra;
+            dw_view[(size_t)o * view_in + k] += merged[(size_t)o * view_in + k];
+        }
+        return;
+    }
+    if (threadIdx.x < 128) db_view[threadIdx.x] += s_vec[threadIdx.x];
+    float a = 0.f;                                               // db_feat[k] = sum_o W_view[o][k] s[o]
+    for (int o = 0; o < 128; ++o) a = fmaf(w_view[(size_t)o * view_in + threadIdx.x], s_vec[o], a);
+    db_feat[threadIdx.x] += a;
+}
+
 static long long* g_wg_trace = nullptr;
 static cudaEvent_t g_split_event = nullptr;   // measurement: recorded between the dgrad and the wgrad launch (bench.py)
 static int g_wg_debug = 0;   // set by snerfdbg_set_wgrad_trace (debug only)
@@ -926,13 +1005,12 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
             wp.jobs[nj++] = e;
         }
     }
+    float* merged = (float*)(wsb + w.merged_grad);       // [128 x view_in] then [128]
     if (m.has_view) {
-        WgJob f = mma_job(8, 4, 7, 4, false, false, grads[SNERF_P_FEAT_W], m.width, grads[SNERF_P_FEAT_B]);   // dW_feat = dY_f^T h8
-        f.n_segs = 1; f.seg[0] = seg(0, 256, 0, 256, 0);
-        wp.jobs[nj++] = f;
-        // dW_view = dY_v^T [feature | E(bands >= trunk_degree) | PE(view dir)]
+        // G = dY_v^T [h8 | E(bands >= trunk_degree) | PE(view dir)] and the column sums of dY_v go to the workspace; the
+        // gradients of W_view, b_view, W_feat, b_feat follow from them (tc_unmerge_grads_kernel below)
         const bool hi = m.enc_hi > 0;
-        WgJob v = mma_job(9, 2, 8, 4, hi, true, grads[SNERF_P_VIEW_W], m.view_in, grads[SNERF_P_VIEW_B]);
+        WgJob v = mma_job(kDySlotView, 2, 7, 4, hi, true, merged, m.view_in, merged + 128 * m.view_in);
         v.seg[0] = seg(0, 256, 0, 256, 0);
         if (hi) {
             v.n_segs = 3;
@@ -944,15 +1022,15 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         }
         wp.jobs[nj++] = v;
         WgJob r{};                                      // dW_rgb = d rgb_pre^T hv
-        r.kind = 2; r.b_slot = 9; r.b_panels = 2; r.dw = grads[SNERF_P_RGB_W]; r.ld = m.view_width; r.db = grads[SNERF_P_RGB_B];
+        r.kind = 2; r.b_slot = kSlotHv; r.b_panels = 2; r.dw = grads[SNERF_P_RGB_W]; r.ld = m.view_width; r.db = grads[SNERF_P_RGB_B];
         wp.jobs[nj++] = r;
     }
     wp.trace = g_wg_trace; wp.debug = g_wg_debug;
     wp.head_dw = grads[SNERF_P_HEAD_W]; wp.head_db = grads[SNERF_P_HEAD_B]; wp.head_ld = m.width;
     if (m.has_view) {
-        // dW_head = d head_pre^T h8 rides on the feature job, whose streamed B operand is the same h8
+        // dW_head = d head_pre^T h8 rides on the view job, whose streamed B operand is the same h8
         for (int j = 0; j < nj; ++j)
-            if (wp.jobs[j].kind == 0 && wp.jobs[j].a_slot == 8) wp.jobs[j].with_head = 1;
+            if (wp.jobs[j].kind == 0 && wp.jobs[j].a_slot == kDySlotView) wp.jobs[j].with_head = 1;
     } else {
         WgJob h{};
         h.kind = 1; h.b_slot = 7; h.b_panels = 4; h.dw = grads[SNERF_P_HEAD_W]; h.ld = m.width; h.db = grads[SNERF_P_HEAD_B];
@@ -1003,6 +1081,15 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         int c0 = 0;
         for (int j = 0; j < nj; ++j) { wp.jobs[j].cta0 = (int16_t)c0; wp.jobs[j].n_cta = (int16_t)n[j]; c0 += n[j]; }
     }
+    auto unmerge = [&]() -> int {
+        if (!m.has_view) return SNERF_OK;
+        tc_unmerge_grads_kernel<<<kUnmergeBlocks, 256, 0, st>>>(merged, prm[SNERF_P_VIEW_W], prm[SNERF_P_FEAT_W], prm[SNERF_P_FEAT_B],
+                                                               grads[SNERF_P_VIEW_W], grads[SNERF_P_VIEW_B], grads[SNERF_P_FEAT_W],
+                                                               grads[SNERF_P_FEAT_B], m.view_in);
+        SNERF_LAUNCH_OK("tc_unmerge_grads_kernel");
+        return SNERF_OK;
+    };
+    if (m.has_view) SNERF_CUDA_OK(cudaMemsetAsync(merged, 0, (size_t)(128 * m.view_in + 128) * sizeof(float), st));
     if (fused) {
         if (wp.debug & 24) { bp.ring.use_flags = 0; wp.ring.use_flags = 0; }     // one role alone: no hand-off (results are garbage)
         SNERF_CUDA_OK(cudaMemsetAsync(ring.ready, 0, (size_t)(1 + kRingConsumers) * kDySlots * ring.cap * sizeof(uint32_t), st));
@@ -1017,13 +1104,13 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         cfg.attrs = at;
         cfg.numAttrs = 1;
         SNERF_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_backward_kernel, bp, wp));
-        return SNERF_OK;
+        return unmerge();
     }
     SNERF_CUDA_OK(launch_clustered(tc_dgrad_kernel, 2 * n_pairs, kBwdThreads, kBwdSmem, st, bp));
     if (g_split_event) cudaEventRecord(g_split_event, st);
     tc_wgrad_kernel<<<num_sms(), kWgThreads, kWgSmem, st>>>(wp);
     SNERF_LAUNCH_OK("tc_wgrad_kernel");
-    return SNERF_OK;
+    return unmerge();
 }
 
 }  // namespace snerf

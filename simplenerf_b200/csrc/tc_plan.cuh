@@ -65,8 +65,18 @@ static inline void add_chunk(TcPlan& pl, TcStep& st, int panel, int ksteps, cons
     pl.packed_bytes += (uint32_t)n_rows * kRowBytes;
 }
 
-// prm may be null (layout only)
-static inline TcPlan build_plan(const snerf_mlp_desc& d, const float* const* prm) {
+// Merged view branch.  feature_linear has no activation (src/models/SimpleNeRF01.py:691-697), so the view layer's feature
+// part is one linear map of the last trunk activation:  W_view[:, :256] (W_feat h + b_feat) = W_vf h + W_view[:, :256] b_feat
+// with W_vf = W_view[:, :256] W_feat  [128 x 256].  The tensor path multiplies by W_vf directly (formed in fp32 at pack
+// time, rounded to bf16 once): the feature step, its dgrad step, its activation / gradient panels (1 KB of the 10.2 KB a
+// point moved through HBM) and its weight-gradient job are gone.  The gradients of the two original matrices follow from
+// G = dY_v^T h (accumulated by the view layer's weight-gradient job) by two small fp32 products (tc_unmerge_grads_kernel).
+constexpr int kSlotHv = 8;                                   // activation-stash slot of the view layer's output
+constexpr int kDySlotView = 9;                               // gradient-ring slot of dY_v (2 panels)
+constexpr size_t kMergedWeightBytes = (128 * 256 + 128) * sizeof(float);   // W_vf and W_view[:, :256] b_feat, fp32, appended to the packed image
+
+// prm may be null (layout only); wvf = the fp32 W_vf appended to the packed image (null: layout only)
+static inline TcPlan build_plan(const snerf_mlp_desc& d, const float* const* prm, const float* wvf = nullptr) {
     const MlpDims m(d);
     TcPlan pl{};
     auto P = [&](int i) -> const float* { return prm ? prm[i] : nullptr; };
@@ -92,32 +102,24 @@ static inline TcPlan build_plan(const snerf_mlp_desc& d, const float* const* prm
     pl.fwd[m.depth - 1].kind = m.has_view ? EPI_RELU_HEAD1 : EPI_RELU_HEAD4;
     pl.fwd[m.skip_layer + 1].last_e_use = 1;
     if (m.has_view) {
-        TcStep& ft = pl.fwd[pl.n_fwd++];
-        ft.n_rows = 256; ft.kind = EPI_LINEAR; ft.bias_row = 8; ft.slot = 8;
-        for (int j = 0; j < 4; ++j) add_chunk(pl, ft, j, 4, P(SNERF_P_FEAT_W), m.width, 256, 0, 64, 64 * j, 0, false);
-        TcStep& vw = pl.fwd[pl.n_fwd++];
-        vw.n_rows = 128; vw.kind = EPI_VIEW; vw.slot = 9;
-        for (int j = 0; j < 4; ++j) add_chunk(pl, vw, j, 4, P(SNERF_P_VIEW_W), m.view_in, 128, 0, 64, 64 * j, 0, false);
+        TcStep& vw = pl.fwd[pl.n_fwd++];       // hv_pre = W_vf h + [per-ray bias] (+ W_view[:, enc part] E)
+        vw.n_rows = 128; vw.kind = EPI_VIEW; vw.slot = kSlotHv;
+        for (int j = 0; j < 4; ++j) add_chunk(pl, vw, j, 4, wvf, m.width, 128, 0, 64, 64 * j, 0, false);
         if (m.enc_hi > 0) {   // points-augmentation: encoding bands trunk_degree.. feed the view layer (:633)
             add_chunk(pl, vw, kPanelE, 4, P(SNERF_P_VIEW_W), m.view_in, 128, m.trunk_in, m.enc, m.width, 0, false);
             pl.fwd[m.skip_layer + 1].last_e_use = 0;
             vw.last_e_use = 1;
         }
     }
-    pl.tile_stash_bytes = (uint32_t)(m.has_view ? 9 * 65536 + 32768 : 8 * 65536);
+    pl.tile_stash_bytes = (uint32_t)(m.has_view ? 8 * 65536 + 32768 : 8 * 65536);
 
     // ---- backward (dgrad) steps: B operand = W^T chunks [256 in-features x 64 out-features] ----
-    // dY_l = gradient w.r.t. the pre-activation of trunk layer l; stash slot l.  Slot 8 = d feature, 9 = d hv.
-    if (m.has_view) {
-        TcStep& vg = pl.bwd[pl.n_bwd++];    // d feature = dY_v W_view[:, :256]   (feature has no activation)
-        vg.n_rows = 256; vg.kind = BWD_LINEAR; vg.slot = 8;
-        for (int c = 0; c < 2; ++c) add_chunk(pl, vg, kPanelP + c, 4, P(SNERF_P_VIEW_W), m.view_in, 256, 0, 64, 0, 64 * c, true);
-    }
+    // dY_l = gradient w.r.t. the pre-activation of trunk layer l; gradient slot l.  Slot 9 = d hv_pre (slot 8 is unused).
     {
-        TcStep& fg = pl.bwd[pl.n_bwd++];    // d h8 = d feature W_feat + d head_pre W_head, masked by h8 > 0
+        TcStep& fg = pl.bwd[pl.n_bwd++];    // d h8 = dY_v W_vf + d head_pre W_head, masked by h8 > 0
         fg.n_rows = 256; fg.kind = BWD_MASK; fg.mask_slot = 7; fg.slot = 7; fg.last_e_use = 1;
         if (m.has_view)
-            for (int c = 0; c < 4; ++c) add_chunk(pl, fg, c, 4, P(SNERF_P_FEAT_W), m.width, 256, 0, 64, 0, 64 * c, true);
+            for (int c = 0; c < 2; ++c) add_chunk(pl, fg, kPanelP + c, 4, wvf, m.width, 256, 0, 64, 0, 64 * c, true);
         add_chunk(pl, fg, kPanelP + 2, 1, P(SNERF_P_HEAD_W), m.width, 256, 0, m.head_out, 0, 0, true);
     }
     for (int l = m.depth - 1; l >= 1; --l) {   // d h_l = dY_l W_l[:, hidden part], masked by h_l > 0
@@ -190,7 +192,7 @@ constexpr uint32_t kBitsSlotBytes = 4096;                 // sign bits of one 12
 constexpr uint32_t kBitsTileBytes = 8 * kBitsSlotBytes;   // trunk layers 0..7
 
 struct TcWorkspace {
-    size_t view_bias, act, dy, bits, flags, total;
+    size_t view_bias, act, dy, bits, flags, merged_grad, total;
     int n_tiles;
     uint32_t ring_cap;
 };
@@ -287,6 +289,8 @@ static inline TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n
         off += (size_t)w.n_tiles * kBitsTileBytes;
         w.flags = off;
         off += align_up((size_t)(1 + kRingConsumers) * kDySlots * w.ring_cap * sizeof(uint32_t), 1024);
+        w.merged_grad = off;          // fp32 [128 x view_in] + [128]: dY_v^T [h | encodings] and the column sums of dY_v
+        off += align_up(m.has_view ? (size_t)(128 * m.view_in + 128) * sizeof(float) : 0, 1024);
     }
     w.total = off + 1024;
     return w;
