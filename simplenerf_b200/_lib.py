@@ -95,6 +95,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is None:
         path = LIB_DBG_PATH if os.environ.get('SNERF_B200_DEBUG_LIB') == '1' else LIB_PATH
+        path = os.environ.get('SNERF_B200_LIB_AB', path)     # developer A/B runs (tools/ab.sh): another build of the same sources
         if not os.path.exists(path):
             raise RuntimeError(f'{path} is missing: build it with `python -m simplenerf_b200.build` '
                                '(there is no CPU or PyTorch fallback for this path)')

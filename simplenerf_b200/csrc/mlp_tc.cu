@@ -61,35 +61,48 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ Pa
     }
 }
 
-// W_vf[o][k] = sum_j W_view[o][j] W_feat[j][k]   (fp32; 128 x 256 x 256): block = 8 output rows x 256 columns
-// and the feature bias seen through the view layer, bvf[o] = sum_j W_view[o][j] b_feat[j], stored behind W_vf
+// W_vf[o][k] = sum_j W_view[o][j] W_feat[j][k]   (fp32; 128 x 256 x 256): blocks 0..63 form 16 x 32 output tiles,
+// block 64 the feature bias seen through the view layer, bvf[o] = sum_j W_view[o][j] b_feat[j], stored behind W_vf
 __global__ void __launch_bounds__(256) tc_merge_view_feature_kernel(const float* __restrict__ w_view, int view_in,
                                                                     const float* __restrict__ w_feat, const float* __restrict__ b_feat,
                                                                     float* __restrict__ wvf) {
-    __shared__ float a[8][256];
-    const int o0 = blockIdx.x * 8, k = threadIdx.x;
-    for (int i = threadIdx.x; i < 8 * 256; i += 256) a[i >> 8][i & 255] = w_view[(size_t)(o0 + (i >> 8)) * view_in + (i & 255)];
-    __syncthreads();
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < 256; ++j) {
-        const float w = w_feat[(size_t)j * 256 + k];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (blockIdx.x == 64) {                                       // warp ty takes rows ty, ty + 8, ...
+        for (int o = ty; o < 128; o += 8) {
+            float a = 0.f;
+            for (int j = tx; j < 256; j += 32) a = fmaf(w_view[(size_t)o * view_in + j], b_feat[j], a);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = fmaf(a[r][j], w, acc[r]);
+            for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+            if (tx == 0) wvf[128 * 256 + o] = a;
+        }
+        return;
     }
+    __shared__ float sa[16][33], sb[32][33];
+    const int o0 = (blockIdx.x >> 3) * 16, k0 = (blockIdx.x & 7) * 32;
+    float acc[2] = {0.f, 0.f};
+    for (int j0 = 0; j0 < 256; j0 += 32) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) wvf[(size_t)(o0 + r) * 256 + k] = acc[r];
-    if (threadIdx.x < 8) {
-        float b = 0.f;
-        for (int j = 0; j < 256; ++j) b = fmaf(a[threadIdx.x][j], b_feat[j], b);
-        wvf[128 * 256 + o0 + threadIdx.x] = b;
+        for (int i = 0; i < 2; ++i) sa[ty + 8 * i][tx] = w_view[(size_t)(o0 + ty + 8 * i) * view_in + j0 + tx];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sb[ty + 8 * i][tx] = w_feat[(size_t)(j0 + ty + 8 * i) * 256 + k0 + tx];
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float w = sb[c][tx];
+            acc[0] = fmaf(sa[ty][c], w, acc[0]);
+            acc[1] = fmaf(sa[ty + 8][c], w, acc[1]);
+        }
+        __syncthreads();
     }
+    wvf[(size_t)(o0 + ty) * 256 + k0 + tx] = acc[0];
+    wvf[(size_t)(o0 + ty + 8) * 256 + k0 + tx] = acc[1];
 }
 
 int tc_pack(const snerf_mlp_desc& d, const float* const* prm, void* packed, cudaStream_t st) {
     float* wvf = nullptr;
     if (d.view_width > 0) {
         wvf = (float*)((uint8_t*)packed + packed_chunk_bytes(d));
-        tc_merge_view_feature_kernel<<<128 / 8, 256, 0, st>>>(prm[SNERF_P_VIEW_W], MlpDims(d).view_in, prm[SNERF_P_FEAT_W], prm[SNERF_P_FEAT_B], wvf);
+        tc_merge_view_feature_kernel<<<65, 256, 0, st>>>(prm[SNERF_P_VIEW_W], MlpDims(d).view_in, prm[SNERF_P_FEAT_W], prm[SNERF_P_FEAT_B], wvf);
         SNERF_LAUNCH_OK("tc_merge_view_feature_kernel");
     }
     const TcPlan pl = build_plan(d, prm, wvf);
@@ -391,9 +404,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + j * 64;
         const uint32_t ready0 = cluster_addr(&bars->tile_ready[0], 0), ready1 = cluster_addr(&bars->tile_ready[1], 0);
-        uint32_t soff[8];      // byte offset of this row's 16-byte chunk c inside a panel
-#pragma unroll
-        for (int c = 0; c < 8; ++c) soff[c] = (uint32_t)row * kRowBytes + (((uint32_t)c ^ ((uint32_t)row & 7u)) << 4);
+        // chunk c of this thread's panel row lives at (panel + row_base) ^ (c << 4)  (128-byte swizzle)
+        const uint32_t row_base = smem_u32(smem + kOffH) + (uint32_t)row * kRowBytes + (((uint32_t)row & 7u) << 4);
         auto job = [&](const int x, const int g, const int s) {
             const TcStep& st = p.steps[s];
             const int kind = st.kind;
@@ -405,7 +417,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
             const bool own = j * 64 < st.n_rows && !(p.debug & 2);        // the step has this panel
             const bool writes_h = ((kind != EPI_VIEW) || save) && !(p.debug & 1);
             const uint32_t acc_addr = lane_addr + x * 256;
-            uint8_t* dst = smem + kOffH + x * 65536 + j * kPanelBytes;
+            const uint32_t dst_row = row_base + x * 65536 + j * kPanelBytes;
             if (kind == EPI_RELU || kind == EPI_LINEAR) {
                 // ---- hidden layers and the feature layer: bias (+ReLU) in packed bf16 ----
                 if (own) {
@@ -429,8 +441,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                             pk[4 * i + 3] = bias_act_bf16x2(__uint_as_float(rr[u & 1][8 * i + 6]), __uint_as_float(rr[u & 1][8 * i + 7]), b.w, relu);
                         }
                         if (writes_h) {
-                            *reinterpret_cast<uint4*>(dst + soff[2 * u]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            *reinterpret_cast<uint4*>(dst + soff[2 * u + 1]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            sts128(dst_row ^ ((2 * u) << 4), pk[0], pk[1], pk[2], pk[3]);
+                            sts128(dst_row ^ ((2 * u + 1) << 4), pk[4], pk[5], pk[6], pk[7]);
                         }
                         if (save && relu) mw[u >> 1] |= relu_bits_unit(pk, u);
                         if (tr) p.trace[512 + (x * 16 + s) * 8 + 1 + u] = clock64();
@@ -579,8 +591,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                         uint32_t pk[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-                        *reinterpret_cast<uint4*>(dst + soff[2 * u]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4*>(dst + soff[2 * u + 1]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        sts128(dst_row ^ ((2 * u) << 4), pk[0], pk[1], pk[2], pk[3]);
+                        sts128(dst_row ^ ((2 * u + 1) << 4), pk[4], pk[5], pk[6], pk[7]);
                         if (save && kind != EPI_VIEW) mw[u >> 1] |= relu_bits_unit(pk, u);
                     }
                 }

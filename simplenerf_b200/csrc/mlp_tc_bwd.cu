@@ -214,9 +214,8 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + j * 64;
         const uint32_t ready0 = cluster_addr(&bars->tile_ready[0], 0), ready1 = cluster_addr(&bars->tile_ready[1], 0);
-        uint32_t soff[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) soff[c] = (uint32_t)row * kRowBytes + (((uint32_t)c ^ ((uint32_t)row & 7u)) << 4);
+        // chunk c of this thread's panel row lives at (panel + row_base) ^ (c << 4)  (128-byte swizzle)
+        const uint32_t row_base = smem_u32(smem + kBOffH) + (uint32_t)row * kRowBytes + (((uint32_t)row & 7u) << 4);
         auto job = [&](const int x, const int g, const int s) {
             const TcStep& st = p.steps[s];
             const uint32_t jx = (uint32_t)(g * p.n_steps + s);
@@ -231,7 +230,7 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
             mbar_wait(&bars->acc_full[x], jx & 1);
             tc_fence_after();
             const uint32_t acc_addr = lane_addr + x * 256;
-            uint8_t* dst = smem + kBOffH + x * 65536 + j * kPanelBytes;
+            const uint32_t dst_row = row_base + x * 65536 + j * kPanelBytes;
             uint32_t rr[2][16];
             tmem_ld16_issue(acc_addr, rr[0]);
             if (ev > 0) mbar_wait(&bars->stash_done[x], (ev - 1) & 1);     // the slot's panels have been copied out
@@ -243,8 +242,8 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
 #pragma unroll
                 for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(rr[u & 1][2 * i]), __uint_as_float(rr[u & 1][2 * i + 1]));
                 if (mask) relu_mask_unit((u >> 1) ? mw.y : mw.x, u, pk);
-                *reinterpret_cast<uint4*>(dst + soff[2 * u]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(dst + soff[2 * u + 1]) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                sts128(dst_row ^ ((2 * u) << 4), pk[0], pk[1], pk[2], pk[3]);
+                sts128(dst_row ^ ((2 * u + 1) << 4), pk[4], pk[5], pk[6], pk[7]);
             }
             fence_async_smem();
             tc_fence_before();
@@ -839,65 +838,64 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_backward_kernel(const __gri
 // With G = dY_v^T h8 [128 x 256] and s = column sums of dY_v [128] (left in the workspace by the view layer's job):
 //   dW_view[:, :256] += G W_feat^T + s b_feat^T      dW_view[:, 256:] += the job's encoding columns      db_view += s
 //   dW_feat          += W_view[:, :256]^T G          db_feat += W_view[:, :256]^T s
-// fp32 on the CUDA cores, 17 MFLOP per call: blocks 0..31 the first product (32 x 32 output tiles), 32..95 the second,
-// 96.. the copies and the two vectors.
-constexpr int kUnmergeBlocks = 32 + 64 + 5;
+// fp32 on the CUDA cores, 17 MFLOP per call: blocks 0..63 the first product (16 x 32 output tiles), 64..191 the second,
+// 192.. the copies and the two vectors.
+constexpr int kUnmergeBlocks = 64 + 128 + 5;
 __global__ void __launch_bounds__(256) tc_unmerge_grads_kernel(const float* __restrict__ merged, const float* __restrict__ w_view,
                                                                const float* __restrict__ w_feat, const float* __restrict__ b_feat,
                                                                float* __restrict__ dw_view, float* __restrict__ db_view,
                                                                float* __restrict__ dw_feat, float* __restrict__ db_feat, int view_in) {
     __shared__ float sa[32][33], sb[32][33];
     const float* s_vec = merged + 128 * view_in;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // thread: column tx, rows ty + 8 i
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // thread: column tx, rows ty and ty + 8
     int b = blockIdx.x;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (b < 32) {
-        const int o0 = (b >> 3) * 32, k0 = (b & 7) * 32;         // out[o][k] = sum_j G[o][j] W_feat[k][j]
+    float acc[2] = {0.f, 0.f};
+    if (b < 64) {
+        const int o0 = (b >> 3) * 16, k0 = (b & 7) * 32;         // out[o][k] = sum_j G[o][j] W_feat[k][j]
         for (int j0 = 0; j0 < 256; j0 += 32) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                sa[ty + 8 * i][tx] = merged[(size_t)(o0 + ty + 8 * i) * view_in + j0 + tx];
-                sb[ty + 8 * i][tx] = w_feat[(size_t)(k0 + ty + 8 * i) * 256 + j0 + tx];
-            }
+            for (int i = 0; i < 2; ++i) sa[ty + 8 * i][tx] = merged[(size_t)(o0 + ty + 8 * i) * view_in + j0 + tx];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sb[ty + 8 * i][tx] = w_feat[(size_t)(k0 + ty + 8 * i) * 256 + j0 + tx];
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
                 const float w = sb[tx][c];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = fmaf(sa[ty + 8 * i][c], w, acc[i]);
+                acc[0] = fmaf(sa[ty][c], w, acc[0]);
+                acc[1] = fmaf(sa[ty + 8][c], w, acc[1]);
             }
             __syncthreads();
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
             const int o = o0 + ty + 8 * i, k = k0 + tx;
             dw_view[(size_t)o * view_in + k] += acc[i] + s_vec[o] * b_feat[k];
         }
         return;
     }
-    b -= 32;
-    if (b < 64) {
-        const int k0 = (b >> 3) * 32, j0 = (b & 7) * 32;         // out[k][j] = sum_o W_view[o][k] G[o][j]
+    b -= 64;
+    if (b < 128) {
+        const int k0 = (b >> 3) * 16, j0 = (b & 7) * 32;         // out[k][j] = sum_o W_view[o][k] G[o][j]
         for (int o0 = 0; o0 < 128; o0 += 32) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                sa[ty + 8 * i][tx] = w_view[(size_t)(o0 + ty + 8 * i) * view_in + k0 + tx];     // [o][k]
-                sb[ty + 8 * i][tx] = merged[(size_t)(o0 + ty + 8 * i) * view_in + j0 + tx];     // [o][j]
+                if (tx < 16) sa[ty + 8 * i][tx] = w_view[(size_t)(o0 + ty + 8 * i) * view_in + k0 + tx];      // [o][k]
+                sb[ty + 8 * i][tx] = merged[(size_t)(o0 + ty + 8 * i) * view_in + j0 + tx];                   // [o][j]
             }
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
                 const float g = sb[c][tx];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = fmaf(sa[c][ty + 8 * i], g, acc[i]);
+                acc[0] = fmaf(sa[c][ty], g, acc[0]);
+                acc[1] = fmaf(sa[c][ty + 8], g, acc[1]);
             }
             __syncthreads();
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dw_feat[(size_t)(k0 + ty + 8 * i) * 256 + j0 + tx] += acc[i];
+        for (int i = 0; i < 2; ++i) dw_feat[(size_t)(k0 + ty + 8 * i) * 256 + j0 + tx] += acc[i];
         return;
     }
-    b -= 64;
+    b -= 128;
     if (b < 4) {                                                 // the encoding columns of dW_view, rows 32 b .. 32 b + 31
         const int extra = view_in - 256;
         for (int i = threadIdx.x; i < 32 * extra; i += 256) {

@@ -27,6 +27,12 @@ __host__ __device__ __forceinline__ uint32_t swz_offset(uint32_t row, uint32_t c
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 16-byte store through a 32-bit shared-space address.  The epilogues address chunk c of their panel row as
+// (panel + row * 128 + ((row & 7) << 4)) ^ (c << 4): one LOP3 per store instead of the swizzle arithmetic per chunk.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

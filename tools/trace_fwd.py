@@ -53,4 +53,4 @@ for s_ in range(10):
         e = t[(x * 16 + s_) * 16: (x * 16 + s_) * 16 + 16]
         d = t[512 + (x * 16 + s_) * 8: 512 + (x * 16 + s_) * 8 + 8]
         r2 = lambda v: int(v - e[2]) if v else None
-        print(f'{x} {s_:2d} | 0 | {[r2(v) for v in d[1:5]]} | {r2(d[5])} | {r2(e[3])}')
+        print(f'{x} {s_:2d} | 0 | {[r2(v) for v in d[1:5]]} | {r2(d[5])} | {r2(e[3])} | unit 0: loaded {r2(d[6])} computed {r2(d[7])}')
