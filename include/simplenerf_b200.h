@@ -123,6 +123,24 @@ int snerf_mlp_forward(const snerf_mlp_desc* desc, const float* const* host_param
                       const float* sigma_noise, float* sigma, float* rgb, void* workspace, size_t workspace_bytes,
                       int n_rays, int n_samples, uint32_t flags, void* stream);
 
+/* ---- X1: evaluation with the samples kept on chip (run_network + volume_rendering in one pass, tensor path) ----------
+ * Replaces  raw = run_network(...); volume_rendering(raw, z_vals, ...)  (src/models/SimpleNeRF01.py:153-160, :219-224, :430-483)
+ * for calls that do not return the raw network outputs (retraw=False, :265-269): sigma / rgb of a sample live in registers
+ * from the head epilogue of the MLP kernel to the compositing arithmetic; what leaves the SM is one 48-byte record per
+ * 32 consecutive samples of a ray (transmittance product, weight / colour / depth sums and centred second moments of the
+ * segment), which a warp-per-ray pass folds into the per-ray maps.  Needs n_samples % 32 == 0 and an MLP with a view branch
+ * (SNERF_ERR_UNSUPPORTED otherwise: the caller keeps using snerf_mlp_forward + snerf_composite_forward).
+ * pts_o / pts_d: the rays the points are generated from (NDC rays with SNERF_FLAG_NDC, :142); rays_o / rays_d: the camera rays
+ * (only their z components are read, for the NDC depth conversion :495-501; may equal pts_* otherwise).
+ * Outputs: rgb_map [n,3], acc, depth, depth_var [n], depth_ndc, depth_var_ndc [n] (NDC only), alpha [n,S] (nullable; :446, a
+ * key of the reference's output dict), weights [n,S] (nullable; the coarse pass hands them to snerf_sample_fine).           */
+size_t snerf_render_workspace_bytes(const snerf_mlp_desc* desc, int n_rays, int n_samples, uint32_t flags);
+int snerf_render_forward(const snerf_mlp_desc* desc, const float* const* host_params, const void* packed,
+                         const float* pts_o, const float* pts_d, const float* view_dirs, const float* z,
+                         const float* rays_o, const float* rays_d, float* rgb_map, float* acc, float* depth,
+                         float* depth_var, float* depth_ndc, float* depth_var_ndc, float* alpha, float* weights,
+                         void* workspace, size_t workspace_bytes, int n_rays, int n_samples, uint32_t flags, void* stream);
+
 /* ---- in-kernel random numbers (production draws in the kernels that consume them) ----------------
  * The reference draws t_rand (:299), u (:341) and the sigma noise (:670) on the CPU generator and copies them to the device.
  * The *_rng entry points draw them where they are consumed, from Philox4x32-10 keyed by `seed`, counter = (element / 4, `offset`):

@@ -55,6 +55,8 @@ _SIGNATURES = {
     'snerf_composite_forward': (C.c_int, [_fp] * 15 + [C.c_int, C.c_int, C.c_uint32, _fp]),
     'snerf_composite_backward': (C.c_int, [_fp] * 17 + [C.c_int, C.c_int, C.c_uint32, _fp]),
     'snerf_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(MlpDesc), C.c_int, C.c_int, C.c_uint32]),
+    'snerf_render_workspace_bytes': (C.c_size_t, [C.POINTER(MlpDesc), C.c_int, C.c_int, C.c_uint32]),
+    'snerf_render_forward': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp), _fp] + [_fp] * 14 + [_fp, C.c_size_t, C.c_int, C.c_int, C.c_uint32, _fp]),
     'snerf_packed_weights_bytes': (C.c_size_t, [C.POINTER(MlpDesc)]),
     'snerf_pack_weights': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp), _fp, _fp]),
     'snerf_mlp_forward': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(_fp), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,

@@ -141,6 +141,38 @@ extern "C" int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const
                        workspace, workspace_bytes, n_rays, n_samples, flags, (cudaStream_t)stream);
 }
 
+extern "C" size_t snerf_render_workspace_bytes(const snerf_mlp_desc* desc, int n_rays, int n_samples, uint32_t flags) {
+    if (validate_desc(desc) != SNERF_OK || n_rays < 0 || n_samples < 1 || (flags & SNERF_FLAG_PRECISE)) return 0;
+    return tc_render_workspace_bytes(MlpDims(*desc), *desc, n_rays, n_samples);
+}
+
+extern "C" int snerf_render_forward(const snerf_mlp_desc* desc, const float* const* host_params, const void* packed,
+                                    const float* pts_o, const float* pts_d, const float* view_dirs, const float* z,
+                                    const float* rays_o, const float* rays_d, float* rgb_map, float* acc, float* depth,
+                                    float* depth_var, float* depth_ndc, float* depth_var_ndc, float* alpha, float* weights,
+                                    void* workspace, size_t workspace_bytes, int n_rays, int n_samples, uint32_t flags, void* stream) {
+    int rc = validate_desc(desc);
+    if (rc != SNERF_OK) return rc;
+    rc = check_params(*desc, (const void* const*)host_params, "snerf_render_forward");
+    if (rc != SNERF_OK) return rc;
+    SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1, "snerf_render_forward: bad sizes");
+    if (n_rays == 0) return SNERF_OK;
+    if (flags & (SNERF_FLAG_PRECISE | SNERF_FLAG_SAVE_FOR_BWD))
+        return fail(SNERF_ERR_UNSUPPORTED, "snerf_render_forward: evaluation on the tensor path only (training keeps sigma / rgb for the backward pass)");
+    const bool ndc = (flags & SNERF_FLAG_NDC) != 0;
+    SNERF_REQUIRE(packed && pts_o && pts_d && z && workspace, "snerf_render_forward: null input");
+    SNERF_REQUIRE(desc->view_degree == 0 || view_dirs != nullptr, "snerf_render_forward: view_dirs required by this MLP");
+    SNERF_REQUIRE(rgb_map && acc && depth && depth_var, "snerf_render_forward: null per-ray output");
+    SNERF_REQUIRE(!ndc || (rays_o && rays_d && depth_ndc && depth_var_ndc), "snerf_render_forward: NDC mode needs rays_o, rays_d, depth_ndc, depth_var_ndc");
+    SNERF_REQUIRE((long long)n_rays * n_samples < (1LL << 31), "snerf_render_forward: more than 2^31 points in one call");
+    FusedComposite fc{};
+    fc.rays_o = rays_o; fc.rays_d = rays_d; fc.rgb_map = rgb_map; fc.acc = acc; fc.depth = depth; fc.depth_var = depth_var;
+    fc.depth_ndc = depth_ndc; fc.depth_var_ndc = depth_var_ndc; fc.alpha = alpha; fc.weights = weights;
+    fc.ndc = ndc; fc.white = (flags & SNERF_FLAG_WHITE_BKGD) != 0;
+    return tc_render_forward(*desc, host_params, packed, pts_o, pts_d, view_dirs, z, fc, workspace, workspace_bytes, n_rays, n_samples,
+                             (cudaStream_t)stream);
+}
+
 extern "C" size_t snerf_visibility_workspace_bytes(const snerf_mlp_desc* desc, int n_rays, int n_samples, int n_other) {
     if (validate_desc(desc) != SNERF_OK || n_rays < 0 || n_samples < 1 || n_other < 0 || desc->view_width <= 0) return 0;
     const size_t b = simt_visibility_workspace_bytes(MlpDims(*desc), n_rays, n_samples, n_other);

@@ -95,14 +95,28 @@ int simt_visibility_backward(const snerf_mlp_desc& d, const float* const* prm, v
 size_t tc_workspace_bytes(const MlpDims& m, const snerf_mlp_desc& d, int n_rays, int n_samples, uint32_t flags);
 size_t tc_packed_bytes(const snerf_mlp_desc& d);
 int tc_pack(const snerf_mlp_desc& d, const float* const* prm, void* packed, cudaStream_t st);
+struct FusedRun {                     // fused evaluation: where the forward kernel leaves the per-run records (mlp_tc.cu)
+    float *seg, *alpha, *wloc;
+    const float *cam_o, *cam_d;
+};
 int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o,
                const float* rays_d, const float* view_dirs, const float* z, const float* noise, float* sigma,
                float* rgb, void* ws, size_t ws_bytes, int n_rays, int n_samples, uint32_t flags, cudaStream_t st,
-               const unsigned long long* rng_seed_offset = nullptr, float noise_std = 0.f);
+               const unsigned long long* rng_seed_offset = nullptr, float noise_std = 0.f, const FusedRun* fused = nullptr);
 int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o,
                 const float* rays_d, const float* view_dirs, const float* z, const float* sigma, const float* rgb,
                 const float* d_sigma, const float* d_rgb, float* const* grads, void* ws, size_t ws_bytes,
                 int n_rays, int n_samples, uint32_t flags, cudaStream_t st);
 int tc_selftest(float* host_max_err, cudaStream_t st);
+// fused evaluation (row X1): MLP forward with the compositing arithmetic in its head epilogue + the per-ray fold
+struct FusedComposite {
+    const float *rays_o, *rays_d;     // camera rays (NDC depth conversion)
+    float *rgb_map, *acc, *depth, *depth_var, *depth_ndc, *depth_var_ndc, *alpha, *weights;
+    bool ndc, white;
+};
+size_t tc_render_workspace_bytes(const MlpDims& m, const snerf_mlp_desc& d, int n_rays, int n_samples);
+int tc_render_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* pts_o,
+                      const float* pts_d, const float* view_dirs, const float* z, const FusedComposite& fc, void* ws,
+                      size_t ws_bytes, int n_rays, int n_samples, cudaStream_t st);
 
 }  // namespace snerf

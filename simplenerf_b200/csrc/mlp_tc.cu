@@ -192,7 +192,11 @@ struct FwdParams {
     RngKey noise_rng;              // use_rng: sigma noise drawn in the head epilogue (element = point index) instead of read from `noise`
     float noise_std;
     int use_rng;
-    float *sigma, *rgb;
+    float *sigma, *rgb;            // null in the fused evaluation (the values stay in registers)
+    // fused evaluation (row X1): compositing arithmetic in the rgb-head epilogue, one record per 32 samples of a ray
+    float* seg;                    // [n_points / 32][kSegFloats]; null = off
+    float *alpha_out, *wloc;       // nullable [n_points]: alpha, and the weights relative to the segment's first sample
+    const float *cam_o, *cam_d;    // camera rays (NDC depth conversion :495-501); null when the depths are metric
     uint8_t* stash;                // null in eval
     uint8_t* bits;                 // (training) ReLU sign bits of the trunk activations, kBitsTileBytes per tile
     long long* trace;              // debug: clock64 timestamps of pair 0 (tools/trace_fwd.py), normally null
@@ -202,6 +206,13 @@ struct FwdParams {
     uint32_t tile_stash_bytes;
     TcStep steps[kMaxSteps];
 };
+
+// One record per warp-aligned run of 32 samples (n_samples % 32 == 0, so a run never straddles two rays):
+//   P = prod (1 - alpha + 1e-10), A = sum w', C = sum w' rgb, Dm / Dn = sum w' z (metric / ndc), Mm / Mn = sum w' (z - D/A)^2
+// with w' = alpha * (transmittance counted from the run's first sample).  composite_fold_kernel multiplies by the
+// transmittance that reaches the run and adds the runs of a ray up.
+constexpr int kSegFloats = 12;
+enum { SEG_P = 0, SEG_A, SEG_CR, SEG_CG, SEG_CB, SEG_DM, SEG_DN, SEG_MM, SEG_MN };
 
 struct FwdBars {
     uint64_t w_full[kPStages];     // leader: own bytes + the peer's relay (2 arrivals); peer: own bytes (1)
@@ -406,6 +417,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
         const uint32_t ready0 = cluster_addr(&bars->tile_ready[0], 0), ready1 = cluster_addr(&bars->tile_ready[1], 0);
         // chunk c of this thread's panel row lives at (panel + row_base) ^ (c << 4)  (128-byte swizzle)
         const uint32_t row_base = smem_u32(smem + kOffH) + (uint32_t)row * kRowBytes + (((uint32_t)row & 7u) << 4);
+        float sig_keep[2] = {0.f, 0.f};     // (fused evaluation) sigma of this thread's row, per slot, from the head step to the rgb step
         auto job = [&](const int x, const int g, const int s) {
             const TcStep& st = p.steps[s];
             const int kind = st.kind;
@@ -528,6 +540,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     for (int h = 0; h < 4; ++h) s_part[((j - 1) * 128 + row) * 4 + h] = head[h];
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+                float col[3] = {0.f, 0.f, 0.f};
                 if (j == 0 && valid) {
 #pragma unroll
                     for (int jj = 0; jj < 3; ++jj) {
@@ -535,9 +548,64 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                         head[0] += o.x; head[1] += o.y; head[2] += o.z;
                     }
 #pragma unroll
-                    for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h] + s_misc[4 + h]);         // :704-707
+                    for (int h = 0; h < 3; ++h) col[h] = sigmoid_acc(head[h] + s_misc[4 + h]);                    // :704-707
+                    if (p.rgb) {
+#pragma unroll
+                        for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = col[h];
+                    }
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // the partial sums may be overwritten by the next head step
+                if (p.seg != nullptr && j == 0) {
+                    // ---- fused evaluation: volume_rendering :430-483 on this warp's 32 consecutive samples of one ray ----
+                    // (same arithmetic as composite.cu: delta :435-441, alpha :446, transmittance :447, NDC depth :495-501)
+                    const int S = p.n_samples;
+                    float sg = 0.f, zz = 0.f, delta = 0.f, zm = 0.f;
+                    if (valid) {
+                        const int ray = (int)((unsigned)pt / (unsigned)S), k = (int)pt - ray * S;
+                        sg = sig_keep[x];
+                        zz = p.z[pt];
+                        const bool ndc = p.cam_o != nullptr;
+                        const float zn = k == S - 1 ? (ndc ? 1.f : 1e10f) : p.z[pt + 1];
+                        const float d0 = p.rays_d[ray * 3], d1 = p.rays_d[ray * 3 + 1], d2 = p.rays_d[ray * 3 + 2];
+                        delta = (zn - zz) * sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+                        zm = zz;
+                        if (ndc) {
+                            const float oz = p.cam_o[ray * 3 + 2], dz = p.cam_d[ray * 3 + 2];
+                            const float tn = -(1.f + oz) / dz, k0 = (oz + tn * dz) / dz;
+                            const float guard = (zz == 1.f) ? 1e-3f : 0.f;
+                            zm = k0 * (__frcp_rn(1.f - zz + guard) - 1.f) + tn;
+                        }
+                    }
+                    const float alpha = valid ? 1.f - __expf(-sg * delta) : 0.f;
+                    const float f = valid ? (1.f - alpha) + 1e-10f : 1.f;
+                    float incl = f;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl *= v;
+                    }
+                    float tr_in = __shfl_up_sync(0xffffffffu, incl, 1);
+                    if (lane == 0) tr_in = 1.f;
+                    const float wl = alpha * tr_in;
+                    auto wsum = [](float v) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        return v;
+                    };
+                    const float A = wsum(wl), Dm = wsum(wl * zm), Dn = wsum(wl * zz);
+                    const float mu_m = A > 0.f ? Dm / A : 0.f, mu_n = A > 0.f ? Dn / A : 0.f;
+                    float rec = 0.f;
+                    const float Cr = wsum(wl * col[0]), Cg = wsum(wl * col[1]), Cb = wsum(wl * col[2]);
+                    const float Mm = wsum(wl * (zm - mu_m) * (zm - mu_m)), Mn = wsum(wl * (zz - mu_n) * (zz - mu_n));
+                    const float P = __shfl_sync(0xffffffffu, incl, 31);
+                    rec = lane == SEG_P ? P : lane == SEG_A ? A : lane == SEG_CR ? Cr : lane == SEG_CG ? Cg : lane == SEG_CB ? Cb :
+                          lane == SEG_DM ? Dm : lane == SEG_DN ? Dn : lane == SEG_MM ? Mm : lane == SEG_MN ? Mn : 0.f;
+                    if (valid) {
+                        if (lane < kSegFloats) p.seg[(size_t)((unsigned long long)pt >> 5) * kSegFloats + lane] = rec;
+                        if (p.alpha_out) p.alpha_out[pt] = alpha;
+                        if (p.wloc) p.wloc[pt] = wl;
+                    }
+                }
                 return;
             }
             // ---- last trunk layer (sigma / rgb head) and the view layer (rgb head): fp32 on the un-rounded activations ----
@@ -628,7 +696,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     float nz = 0.f;
                     if (p.noise) nz = p.noise[pt];
                     else if (p.use_rng) nz = p.noise_std * rng_pick(rng_normal4(p.noise_rng, (unsigned long long)pt >> 2), (unsigned long long)pt);
-                    p.sigma[pt] = fmaxf(head[0] + nz, 0.f);                                        // :668-672
+                    const float sg = fmaxf(head[0] + nz, 0.f);                                     // :668-672
+                    if (p.sigma) p.sigma[pt] = sg;
+                    sig_keep[x] = sg;
                     if (kind == EPI_RELU_HEAD4) {
 #pragma unroll
                         for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
@@ -747,7 +817,8 @@ static int g_fwd_debug = 0;
 
 int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* rays_o, const float* rays_d,
                const float* view_dirs, const float* z, const float* noise, float* sigma, float* rgb, void* ws, size_t ws_bytes,
-               int n_rays, int n_samples, uint32_t flags, cudaStream_t st, const unsigned long long* rng_seed_offset, float noise_std) {
+               int n_rays, int n_samples, uint32_t flags, cudaStream_t st, const unsigned long long* rng_seed_offset, float noise_std,
+               const FusedRun* fused) {
     const MlpDims m(d);
     const TcPlan pl = build_plan(d, prm);
     const TcWorkspace w = tc_ws_layout(m, pl, n_rays, n_samples, flags);
@@ -775,6 +846,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     }
     p.stash = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.act : nullptr;
     p.bits = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.bits : nullptr;
+    if (fused) { p.seg = fused->seg; p.alpha_out = fused->alpha; p.wloc = fused->wloc; p.cam_o = fused->cam_o; p.cam_d = fused->cam_d; }
     p.trace = g_trace; p.debug = g_fwd_debug;
     p.n_points = (long long)n_rays * n_samples;
     p.n_samples = n_samples; p.n_tiles = w.n_tiles; p.n_steps = pl.n_fwd; p.pts_degree = d.pts_degree; p.head_out = m.head_out;
@@ -789,6 +861,102 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     }
     if (p.trace) SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<true>, pair_grid(w.n_tiles), kFwdThreads, kFwdSmem, st, p));
     else SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<false>, pair_grid(w.n_tiles), kFwdThreads, kFwdSmem, st, p));
+    return SNERF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused evaluation (row X1): fold of the per-run records into the per-ray maps, one warp per ray
+// ------------------------------------------------------------------------------------------------
+// Run k of a ray starts with transmittance T_k = prod_{j<k} P_j (:447); with w = T_k w':
+//   acc = sum T_k A_k, rgb = sum T_k C_k, depth = sum T_k D_k / (acc + 1e-6)   (:449-459)
+//   depth_var = sum_k T_k (M_k + A_k (D_k / A_k - depth)^2)                      (:454, :460; the cross terms vanish)
+// and the weights of the run's samples are T_k times the run-relative weights the MLP kernel left in `wloc`.
+constexpr int kFoldWarps = 8;
+__global__ void __launch_bounds__(kFoldWarps * 32) composite_fold_kernel(const float* __restrict__ seg, const float* __restrict__ wloc,
+                                                                         float* __restrict__ rgb_map, float* __restrict__ acc_out,
+                                                                         float* __restrict__ depth, float* __restrict__ depth_var,
+                                                                         float* __restrict__ depth_ndc, float* __restrict__ depth_var_ndc,
+                                                                         float* __restrict__ weights, int n_rays, int n_samples, int white) {
+    const int ray = blockIdx.x * kFoldWarps + threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (ray >= n_rays) return;
+    const int n_seg = n_samples / 32;                      // <= 32 (host check)
+    float r[kSegFloats];
+#pragma unroll
+    for (int i = 0; i < kSegFloats; ++i) r[i] = 0.f;
+    r[SEG_P] = 1.f;
+    if (lane < n_seg) {
+        const float4* src = reinterpret_cast<const float4*>(seg + ((size_t)ray * n_seg + lane) * kSegFloats);
+        const float4 a = src[0], b = src[1], c = src[2];
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w; r[8] = c.x;
+    }
+    float incl = r[SEG_P];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl *= v;
+    }
+    float t_in = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) t_in = 1.f;
+    auto wsum = [](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    const float acc = wsum(t_in * r[SEG_A]);
+    const float cr = wsum(t_in * r[SEG_CR]), cg = wsum(t_in * r[SEG_CG]), cb = wsum(t_in * r[SEG_CB]);
+    const float inv = 1.f / (acc + 1e-6f);
+    const float d_m = wsum(t_in * r[SEG_DM]) * inv, d_n = wsum(t_in * r[SEG_DN]) * inv;
+    const float mu_m = r[SEG_A] > 0.f ? r[SEG_DM] / r[SEG_A] : 0.f, mu_n = r[SEG_A] > 0.f ? r[SEG_DN] / r[SEG_A] : 0.f;
+    const float v_m = wsum(t_in * (r[SEG_MM] + r[SEG_A] * (mu_m - d_m) * (mu_m - d_m)));
+    const float v_n = wsum(t_in * (r[SEG_MN] + r[SEG_A] * (mu_n - d_n) * (mu_n - d_n)));
+    if (lane == 0) {
+        const float bg = white ? 1.f - acc : 0.f;                                                   // :463
+        rgb_map[(size_t)ray * 3 + 0] = cr + bg;
+        rgb_map[(size_t)ray * 3 + 1] = cg + bg;
+        rgb_map[(size_t)ray * 3 + 2] = cb + bg;
+        acc_out[ray] = acc;
+        depth[ray] = d_m;
+        depth_var[ray] = v_m;
+        if (depth_ndc) { depth_ndc[ray] = d_n; depth_var_ndc[ray] = v_n; }
+    }
+    if (weights) {
+        for (int k = 0; k < n_seg; ++k) {
+            const float t = __shfl_sync(0xffffffffu, t_in, k);
+            const size_t o = (size_t)ray * n_samples + k * 32 + lane;
+            weights[o] = t * wloc[o];                                                               // :448
+        }
+    }
+}
+
+size_t tc_render_workspace_bytes(const MlpDims& m, const snerf_mlp_desc& d, int n_rays, int n_samples) {
+    const size_t P = (size_t)n_rays * n_samples;
+    return tc_workspace_bytes(m, d, n_rays, n_samples, 0) + align_up(P / 32 * kSegFloats * sizeof(float), 1024) +
+           align_up(P * sizeof(float), 1024) + 1024;
+}
+
+int tc_render_forward(const snerf_mlp_desc& d, const float* const* prm, const void* packed, const float* pts_o,
+                      const float* pts_d, const float* view_dirs, const float* z, const FusedComposite& fc, void* ws,
+                      size_t ws_bytes, int n_rays, int n_samples, cudaStream_t st) {
+    const MlpDims m(d);
+    if (!m.has_view || n_samples % 32 != 0 || n_samples > 1024)
+        return fail(SNERF_ERR_UNSUPPORTED, "snerf_render_forward: needs an MLP with a view branch and n_samples %% 32 == 0 (<= 1024), got %d", n_samples);
+    SNERF_REQUIRE(ws_bytes >= tc_render_workspace_bytes(m, d, n_rays, n_samples), "snerf_render_forward: workspace too small");
+    const size_t P = (size_t)n_rays * n_samples;
+    const size_t base = tc_workspace_bytes(m, d, n_rays, n_samples, 0);
+    uint8_t* wsb = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    FusedRun fr{};
+    fr.seg = (float*)(wsb + align_up(base, 1024));
+    fr.wloc = fc.weights ? (float*)((uint8_t*)fr.seg + align_up(P / 32 * kSegFloats * sizeof(float), 1024)) : nullptr;
+    fr.alpha = fc.alpha;
+    fr.cam_o = fc.ndc ? fc.rays_o : nullptr;
+    fr.cam_d = fc.ndc ? fc.rays_d : nullptr;
+    const int rc = tc_forward(d, prm, packed, pts_o, pts_d, view_dirs, z, nullptr, nullptr, nullptr, ws, base, n_rays, n_samples, 0, st,
+                              nullptr, 0.f, &fr);
+    if (rc != SNERF_OK) return rc;
+    composite_fold_kernel<<<(n_rays + kFoldWarps - 1) / kFoldWarps, kFoldWarps * 32, 0, st>>>(
+        fr.seg, fr.wloc, fc.rgb_map, fc.acc, fc.depth, fc.depth_var, fc.ndc ? fc.depth_ndc : nullptr, fc.ndc ? fc.depth_var_ndc : nullptr,
+        fc.weights, n_rays, n_samples, fc.white ? 1 : 0);
+    SNERF_LAUNCH_OK("composite_fold_kernel");
     return SNERF_OK;
 }
 

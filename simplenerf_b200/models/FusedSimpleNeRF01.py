@@ -303,6 +303,7 @@ class FusedSimpleNeRF(torch.nn.Module):
             raise NotImplementedError("predict_visibility=True (secondary-view visibility head, SURVEY row a14 / N4) is built on the "
                                       "fp32 path only: set configs['model']['precision'] = 'fp32' (every shipped config has it False)")
         self.launch_rays = int(mc.get('launch_rays', 65536))
+        self.fused_composite = bool(mc.get('fused_composite', True))   # evaluation: MLP + compositing in one pass (row X1)
         rng = mc.get('rng', 'device')
         if rng not in ('device', 'torch', 'reference'):
             raise ValueError(f"configs['model']['rng'] must be 'device', 'torch' or 'reference', got {rng!r}")
@@ -380,6 +381,16 @@ class FusedSimpleNeRF(torch.nn.Module):
             pts_o, pts_d = rays_o, rays_d                                        # :140
         view_dirs = f32(batch['view_dirs']) if block.use_view_dirs else rays_d
         rays_o2 = batch.get('rays_o2') if block.predict_visibility else None
+        if (self.fused_composite and not retraw and not need_grad and not self.training and self.precision == 'bf16'
+                and block.has_view and not block.predict_visibility and s % 32 == 0 and s <= 1024):
+            # nothing downstream wants the raw network outputs (:265-269), so the samples stay on chip
+            # between the MLP and the compositing sums (snerf_render_forward); `weights` only where the resampler reads them
+            detached = [None if q is None else q.detach() for q in table]
+            maps = ops.render_forward(block.desc, detached, block.packed(detached), pts_o, pts_d, view_dirs, z, rays_o, rays_d,
+                                      self.ndc, bool(mc['white_bkgd']), want_weights=(level == 'coarse' and self.fine_mlp_needed))
+            for k, v in maps.items():
+                out[f'{prefix}{k}_{level}'] = v
+            return maps
         res = _RenderStream.apply(block, opts, z, noise, rays_o, rays_d, pts_o, pts_d, view_dirs, rays_o2, *params)
         keys = ['rgb', 'acc', 'depth', 'depth_var'] + (['depth_ndc', 'depth_var_ndc'] if self.ndc else []) + \
                ['alpha', 'visibility', 'weights'] + (['visibility2'] if rays_o2 is not None else [])

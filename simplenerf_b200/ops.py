@@ -223,6 +223,35 @@ def mlp_forward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, noi
     return sigma, rgb
 
 
+def render_forward(desc: MlpDesc, params, packed, pts_o, pts_d, view_dirs, z, rays_o, rays_d, ndc: bool, white_bkgd: bool,
+                   want_weights: bool) -> Dict[str, torch.Tensor]:
+    """Evaluation with the samples kept on chip: run_network + volume_rendering (reference :153-160, :430-483)
+    in one pass -- sigma / rgb never reach HBM.  Returns the per-ray maps, `alpha` [N,S] and, on request, `weights` [N,S]."""
+    n, s = z.shape
+    dev = z.device
+    out = {'rgb': torch.empty((n, 3), device=dev), 'acc': torch.empty(n, device=dev),
+           'depth': torch.empty(n, device=dev), 'depth_var': torch.empty(n, device=dev)}
+    if ndc:
+        out['depth_ndc'] = torch.empty(n, device=dev)
+        out['depth_var_ndc'] = torch.empty(n, device=dev)
+    out['alpha'] = torch.empty((n, s), device=dev)
+    if want_weights:
+        out['weights'] = torch.empty((n, s), device=dev)
+    flags = (FLAG_NDC if ndc else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0)
+    nbytes = _lib.load().snerf_render_workspace_bytes(C.byref(desc), n, s, flags)
+    if nbytes == 0:
+        raise RuntimeError(f'snerf_render_workspace_bytes: {_lib.load().snerf_last_error().decode()}')
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    LAUNCHES['count'] += 3          # view-bias table, the MLP kernel with the compositing arithmetic in its epilogue, the per-ray fold
+    with _timed('mlp_forward'):
+        _lib.check(_lib.load().snerf_render_forward(
+            C.byref(desc), pointer_table(params), _ptr(packed, torch.uint8), _ptr(pts_o), _ptr(pts_d), _ptr(view_dirs), _ptr(z),
+            _ptr(rays_o), _ptr(rays_d), _ptr(out['rgb']), _ptr(out['acc']), _ptr(out['depth']), _ptr(out['depth_var']),
+            _ptr(out.get('depth_ndc')), _ptr(out.get('depth_var_ndc')), _ptr(out['alpha']), _ptr(out.get('weights')),
+            _ptr(ws, torch.uint8), ws.numel(), n, s, flags, _stream()), 'snerf_render_forward')
+    return out
+
+
 def mlp_backward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, sigma, rgb, d_sigma, d_rgb,
                  grads: List[Optional[torch.Tensor]], workspace, flags: int) -> None:
     n, s = z.shape
