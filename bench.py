@@ -269,6 +269,27 @@ def trainer_context(steps: int, warmup: int):
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / steps
         out[key] = {'value': RAYS_PER_GPU / dt, 'unit': 'rays/s', 'ms_per_step': 1e3 * dt, 'steps': steps}
+        if key == 'dropin_fused_losses_adam':
+            # (d) the same model, losses and optimizer driven by the drop-in's own per-rank step (simplenerf_b200.trainer.
+            # RayShardedTrainStep = the body of Trainer01.train_one_iter without its ten .item() reads per sub-batch) on a batch the
+            # reference's preprocessor assembled, resident on the device: device time of the full C2 step with the shipped losses
+            from simplenerf_b200.trainer import RayShardedTrainStep
+            batch = trainer.train_data_loader.get_next_batch(20200)
+            model = trainer.model.module if hasattr(trainer.model, 'module') else trainer.model
+            step = RayShardedTrainStep(trainer.configs, model, trainer.loss_computer, trainer.optimizer)
+            for _ in range(max(warmup, 3)):
+                step(batch)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(4 * steps):
+                step(batch)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / (4 * steps)
+            out['train_full'] = {'value': RAYS_PER_GPU / (ms * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms, 'steps': 4 * steps,
+                                 'what': 'RayShardedTrainStep: 2 sub-batches of 2048 rays (2048 image + 2048 sparse-depth rays), FusedSimpleNeRF01 bf16, '
+                                         'FusedLossComputer with the 9 shipped losses, FusedAdam; CUDA events, batch resident in HBM'}
         del trainer
         torch.cuda.empty_cache()
     return out

@@ -394,6 +394,142 @@ __global__ void __launch_bounds__(kCompWarps* kWarp, (C >= 8 ? 3 : 0)) composite
     }
 }
 
+// Backward for 256 samples per ray: TWO warps per ray, four consecutive samples per lane.  With one warp per ray a lane owns
+// eight samples and the kernel needs 108 registers (capped at 80: 0.62 of the HBM bandwidth); four per lane is the shape of the
+// 128-sample kernel (0.72).  The two warps meet three times through shared memory: the transmittance that reaches the second
+// half, the per-ray sums, and the suffix sum of the second half.  Arithmetic and order of operations inside a warp are those
+// of RayState / composite_bwd_kernel above.
+__global__ void __launch_bounds__(kCompWarps* kWarp) composite_bwd_pair_kernel(const CompositeArgs a) {
+    constexpr int C = 4;
+    __shared__ float s_x[kCompWarps / 2][2][8];
+    const int warp = threadIdx.x / kWarp, l32 = threadIdx.x % kWarp, half = warp & 1, pair = warp >> 1;
+    const int ray_raw = blockIdx.x * (kCompWarps / 2) + pair;
+    const bool valid = ray_raw < a.n_rays;
+    const int ray = valid ? ray_raw : a.n_rays - 1;            // both warps of a pair stay in step through the barriers
+    const int s = a.s, lane = half * kWarp + l32;              // lane within the ray: samples lane * 4 .. + 3
+    auto meet = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory"); };
+    float* mine = s_x[pair][half];
+    const float* other = s_x[pair][half ^ 1];
+
+    const float* rgb = a.rgb + (size_t)ray * s * 3;
+    float c[3 * C];
+    load_vec<3 * C>(rgb + lane * 3 * C, c);
+    const float* sg = a.sigma + (size_t)ray * s;
+    const float* z = a.z + (size_t)ray * s;
+    const float* dvec = (a.ndc ? a.rays_d_ndc : a.rays_d) + (size_t)ray * 3;
+    const float dn = sqrtf(dvec[0] * dvec[0] + dvec[1] * dvec[1] + dvec[2] * dvec[2]);
+    const float tail = a.ndc ? 1.f : 1e10f;
+    float k0 = 0.f, tn = 0.f;
+    if (a.ndc) {
+        const float oz = a.rays_o[(size_t)ray * 3 + 2], dz = a.rays_d[(size_t)ray * 3 + 2];
+        tn = -(1.f + oz) / dz;
+        k0 = (oz + tn * dz) / dz;
+    }
+    float sig[C], zz[C], zm[C], delta[C], alpha[C], trans[C], w[C];
+    load_vec<C>(sg + lane * C, sig);
+    load_vec<C>(z + lane * C, zz);
+    const float up = lane == 63 ? tail : __ldg(z + lane * C + C);       // first depth of the next lane (the other warp's for lane 31)
+    float fprod = 1.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        const float zn = i == C - 1 ? up : zz[i + 1];
+        delta[i] = (zn - zz[i]) * dn;
+        alpha[i] = 1.f - __expf(-sig[i] * delta[i]);
+        if (a.ndc) {
+            const float guard = (zz[i] == 1.f) ? 1e-3f : 0.f;
+            zm[i] = k0 * (__frcp_rn(1.f - zz[i] + guard) - 1.f) + tn;
+        } else {
+            zm[i] = zz[i];
+        }
+        fprod *= (1.f - alpha[i]) + 1e-10f;
+    }
+    float incl = fprod;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+        const float v = __shfl_up_sync(kFull, incl, o);
+        if (l32 >= o) incl *= v;
+    }
+    float t = __shfl_up_sync(kFull, incl, 1);
+    if (l32 == 0) t = 1.f;
+    if (l32 == kWarp - 1) mine[0] = incl;                      // product of this half
+    meet();
+    if (half == 1) t *= other[0];                              // transmittance that reaches the second half
+    float acc = 0.f, dsum = 0.f, dsum_ndc = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        trans[i] = t;
+        w[i] = alpha[i] * t;
+        t *= (1.f - alpha[i]) + 1e-10f;
+        acc += w[i];
+        dsum += w[i] * zm[i];
+        dsum_ndc += w[i] * zz[i];
+    }
+    acc = group_sum<kWarp>(acc);
+    dsum = group_sum<kWarp>(dsum);
+    dsum_ndc = group_sum<kWarp>(dsum_ndc);
+    if (l32 == 0) { mine[1] = acc; mine[2] = dsum; mine[3] = dsum_ndc; }
+    meet();
+    // first half + second half, in that order in both warps: the two agree bit for bit
+    acc = half == 0 ? acc + other[1] : other[1] + acc;
+    dsum = half == 0 ? dsum + other[2] : other[2] + dsum;
+    dsum_ndc = half == 0 ? dsum_ndc + other[3] : other[3] + dsum_ndc;
+
+    const float inv = 1.f / (acc + 1e-6f);
+    const float depth = dsum * inv, depth_ndc = dsum_ndc * inv;
+    float gr = 0.f, gg = 0.f, gb = 0.f;
+    if (a.g_rgb_map) {
+        gr = a.g_rgb_map[(size_t)ray * 3 + 0];
+        gg = a.g_rgb_map[(size_t)ray * 3 + 1];
+        gb = a.g_rgb_map[(size_t)ray * 3 + 2];
+    }
+    float g_const = a.g_acc ? a.g_acc[ray] : 0.f;
+    if (a.white) g_const -= gr + gg + gb;
+    const float gd = a.g_depth ? a.g_depth[ray] : 0.f;
+    const float gdn = (a.ndc && a.g_depth_ndc) ? a.g_depth_ndc[ray] : 0.f;
+    const float gv = a.g_depth_var ? a.g_depth_var[ray] : 0.f;
+    const float gvn = (a.ndc && a.g_depth_var_ndc) ? a.g_depth_var_ndc[ray] : 0.f;
+    const float resid = dsum - depth * acc, resid_ndc = dsum_ndc - depth_ndc * acc;
+    float g[C], gt[C], lane_gt = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        const size_t o = (size_t)ray * s + lane * C + i;
+        const float e = zm[i] - depth, en = zz[i] - depth_ndc;
+        float gi = gr * c[3 * i] + gg * c[3 * i + 1] + gb * c[3 * i + 2] + g_const;
+        gi += gd * e * inv + gdn * en * inv;
+        gi += gv * (e * e - 2.f * e * inv * resid) + gvn * (en * en - 2.f * en * inv * resid_ndc);
+        if (a.g_weights) gi += a.g_weights[o];
+        float big_g = gi * alpha[i];
+        if (a.g_vis) big_g += a.g_vis[o];
+        g[i] = gi;
+        gt[i] = big_g * trans[i];
+        lane_gt += gt[i];
+    }
+    float dr[3 * C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) { dr[3 * i] = w[i] * gr; dr[3 * i + 1] = w[i] * gg; dr[3 * i + 2] = w[i] * gb; }
+    if (valid) store_vec<3 * C>(a.d_rgb + ((size_t)ray * s + lane * C) * 3, dr);
+    float sincl = lane_gt;                                     // inclusive suffix over the lanes of this half
+#pragma unroll
+    for (int off = 1; off < kWarp; off <<= 1) {
+        const float v = __shfl_down_sync(kFull, sincl, off);
+        if (l32 + off < kWarp) sincl += v;
+    }
+    if (l32 == 0) mine[4] = sincl;                             // everything owned by this half
+    meet();
+    float suffix = sincl - lane_gt;
+    if (half == 0) suffix += other[4];
+    float ds[C];
+#pragma unroll
+    for (int i = C - 1; i >= 0; --i) {
+        const float f = (1.f - alpha[i]) + 1e-10f;
+        float d_alpha = g[i] * trans[i] - suffix * __frcp_rn(f);
+        if (a.g_alpha) d_alpha += a.g_alpha[(size_t)ray * s + lane * C + i];
+        ds[i] = d_alpha * delta[i] * (1.f - alpha[i]);
+        suffix += gt[i];
+    }
+    if (valid) store_vec<C>(a.d_sigma + (size_t)ray * s + lane * C, ds);
+}
+
 template <int C, bool CONTIG, int G = kWarp>
 static int launch_composite(const CompositeArgs& a, bool backward, cudaStream_t st) {
     const int blocks = ceil_div(a.n_rays, kCompWarps * (kWarp / G));
@@ -411,7 +547,13 @@ static int dispatch_composite(const CompositeArgs& a, bool backward, cudaStream_
         case 64: return launch_composite<4, true, 16>(a, backward, st);    // two rays per warp, float4 rows
         case 128: return launch_composite<4, true>(a, backward, st);
         case 192: return launch_composite<6, true>(a, backward, st);
-        case 256: return launch_composite<8, true>(a, backward, st);
+        case 256:
+            if (backward) {
+                composite_bwd_pair_kernel<<<ceil_div(a.n_rays, kCompWarps / 2), kCompWarps * kWarp, 0, st>>>(a);
+                SNERF_LAUNCH_OK("composite_bwd_pair_kernel");
+                return SNERF_OK;
+            }
+            return launch_composite<8, true>(a, backward, st);
         default: break;
     }
     const int items = ceil_div(a.s, kWarp);

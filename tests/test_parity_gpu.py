@@ -175,7 +175,7 @@ def test_composite_forward_vs_oracle(ndc, s, white):
 
 
 @pytest.mark.parametrize('ndc', [True, False])
-@pytest.mark.parametrize('s', [64, 192])
+@pytest.mark.parametrize('s', [64, 192, 256, 128])
 def test_composite_backward_vs_autograd(ndc, s):
     n = 130
     b, sigma, rgb, z = _composite_case(n, s, ndc, 40 + s)
