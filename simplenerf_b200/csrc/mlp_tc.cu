@@ -122,8 +122,23 @@ constexpr int kVbRays = 16;
 __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restrict__ view_dirs, const float* __restrict__ w_view,
                                                            const float* __restrict__ b_view, const float* __restrict__ b_merged,
                                                            float* __restrict__ vb, int n_rays,
-                                                           int view_degree, int view_in, int col0, int venc) {
+                                                           int view_degree, int view_in, int col0, int venc,
+                                                           const float* __restrict__ pts_d, const float* __restrict__ cam_o,
+                                                           const float* __restrict__ cam_d, float4* __restrict__ rayc) {
     const int ray0 = blockIdx.x * kVbRays;
+    // fused evaluation: the per-ray constants of the compositing arithmetic -- |d| (:436 / :441) and, for NDC depths, the two
+    // factors of convert_depth_from_ndc (:498, :501), with composite.cu's expressions
+    if (rayc != nullptr && threadIdx.x < kVbRays && ray0 + threadIdx.x < n_rays) {
+        const int ray = ray0 + threadIdx.x;
+        const float d0 = pts_d[ray * 3], d1 = pts_d[ray * 3 + 1], d2 = pts_d[ray * 3 + 2];
+        float tn = 0.f, k0 = 0.f;
+        if (cam_o != nullptr) {
+            const float oz = cam_o[ray * 3 + 2], dz = cam_d[ray * 3 + 2];
+            tn = -(1.f + oz) / dz;
+            k0 = (oz + tn * dz) / dz;
+        }
+        rayc[ray] = make_float4(sqrtf(d0 * d0 + d1 * d1 + d2 * d2), tn, k0, 0.f);
+    }
     __shared__ float ve[kVbRays][32];
     for (int e = threadIdx.x; e < kVbRays * 32; e += blockDim.x) {
         const int r = e >> 5, idx = e & 31, ray = ray0 + r;
@@ -196,7 +211,8 @@ struct FwdParams {
     // fused evaluation (row X1): compositing arithmetic in the rgb-head epilogue, one record per 32 samples of a ray
     float* seg;                    // [n_points / 32][kSegFloats]; null = off
     float *alpha_out, *wloc;       // nullable [n_points]: alpha, and the weights relative to the segment's first sample
-    const float *cam_o, *cam_d;    // camera rays (NDC depth conversion :495-501); null when the depths are metric
+    const float4* rayc;            // per ray: |d|, and the two factors of the NDC depth conversion (tc_view_bias_kernel)
+    int ndc;
     uint8_t* stash;                // null in eval
     uint8_t* bits;                 // (training) ReLU sign bits of the trunk activations, kBitsTileBytes per tile
     long long* trace;              // debug: clock64 timestamps of pair 0 (tools/trace_fwd.py), normally null
@@ -207,12 +223,13 @@ struct FwdParams {
     TcStep steps[kMaxSteps];
 };
 
-// One record per warp-aligned run of 32 samples (n_samples % 32 == 0, so a run never straddles two rays):
-//   P = prod (1 - alpha + 1e-10), A = sum w', C = sum w' rgb, Dm / Dn = sum w' z (metric / ndc), Mm / Mn = sum w' (z - D/A)^2
-// with w' = alpha * (transmittance counted from the run's first sample).  composite_fold_kernel multiplies by the
-// transmittance that reaches the run and adds the runs of a ray up.
+// One record per warp-aligned run of 32 samples (n_samples % 32 == 0, so a run never straddles two rays).  With
+// w' = alpha * (transmittance counted from the run's first sample) and the run's first depths as reference points:
+//   P = prod (1 - alpha + 1e-10), A = sum w', C = sum w' rgb, S1 = sum w' (z - z_ref), S2 = sum w' (z - z_ref)^2
+// (metric and ndc depths).  composite_fold_kernel multiplies by the transmittance that reaches the run and adds the runs of a
+// ray up; the second moment about the ray's depth follows from S1, S2 without cancellation (z - z_ref spans one run only).
 constexpr int kSegFloats = 12;
-enum { SEG_P = 0, SEG_A, SEG_CR, SEG_CG, SEG_CB, SEG_DM, SEG_DN, SEG_MM, SEG_MN };
+enum { SEG_P = 0, SEG_A, SEG_CR, SEG_CG, SEG_CB, SEG_S1M, SEG_S1N, SEG_S2M, SEG_S2N, SEG_ZM, SEG_ZN };
 
 struct FwdBars {
     uint64_t w_full[kPStages];     // leader: own bytes + the peer's relay (2 arrivals); peer: own bytes (1)
@@ -422,6 +439,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
             const TcStep& st = p.steps[s];
             const int kind = st.kind;
             const uint32_t jx = (uint32_t)(g * p.n_steps + s);
+            // fused evaluation: this row's depths and its ray's constants are requested before the wait for the accumulator
+            float pf_z = 0.f, pf_zn = 0.f;
+            float4 pf_rc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.seg != nullptr && kind == EPI_VIEW && j == 0) {
+                const long long pt0 = (long long)tile_of(2 * g + x) * kTileRows + row;
+                if (pt0 < p.n_points) {
+                    const int ray = (int)((unsigned)pt0 / (unsigned)p.n_samples), k = (int)pt0 - ray * p.n_samples;
+                    pf_z = __ldg(p.z + pt0);
+                    pf_zn = k == p.n_samples - 1 ? (p.ndc ? 1.f : 1e10f) : __ldg(p.z + pt0 + 1);        // :433 / :438
+                    pf_rc = __ldg(p.rayc + ray);
+                }
+            }
             mbar_wait(&bars->acc_full[x], jx & 1);
             tc_fence_after();
             const bool tr = kTrace && p.trace && blockIdx.x == 0 && g == 1 && warp == kWarpEpi0 && lane == 0;
@@ -558,27 +587,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 if (p.seg != nullptr && j == 0) {
                     // ---- fused evaluation: volume_rendering :430-483 on this warp's 32 consecutive samples of one ray ----
                     // (same arithmetic as composite.cu: delta :435-441, alpha :446, transmittance :447, NDC depth :495-501)
-                    const int S = p.n_samples;
-                    float sg = 0.f, zz = 0.f, delta = 0.f, zm = 0.f;
-                    if (valid) {
-                        const int ray = (int)((unsigned)pt / (unsigned)S), k = (int)pt - ray * S;
-                        sg = sig_keep[x];
-                        zz = p.z[pt];
-                        const bool ndc = p.cam_o != nullptr;
-                        const float zn = k == S - 1 ? (ndc ? 1.f : 1e10f) : p.z[pt + 1];
-                        const float d0 = p.rays_d[ray * 3], d1 = p.rays_d[ray * 3 + 1], d2 = p.rays_d[ray * 3 + 2];
-                        delta = (zn - zz) * sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-                        zm = zz;
-                        if (ndc) {
-                            const float oz = p.cam_o[ray * 3 + 2], dz = p.cam_d[ray * 3 + 2];
-                            const float tn = -(1.f + oz) / dz, k0 = (oz + tn * dz) / dz;
-                            const float guard = (zz == 1.f) ? 1e-3f : 0.f;
-                            zm = k0 * (__frcp_rn(1.f - zz + guard) - 1.f) + tn;
-                        }
+                    const float sg = valid ? sig_keep[x] : 0.f, zz = pf_z;
+                    const float delta = (pf_zn - zz) * pf_rc.x;
+                    float zm = zz;
+                    if (p.ndc) {
+                        const float guard = (zz == 1.f) ? 1e-3f : 0.f;
+                        zm = pf_rc.z * (__frcp_rn(1.f - zz + guard) - 1.f) + pf_rc.y;
                     }
                     const float alpha = valid ? 1.f - __expf(-sg * delta) : 0.f;
-                    const float f = valid ? (1.f - alpha) + 1e-10f : 1.f;
-                    float incl = f;
+                    float incl = valid ? (1.f - alpha) + 1e-10f : 1.f;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const float v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -587,21 +604,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     float tr_in = __shfl_up_sync(0xffffffffu, incl, 1);
                     if (lane == 0) tr_in = 1.f;
                     const float wl = alpha * tr_in;
-                    auto wsum = [](float v) {
+                    const float zm_ref = __shfl_sync(0xffffffffu, zm, 0), zn_ref = __shfl_sync(0xffffffffu, zz, 0);
+                    const float em = zm - zm_ref, en = zz - zn_ref;
+                    // eight sums over the warp in nine shuffles: every step halves the values a lane still carries
+                    float v8[8] = {wl, wl * col[0], wl * col[1], wl * col[2], wl * em, wl * en, wl * em * em, wl * en * en};
+                    float v4[4], v2[2];
+                    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                        return v;
-                    };
-                    const float A = wsum(wl), Dm = wsum(wl * zm), Dn = wsum(wl * zz);
-                    const float mu_m = A > 0.f ? Dm / A : 0.f, mu_n = A > 0.f ? Dn / A : 0.f;
-                    float rec = 0.f;
-                    const float Cr = wsum(wl * col[0]), Cg = wsum(wl * col[1]), Cb = wsum(wl * col[2]);
-                    const float Mm = wsum(wl * (zm - mu_m) * (zm - mu_m)), Mn = wsum(wl * (zz - mu_n) * (zz - mu_n));
-                    const float P = __shfl_sync(0xffffffffu, incl, 31);
-                    rec = lane == SEG_P ? P : lane == SEG_A ? A : lane == SEG_CR ? Cr : lane == SEG_CG ? Cg : lane == SEG_CB ? Cb :
-                          lane == SEG_DM ? Dm : lane == SEG_DN ? Dn : lane == SEG_MM ? Mm : lane == SEG_MN ? Mn : 0.f;
+                    for (int i = 0; i < 4; ++i) {
+                        const float got = __shfl_xor_sync(0xffffffffu, h16 ? v8[i] : v8[i + 4], 16);
+                        v4[i] = (h16 ? v8[i + 4] : v8[i]) + got;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float got = __shfl_xor_sync(0xffffffffu, h8 ? v4[i] : v4[i + 2], 8);
+                        v2[i] = (h8 ? v4[i + 2] : v4[i]) + got;
+                    }
+                    float v1 = (h4 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? v2[0] : v2[1], 4);
+                    v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+                    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);                // lane l: sum number (l >> 2)
                     if (valid) {
-                        if (lane < kSegFloats) p.seg[(size_t)((unsigned long long)pt >> 5) * kSegFloats + lane] = rec;
+                        float* rec = p.seg + (size_t)((unsigned long long)pt >> 5) * kSegFloats;
+                        if ((lane & 3) == 0) rec[SEG_A + (lane >> 2)] = v1;
+                        if (lane == 31) rec[SEG_P] = incl;
+                        if (lane == 1) rec[SEG_ZM] = zm_ref;
+                        if (lane == 2) rec[SEG_ZN] = zn_ref;
                         if (p.alpha_out) p.alpha_out[pt] = alpha;
                         if (p.wloc) p.wloc[pt] = wl;
                     }
@@ -828,7 +855,9 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     if (m.has_view) {
         tc_view_bias_kernel<<<(n_rays + kVbRays - 1) / kVbRays, 128, 0, st>>>(view_dirs, prm[SNERF_P_VIEW_W], prm[SNERF_P_VIEW_B],
                                                     (const float*)((const uint8_t*)packed + align_up(pl.packed_bytes, 1024)) + 128 * 256,
-                                                    (float*)(wsb + w.view_bias), n_rays, d.view_degree, m.view_in, m.width + m.enc_hi, m.venc);
+                                                    (float*)(wsb + w.view_bias), n_rays, d.view_degree, m.view_in, m.width + m.enc_hi, m.venc,
+                                                    rays_d, fused ? fused->cam_o : nullptr, fused ? fused->cam_d : nullptr,
+                                                    fused ? (float4*)(wsb + w.view_bias + (size_t)n_rays * 128 * sizeof(float)) : nullptr);
         SNERF_LAUNCH_OK("tc_view_bias_kernel");
     }
     FwdParams p{};
@@ -846,7 +875,10 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     }
     p.stash = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.act : nullptr;
     p.bits = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.bits : nullptr;
-    if (fused) { p.seg = fused->seg; p.alpha_out = fused->alpha; p.wloc = fused->wloc; p.cam_o = fused->cam_o; p.cam_d = fused->cam_d; }
+    if (fused) {
+        p.seg = fused->seg; p.alpha_out = fused->alpha; p.wloc = fused->wloc; p.ndc = fused->cam_o != nullptr ? 1 : 0;
+        p.rayc = (const float4*)(wsb + w.view_bias + (size_t)n_rays * 128 * sizeof(float));
+    }
     p.trace = g_trace; p.debug = g_fwd_debug;
     p.n_points = (long long)n_rays * n_samples;
     p.n_samples = n_samples; p.n_tiles = w.n_tiles; p.n_steps = pl.n_fwd; p.pts_degree = d.pts_degree; p.head_out = m.head_out;
@@ -869,7 +901,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
 // ------------------------------------------------------------------------------------------------
 // Run k of a ray starts with transmittance T_k = prod_{j<k} P_j (:447); with w = T_k w':
 //   acc = sum T_k A_k, rgb = sum T_k C_k, depth = sum T_k D_k / (acc + 1e-6)   (:449-459)
-//   depth_var = sum_k T_k (M_k + A_k (D_k / A_k - depth)^2)                      (:454, :460; the cross terms vanish)
+//   depth_var = sum_k T_k (S2_k - 2 S1_k (depth - z_ref,k) + A_k (depth - z_ref,k)^2)   (:454, :460; D_k = S1_k + A_k z_ref,k)
 // and the weights of the run's samples are T_k times the run-relative weights the MLP kernel left in `wloc`.
 constexpr int kFoldWarps = 8;
 __global__ void __launch_bounds__(kFoldWarps * 32) composite_fold_kernel(const float* __restrict__ seg, const float* __restrict__ wloc,
@@ -887,7 +919,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) composite_fold_kernel(const f
     if (lane < n_seg) {
         const float4* src = reinterpret_cast<const float4*>(seg + ((size_t)ray * n_seg + lane) * kSegFloats);
         const float4 a = src[0], b = src[1], c = src[2];
-        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w; r[8] = c.x;
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w; r[8] = c.x; r[9] = c.y; r[10] = c.z;
     }
     float incl = r[SEG_P];
 #pragma unroll
@@ -902,13 +934,15 @@ __global__ void __launch_bounds__(kFoldWarps * 32) composite_fold_kernel(const f
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         return v;
     };
-    const float acc = wsum(t_in * r[SEG_A]);
+    const float A = r[SEG_A];
+    const float acc = wsum(t_in * A);
     const float cr = wsum(t_in * r[SEG_CR]), cg = wsum(t_in * r[SEG_CG]), cb = wsum(t_in * r[SEG_CB]);
     const float inv = 1.f / (acc + 1e-6f);
-    const float d_m = wsum(t_in * r[SEG_DM]) * inv, d_n = wsum(t_in * r[SEG_DN]) * inv;
-    const float mu_m = r[SEG_A] > 0.f ? r[SEG_DM] / r[SEG_A] : 0.f, mu_n = r[SEG_A] > 0.f ? r[SEG_DN] / r[SEG_A] : 0.f;
-    const float v_m = wsum(t_in * (r[SEG_MM] + r[SEG_A] * (mu_m - d_m) * (mu_m - d_m)));
-    const float v_n = wsum(t_in * (r[SEG_MN] + r[SEG_A] * (mu_n - d_n) * (mu_n - d_n)));
+    const float d_m = wsum(t_in * (r[SEG_S1M] + A * r[SEG_ZM])) * inv, d_n = wsum(t_in * (r[SEG_S1N] + A * r[SEG_ZN])) * inv;
+    // run k about the ray's depth: sum w' (z - depth)^2 = S2 - 2 S1 (depth - z_ref) + A (depth - z_ref)^2
+    const float gm = d_m - r[SEG_ZM], gn = d_n - r[SEG_ZN];
+    const float v_m = wsum(t_in * (r[SEG_S2M] - 2.f * r[SEG_S1M] * gm + A * gm * gm));
+    const float v_n = wsum(t_in * (r[SEG_S2N] - 2.f * r[SEG_S1N] * gn + A * gn * gn));
     if (lane == 0) {
         const float bg = white ? 1.f - acc : 0.f;                                                   // :463
         rgb_map[(size_t)ray * 3 + 0] = cr + bg;

@@ -278,7 +278,7 @@ static inline TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n
     w.n_tiles = (int)((P + kTileRows - 1) / kTileRows);
     size_t off = 0;
     w.view_bias = off;
-    off += align_up(m.has_view ? (size_t)n_rays * 128 * sizeof(float) : 0, 1024);
+    off += align_up(m.has_view ? (size_t)n_rays * (128 + 4) * sizeof(float) : 0, 1024);     // per-ray view bias, then 4 compositing constants per ray
     if (flags & SNERF_FLAG_SAVE_FOR_BWD) {
         w.act = off;
         off += (size_t)w.n_tiles * pl.tile_stash_bytes;
