@@ -8,7 +8,7 @@
 
 namespace snerf {
 
-constexpr int kAdamChunk = 8192;
+constexpr int kAdamChunk = 2048;     // 2 K elements per block: ~1100 blocks for the 2.27 M parameters (8 K left the loads latency-bound)
 constexpr int kAdamThreads = 256;
 
 struct AdamTable {

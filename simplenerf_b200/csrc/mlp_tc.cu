@@ -109,7 +109,7 @@ int tc_pack(const snerf_mlp_desc& d, const float* const* prm, void* packed, cuda
     PackParams pp;
     pp.n = pl.n_pack;
     for (int i = 0; i < pl.n_pack; ++i) pp.c[i] = pl.pack[i];
-    tc_pack_kernel<<<dim3(2, pl.n_pack), 256, 0, st>>>(pp, (uint8_t*)packed);
+    tc_pack_kernel<<<dim3(8, pl.n_pack), 256, 0, st>>>(pp, (uint8_t*)packed);
     SNERF_LAUNCH_OK("tc_pack_kernel");
     return SNERF_OK;
 }
