@@ -344,3 +344,35 @@ def test_fused_evaluation_equals_the_two_kernel_path(camera):
     for k in ('rgb_coarse', 'acc_coarse', 'depth_coarse'):
         scale = max(1.0, float(want[k].abs().max())) if 'depth' in k else 1.0
         assert float((got[k].cpu() - want[k]).abs().max()) <= 1e-3 * scale, k
+
+
+@pytest.mark.parametrize('s,ndc,white', [(32, False, True), (96, True, False), (64, True, True), (192, False, False)])
+def test_render_forward_entry_point_shapes_and_flags(s, ndc, white):
+    """snerf_render_forward against snerf_mlp_forward + snerf_composite_forward on the same rays: run lengths other than the
+    model's (one run per ray at 32 samples, three at 96), white background, metric and NDC depths, a ray count that fills neither
+    a fold block nor a tile; weights on request equal the compositing kernel's."""
+    if not _has_tc():
+        pytest.skip('tensor path not built')
+    n = 1001
+    cfg = synthetic.make_configs('vanilla')['model']['coarse_mlp']
+    block = MlpBlock(cfg).to(DEV)
+    with torch.no_grad():
+        block.pts_output_linear.weight.mul_(30.0)          # a dense field (SURVEY.md H1): acc ~ 1, depth well conditioned
+        block.pts_output_linear.bias.add_(5.0)
+    b = synthetic.make_ray_batch('llff', n, 9)
+    g = torch.Generator().manual_seed(s)
+    z = torch.sort(torch.rand((n, s), generator=g), -1)[0] if ndc else 1 + 5 * torch.sort(torch.rand((n, s), generator=g), -1)[0]
+    z = cuda(z)
+    rays_o, rays_d, vd = cuda(b['rays_o']), cuda(b['rays_d']), cuda(b['view_dirs'])
+    pts_o, pts_d = (cuda(b['rays_o_ndc']), cuda(b['rays_d_ndc'])) if ndc else (rays_o, rays_d)
+    table = [None if p is None else p.detach() for p in block.param_table()]
+    packed = block.packed(table, force=True)
+    ws = torch.empty(ops.mlp_workspace_bytes(block.desc, n, s, 0), dtype=torch.uint8, device=DEV)
+    sigma, rgb = ops.mlp_forward(block.desc, table, packed, pts_o, pts_d, vd, z, None, ws, 0)
+    want = ops.composite_forward(sigma, rgb, z, rays_o, rays_d, pts_d if ndc else None, ndc, white)
+    got = ops.render_forward(block.desc, table, packed, pts_o, pts_d, vd, z, rays_o, rays_d, ndc, white, want_weights=True)
+    assert set(got) == set(want) - {'visibility'}
+    for k, v in got.items():
+        scale = max(1.0, float(want[k].abs().max()))
+        tol = 1e-4 if 'depth_var' in k else 3e-6
+        assert float((v - want[k]).abs().max()) <= tol * scale, (k, float((v - want[k]).abs().max()), scale)
