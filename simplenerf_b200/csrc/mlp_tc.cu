@@ -254,7 +254,8 @@ __device__ __forceinline__ uint32_t bias_act_bf16x2(float lo, float hi, uint32_t
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
-template <bool kTrace>
+// kSave: training (activation stash + ReLU sign bits); a template parameter so that the epilogue's inner loop carries no test of it
+template <bool kTrace, bool kSave>
 __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -266,7 +267,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
     float* s_misc = (float*)(smem + kOffConst + kConstMisc);
     float* s_part = (float*)(smem + kOffConst + kConstPart);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const bool save = p.stash != nullptr;
+    constexpr bool save = kSave;
+    const int dbg = kTrace ? p.debug : 0;          // stage switches exist in the traced build only
     const uint32_t rank = cluster_rank();
     // roles by warp id -- the sub-partition arbiter issues the highest eligible warp id first, so the latency-critical
     // epilogue warps sit on top and the helpers below them:
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                         for (int c = 0; c < st.n_chunks; ++c, ++cnt) {
                             const uint32_t stage = cnt % kPStages, round = cnt / kPStages;
                             if (round > 0) mbar_wait(&bars->w_empty[stage], (round - 1) & 1);
-                            if (p.debug & 4) { mbar_arrive(&bars->w_full[stage]); continue; }
+                            if (dbg & 4) { mbar_arrive(&bars->w_full[stage]); continue; }
                             mbar_arrive_expect_tx(&bars->w_full[stage], half);
                             bulk_g2s(smem + kOffRing + stage * kPStageBytes, p.packed + st.w_off + (uint32_t)c * bytes + rank * half, half,
                                      &bars->w_full[stage]);
@@ -455,18 +457,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
             tc_fence_after();
             const bool tr = kTrace && p.trace && blockIdx.x == 0 && g == 1 && warp == kWarpEpi0 && lane == 0;
             if (tr) p.trace[(x * 16 + s) * 16 + 2] = clock64();
-            const bool own = j * 64 < st.n_rows && !(p.debug & 2);        // the step has this panel
-            const bool writes_h = ((kind != EPI_VIEW) || save) && !(p.debug & 1);
+            const bool own = j * 64 < st.n_rows && !(dbg & 2);        // the step has this panel
+            const bool writes_h = ((kind != EPI_VIEW) || save) && !(dbg & 1);
             const uint32_t acc_addr = lane_addr + x * 256;
-            const uint32_t dst_row = row_base + x * 65536 + j * kPanelBytes;
-            if (kind == EPI_RELU || kind == EPI_LINEAR) {
+            uint32_t dst_row = row_base + x * 65536 + j * kPanelBytes;
+            asm volatile("" : "+r"(dst_row));       // keep the address in its register: ptxas otherwise re-derives it from the row per store
+            if (kind == EPI_RELU) {
                 // ---- hidden layers and the feature layer: bias (+ReLU) in packed bf16 ----
                 if (own) {
                     uint32_t rr[2][16];
                     uint32_t mw[2] = {0u, 0u};
                     tmem_ld16_issue(acc_addr, rr[0]);
                     const uint4* bb = reinterpret_cast<const uint4*>(s_bias16 + st.bias_row * 256 + j * 64);
-                    const bool relu = kind == EPI_RELU;
+                    constexpr bool relu = true;
                     if (save && jx > 0) mbar_wait(&bars->stash_done[x], (jx - 1) & 1);   // the slot's panels have been copied out
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 const bool valid = pt < p.n_points;
                 const int pan = j >> 1, u0 = 2 * (j & 1);
                 float head[4] = {0.f, 0.f, 0.f, 0.f};
-                if (!(p.debug & 2)) {
+                if (!(dbg & 2)) {
                     const uint32_t vaddr = tmem + ((uint32_t)(q * 32) << 16) + x * 256 + pan * 64 + u0 * 16;
                     uint32_t rr[2][16];
                     tmem_ld16_issue(vaddr, rr[0]);
@@ -887,12 +890,20 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     SNERF_REQUIRE(p.n_points < (1LL << 31), "mlp_forward: more than 2^31 points in one call");
     static bool attr = false;
     if (!attr) {
-        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
-        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
         attr = true;
     }
-    if (p.trace) SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<true>, pair_grid(w.n_tiles), kFwdThreads, kFwdSmem, st, p));
-    else SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<false>, pair_grid(w.n_tiles), kFwdThreads, kFwdSmem, st, p));
+    const int grid = pair_grid(w.n_tiles);
+    if (p.trace) {
+        if (p.stash) SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<true, true>, grid, kFwdThreads, kFwdSmem, st, p));
+        else SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<true, false>, grid, kFwdThreads, kFwdSmem, st, p));
+    } else {
+        if (p.stash) SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<false, true>, grid, kFwdThreads, kFwdSmem, st, p));
+        else SNERF_CUDA_OK(launch_clustered(tc_forward_kernel<false, false>, grid, kFwdThreads, kFwdSmem, st, p));
+    }
     return SNERF_OK;
 }
 

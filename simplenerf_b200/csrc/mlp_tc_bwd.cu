@@ -220,7 +220,7 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
             const TcStep& st = p.steps[s];
             const uint32_t jx = (uint32_t)(g * p.n_steps + s);
             const uint32_t ev = (uint32_t)(g * n_events + pv + s);          // this job's stash event within the slot
-            const bool mask = st.kind == BWD_MASK;
+            constexpr bool mask = true;      // every step of the chain ends in a ReLU mask (the linear feature step is merged away)
             uint2 mw = make_uint2(0u, 0u);                                  // dummy tiles carry zero gradients
             if (mask) {
                 const int tile = tile_of(2 * g + x);
@@ -230,7 +230,8 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
             mbar_wait(&bars->acc_full[x], jx & 1);
             tc_fence_after();
             const uint32_t acc_addr = lane_addr + x * 256;
-            const uint32_t dst_row = row_base + x * 65536 + j * kPanelBytes;
+            uint32_t dst_row = row_base + x * 65536 + j * kPanelBytes;
+            asm volatile("" : "+r"(dst_row));       // keep the address in its register: ptxas otherwise re-derives it from the row per store
             uint32_t rr[2][16];
             tmem_ld16_issue(acc_addr, rr[0]);
             if (ev > 0) mbar_wait(&bars->stash_done[x], (ev - 1) & 1);     // the slot's panels have been copied out
