@@ -16,6 +16,8 @@
 //                              un-rounded activations; in training also the ReLU sign bits for the backward pass
 //   warp 22     MMA issuer (leader CTA: converged warp, one elected lane) / weight relay (peer CTA)
 // Activations never leave the SM in eval mode.
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_plan.cuh"
@@ -638,23 +640,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 }
                 return;
             }
-            // ---- last trunk layer (sigma / rgb head) and the view layer (rgb head): fp32 on the un-rounded activations ----
+            // ---- last trunk layer with the sigma head (1 row) or the sigma + rgb head (4 rows): fp32 on the un-rounded activations ----
             const int tile = tile_of(2 * g + x);
             const long long pt = (long long)tile * kTileRows + row;
             const bool valid = pt < p.n_points;
             float head[4] = {0.f, 0.f, 0.f, 0.f};
-            if (own) {
+            auto head_units = [&](auto nh_tag) {
+                constexpr int NH = decltype(nh_tag)::value;
                 uint32_t rr[2][16];
                 tmem_ld16_issue(acc_addr, rr[0]);
                 if (save && jx > 0) mbar_wait(&bars->stash_done[x], (jx - 1) & 1);
-                const float* vbias = nullptr;
-                if (kind == EPI_VIEW) {
-                    const int ray = valid ? (int)((unsigned)pt / (unsigned)p.n_samples) : 0;   // host guarantees n_points < 2^31
-                    vbias = p.view_bias + (size_t)ray * 128 + j * 64;
-                }
-                const float* wbase = kind == EPI_VIEW ? s_wrgb : s_whead;
-                const int wld = kind == EPI_VIEW ? 128 : 256;
-                const int nh = kind == EPI_RELU_HEAD1 ? 1 : (kind == EPI_VIEW ? 3 : 4);
                 uint32_t mw[2] = {0u, 0u};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -662,28 +657,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     tmem_ld_wait16(rr[u & 1]);
                     if (u + 1 < 4) tmem_ld16_issue(acc_addr + (u + 1) * 16, rr[(u + 1) & 1]);
                     float v[16];
-                    const float4* bb = kind == EPI_VIEW ? reinterpret_cast<const float4*>(vbias + u * 16)
-                                                        : reinterpret_cast<const float4*>(s_bias32 + col0);
+                    const float4* bb = reinterpret_cast<const float4*>(s_bias32 + col0);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 b = kind == EPI_VIEW ? __ldg(bb + i) : bb[i];
+                        const float4 b = bb[i];
                         v[4 * i + 0] = fmaxf(__uint_as_float(rr[u & 1][4 * i + 0]) + b.x, 0.f);
                         v[4 * i + 1] = fmaxf(__uint_as_float(rr[u & 1][4 * i + 1]) + b.y, 0.f);
                         v[4 * i + 2] = fmaxf(__uint_as_float(rr[u & 1][4 * i + 2]) + b.z, 0.f);
                         v[4 * i + 3] = fmaxf(__uint_as_float(rr[u & 1][4 * i + 3]) + b.w, 0.f);
                     }
 #pragma unroll
-                    for (int hh = 0; hh < 4; ++hh) {
-                        if (hh < nh) {
-                            const float4* w = reinterpret_cast<const float4*>(wbase + hh * wld + col0);
-                            float a = head[hh];
+                    for (int hh = 0; hh < NH; ++hh) {
+                        const float4* w = reinterpret_cast<const float4*>(s_whead + hh * 256 + col0);
+                        float a = head[hh];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float4 ww = w[i];
-                                a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
-                            }
-                            head[hh] = a;
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 ww = w[i];
+                            a = fmaf(v[4 * i], ww.x, fmaf(v[4 * i + 1], ww.y, fmaf(v[4 * i + 2], ww.z, fmaf(v[4 * i + 3], ww.w, a))));
                         }
+                        head[hh] = a;
                     }
                     if (writes_h) {
                         uint32_t pk[8];
@@ -691,12 +683,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                         for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
                         sts128(dst_row ^ ((2 * u) << 4), pk[0], pk[1], pk[2], pk[3]);
                         sts128(dst_row ^ ((2 * u + 1) << 4), pk[4], pk[5], pk[6], pk[7]);
-                        if (save && kind != EPI_VIEW) mw[u >> 1] |= relu_bits_unit(pk, u);
+                        if (save) mw[u >> 1] |= relu_bits_unit(pk, u);
                     }
                 }
                 if (writes_h) fence_async_smem();
-                if (save && kind != EPI_VIEW && tile < p.n_tiles)
+                if (save && tile < p.n_tiles)
                     *reinterpret_cast<uint2*>(p.bits + (size_t)tile * kBitsTileBytes + (size_t)st.slot * kBitsSlotBytes + row * 32 + j * 8) = make_uint2(mw[0], mw[1]);
+            };
+            if (own) {
+                if (kind == EPI_RELU_HEAD1) head_units(std::integral_constant<int, 1>{});
+                else head_units(std::integral_constant<int, 4>{});
             }
             tc_fence_before();
             __syncwarp();
@@ -712,17 +708,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
             if (j == 0 && valid) {
-                const int mb = kind == EPI_VIEW ? 4 : 0;
 #pragma unroll
                 for (int jj = 0; jj < 3; ++jj) {
                     const float4 o = *reinterpret_cast<const float4*>(s_part + (jj * 128 + row) * 4);
                     head[0] += o.x; head[1] += o.y; head[2] += o.z; head[3] += o.w;
                 }
-                head[0] += s_misc[mb + 0]; head[1] += s_misc[mb + 1]; head[2] += s_misc[mb + 2]; head[3] += s_misc[mb + 3];
-                if (kind == EPI_VIEW) {
-#pragma unroll
-                    for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[h]);             // :704-707
-                } else {
+                head[0] += s_misc[0]; head[1] += s_misc[1]; head[2] += s_misc[2]; head[3] += s_misc[3];
+                {
                     float nz = 0.f;
                     if (p.noise) nz = p.noise[pt];
                     else if (p.use_rng) nz = p.noise_std * rng_pick(rng_normal4(p.noise_rng, (unsigned long long)pt >> 2), (unsigned long long)pt);
