@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     const int n = ((two && st.n_chunks > kPStages) ? 2 : 1) * st.n_chunks;
                     for (int c = 0; c < n; ++c, ++cnt) {
                         const uint32_t stage = cnt % kPStages;
-                        mbar_wait(&bars->w_full[stage], (cnt / kPStages) & 1);
+                        mbar_wait_spin(&bars->w_full[stage], (cnt / kPStages) & 1);
                         mbar_arrive_cluster(cluster_addr(&bars->w_full[stage], 0));
                     }
                 }

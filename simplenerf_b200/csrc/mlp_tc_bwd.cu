@@ -141,7 +141,7 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
                     const int n = ((two && st.n_chunks > kBStages) ? 2 : 1) * st.n_chunks;
                     for (int c = 0; c < n; ++c, ++cnt) {
                         const uint32_t stage = cnt % kBStages;
-                        mbar_wait(&bars->w_full[stage], (cnt / kBStages) & 1);
+                        mbar_wait_spin(&bars->w_full[stage], (cnt / kBStages) & 1);
                         mbar_arrive_cluster(cluster_addr(&bars->w_full[stage], 0));
                     }
                 }

@@ -80,6 +80,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Spinning wait for a thread with nothing else to do and a hand-off on the critical path (the weight relay of the pair kernels):
+// test_wait never suspends, so the phase flip is seen within a few cycles instead of after the wake-up of a suspended try_wait.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    if (mbar_test_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    int n = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        if ((++n & 1023) == 0 && clock64() - t0 > 4000000000LL) {
+            printf("simplenerf_b200: mbarrier spin timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+
 // Wait used by helper warps (loaders, stash writers, encoders).  mbarrier.try_wait is a hardware-suspended wait (the
 // thread does not burn issue slots while the phase is pending), so no software back-off is wanted: a __nanosleep
 // between probes was measured to add ~1 us (~2000 cycles) to every ring refill -- the sleep granularity is far coarser
