@@ -67,6 +67,8 @@ enum {
 #define SNERF_FLAG_SAVE_FOR_BWD 8u /* MLP forward keeps activations in the workspace             */
 #define SNERF_FLAG_PRECISE 16u     /* fp32 CUDA-core MLP instead of the bf16 tcgen05 MLP         */
 #define SNERF_FLAG_VIS_GRAD 32u    /* snerf_mlp_backward: add what snerf_visibility_backward left in the workspace */
+#define SNERF_FLAG_VIS_HEAD 64u    /* tensor path: snerf_mlp_forward also keeps what the snerf_visibility_* calls read (the view
+                                      layer's point part in bf16, the rays' own direction encodings); ignored by the precise path */
 
 int snerf_abi_version(void);
 const char* snerf_last_error(void);
@@ -169,7 +171,7 @@ int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const* host_para
                        float* const* host_grads, void* workspace, size_t workspace_bytes, int n_rays,
                        int n_samples, uint32_t flags, void* stream);
 
-/* ---- a14 / N4: secondary-view visibility head (predict_visibility=True), precise fp32 path ---------
+/* ---- a14 / N4: secondary-view visibility head (predict_visibility=True) ------------------------------
  * With predict_visibility the reference's views_output_linear has a fourth row (src/models/SimpleNeRF01.py:596-608):
  *   visibility  = sigmoid(row 3 . relu(view layer))                                   (:710-713)
  *   visibility2 = the same with the view layer re-run per OTHER view on [feature | enc_hi | PE(dir2)], dir2 the unit
@@ -178,7 +180,12 @@ int snerf_mlp_backward(const snerf_mlp_desc* desc, const float* const* host_para
  * snerf_mlp_forward(SNERF_FLAG_PRECISE | SNERF_FLAG_SAVE_FOR_BWD) of the same MLP and points left behind, plus their own
  * (snerf_visibility_workspace_bytes).  z is NDC depth with SNERF_FLAG_NDC (converted as :319-321).
  * Backward order within a step: snerf_visibility_backward FIRST (it adds the fourth-row and view-layer gradients to
- * `grads` and leaves d hv / d feature in the MLP workspace), then snerf_mlp_backward(flags | SNERF_FLAG_VIS_GRAD).      */
+ * `grads` and leaves d hv / d feature in the MLP workspace), then snerf_mlp_backward(flags | SNERF_FLAG_VIS_GRAD).
+ * Tensor path (no SNERF_FLAG_PRECISE): the same calls and order on the workspace of snerf_mlp_forward(SNERF_FLAG_VIS_HEAD
+ * [| SNERF_FLAG_SAVE_FOR_BWD]); pass the forward call's flags (plus SNERF_FLAG_NDC) to both visibility calls.  The view
+ * layer's point part W_vf h (+ enc_hi part) is shared by all views and comes from the tcgen05 kernel (bf16); the per-view
+ * direction part (27 x 128 per point and view), the ReLU, the fourth-row dot product and their gradients run on the CUDA
+ * cores in fp32 (vis_tc.cu).  n_other <= 8 there.                                                                        */
 size_t snerf_visibility_workspace_bytes(const snerf_mlp_desc* desc, int n_rays, int n_samples, int n_other);
 int snerf_visibility_forward(const snerf_mlp_desc* desc, const float* const* host_params, const void* mlp_workspace,
                              const float* rays_o, const float* rays_d, const float* z, const float* rays_o2,

@@ -27,7 +27,7 @@ class _RoundBf16(torch.autograd.Function):
 bf = _RoundBf16.apply
 
 
-def mlp_forward_bf16(spec, params, pts, view_dirs, sigma_noise=None):
+def mlp_forward_bf16(spec, params, pts, view_dirs, sigma_noise=None, view_dirs2=None):
     enc = orc.positional_encoding(pts, spec.pts_degree)
     e_bf = bf(enc)
     x = e_bf[:, :spec.trunk_in]
@@ -55,11 +55,22 @@ def mlp_forward_bf16(spec, params, pts, view_dirs, sigma_noise=None):
     n_hi = spec.pts_enc_dim - spec.trunk_in
     venc = orc.positional_encoding(view_dirs, spec.view_degree)
     merged = bf(wv[:, :spec.width] @ params['feature_linear.weight'])
-    pre = (F.linear(x, merged) + F.linear(params['feature_linear.bias'], wv[:, :spec.width])
-           + F.linear(venc, wv[:, spec.width + n_hi:], params['views_linears.0.bias']))
+    pre_pt = F.linear(x, merged)                 # the part every view shares: the tensor core's accumulator
     if n_hi:
-        pre = pre + F.linear(e_bf[:, spec.trunk_in:], bf(wv[:, spec.width:spec.width + n_hi]))
-    hv = F.relu(pre)
-    out['rgb'] = out['rgb_view_dependent'] = torch.sigmoid(
-        F.linear(hv, params['views_output_linear.weight'], params['views_output_linear.bias']))
+        pre_pt = pre_pt + F.linear(e_bf[:, spec.trunk_in:], bf(wv[:, spec.width:spec.width + n_hi]))
+    b_common = F.linear(params['feature_linear.bias'], wv[:, :spec.width]) + params['views_linears.0.bias']
+    w_dir = wv[:, spec.width + n_hi:]
+    hv = F.relu(pre_pt + b_common + F.linear(venc, w_dir))
+    vout = F.linear(hv, params['views_output_linear.weight'], params['views_output_linear.bias'])
+    out['rgb'] = out['rgb_view_dependent'] = torch.sigmoid(vout[..., 0:3])
+    if spec.predict_visibility:
+        # visibility head (vis_tc.cu): the shared accumulator reaches the CUDA-core kernel rounded to bf16, the per-view
+        # direction part, the ReLU and the fourth row are fp32 (own view and other views alike)
+        w_vis, b_vis = params['views_output_linear.weight'][3:4], params['views_output_linear.bias'][3:4]
+        shared = bf(pre_pt) + b_common
+        out['visibility'] = torch.sigmoid(F.linear(F.relu(shared + F.linear(venc, w_dir)), w_vis, b_vis))
+        if view_dirs2 is not None:
+            venc2 = orc.positional_encoding(view_dirs2, spec.view_degree)                     # [P, nf-1, 27]
+            hv2 = F.relu(shared[:, None, :] + F.linear(venc2, w_dir))
+            out['visibility2'] = torch.sigmoid(F.linear(hv2, w_vis, b_vis))
     return out

@@ -13,7 +13,7 @@ LIB_DBG_PATH = os.path.join(PKG, 'libsimplenerf_b200_dbg.so')
 
 P_COUNT = 24
 P_HEAD_W, P_HEAD_B, P_FEAT_W, P_FEAT_B, P_VIEW_W, P_VIEW_B, P_RGB_W, P_RGB_B = 16, 17, 18, 19, 20, 21, 22, 23
-FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP, FLAG_SAVE_FOR_BWD, FLAG_PRECISE, FLAG_VIS_GRAD = 1, 2, 4, 8, 16, 32
+FLAG_NDC, FLAG_WHITE_BKGD, FLAG_LINDISP, FLAG_SAVE_FOR_BWD, FLAG_PRECISE, FLAG_VIS_GRAD, FLAG_VIS_HEAD = 1, 2, 4, 8, 16, 32, 64
 
 
 class MlpDesc(C.Structure):

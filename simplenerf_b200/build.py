@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libsimplenerf_b200.so')
 LIB_DBG = os.path.join(PKG, 'libsimplenerf_b200_dbg.so')
-SOURCES = ['api.cu', 'sampling.cu', 'composite.cu', 'mlp_simt.cu', 'mlp_tc.cu', 'mlp_tc_bwd.cu', 'adam.cu', 'raygen.cu', 'losses.cu', 'gather.cu']
+SOURCES = ['api.cu', 'sampling.cu', 'composite.cu', 'mlp_simt.cu', 'mlp_tc.cu', 'mlp_tc_bwd.cu', 'vis_tc.cu', 'adam.cu', 'raygen.cu', 'losses.cu', 'gather.cu']
 # developer library: the product sources compiled with -DSNERF_DEBUG (snerfdbg_* entry points: clock64 traces, stage
 # switches, descriptor probe) plus the stand-alone probe kernels -- kept out of the product library
 DEBUG_SOURCES = SOURCES + ['tmem_bench.cu', 'pair_probe.cu', 'store_probe.cu']

@@ -189,10 +189,12 @@ extern "C" int snerf_visibility_forward(const snerf_mlp_desc* desc, const float*
     if (rc != SNERF_OK) return rc;
     SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_other >= 0, "snerf_visibility_forward: bad sizes");
     if (n_rays == 0) return SNERF_OK;
-    if (!(flags & SNERF_FLAG_PRECISE)) return fail(SNERF_ERR_UNSUPPORTED, "snerf_visibility_forward: built on the precise (fp32) path only");
     SNERF_REQUIRE(desc->view_width > 0 && desc->view_degree > 0, "snerf_visibility_forward: the MLP has no view branch");
     SNERF_REQUIRE(mlp_workspace && rays_o && rays_d && z && visibility && workspace, "snerf_visibility_forward: null pointer");
     SNERF_REQUIRE(n_other == 0 || (rays_o2 && visibility2), "snerf_visibility_forward: rays_o2 / visibility2 needed for %d other views", n_other);
+    if (!(flags & SNERF_FLAG_PRECISE))      // tensor path: everything it needs sits in the MLP workspace (SNERF_FLAG_VIS_HEAD)
+        return tc_visibility_forward(*desc, host_params, mlp_workspace, rays_o, rays_d, z, rays_o2, visibility, visibility2, n_rays,
+                                     n_samples, n_other, flags, (cudaStream_t)stream);
     return simt_visibility_forward(*desc, host_params, mlp_workspace, rays_o, rays_d, z, rays_o2, visibility, visibility2, workspace,
                                    workspace_bytes, n_rays, n_samples, n_other, flags, (cudaStream_t)stream);
 }
@@ -211,11 +213,13 @@ extern "C" int snerf_visibility_backward(const snerf_mlp_desc* desc, const float
     if (rc != SNERF_OK) return rc;
     SNERF_REQUIRE(n_rays >= 0 && n_samples >= 1 && n_other >= 0, "snerf_visibility_backward: bad sizes");
     if (n_rays == 0) return SNERF_OK;
-    if (!(flags & SNERF_FLAG_PRECISE)) return fail(SNERF_ERR_UNSUPPORTED, "snerf_visibility_backward: built on the precise (fp32) path only");
     SNERF_REQUIRE(flags & SNERF_FLAG_SAVE_FOR_BWD, "snerf_visibility_backward: the forward must have run with SNERF_FLAG_SAVE_FOR_BWD");
     SNERF_REQUIRE(desc->view_width > 0 && desc->view_degree > 0, "snerf_visibility_backward: the MLP has no view branch");
     SNERF_REQUIRE(mlp_workspace && rays_o && rays_d && z && visibility && workspace, "snerf_visibility_backward: null pointer");
     SNERF_REQUIRE(n_other == 0 || (rays_o2 && visibility2), "snerf_visibility_backward: rays_o2 / visibility2 needed");
+    if (!(flags & SNERF_FLAG_PRECISE))
+        return tc_visibility_backward(*desc, host_params, mlp_workspace, rays_o, rays_d, z, rays_o2, visibility, visibility2, d_visibility,
+                                      d_visibility2, host_grads, n_rays, n_samples, n_other, flags, (cudaStream_t)stream);
     return simt_visibility_backward(*desc, host_params, mlp_workspace, rays_o, rays_d, z, rays_o2, visibility, visibility2, d_visibility,
                                     d_visibility2, host_grads, workspace, workspace_bytes, n_rays, n_samples, n_other, flags,
                                     (cudaStream_t)stream);

@@ -108,6 +108,14 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
                 const float* d_sigma, const float* d_rgb, float* const* grads, void* ws, size_t ws_bytes,
                 int n_rays, int n_samples, uint32_t flags, cudaStream_t st);
 int tc_selftest(float* host_max_err, cudaStream_t st);
+// vis_tc.cu : visibility head on the workspace of a tensor-path forward with SNERF_FLAG_VIS_HEAD
+int tc_visibility_forward(const snerf_mlp_desc& d, const float* const* prm, const void* mlp_ws, const float* rays_o,
+                          const float* rays_d, const float* z, const float* rays_o2, float* visibility, float* visibility2,
+                          int n_rays, int n_samples, int n_other, uint32_t flags, cudaStream_t st);
+int tc_visibility_backward(const snerf_mlp_desc& d, const float* const* prm, void* mlp_ws, const float* rays_o,
+                           const float* rays_d, const float* z, const float* rays_o2, const float* visibility,
+                           const float* visibility2, const float* d_visibility, const float* d_visibility2,
+                           float* const* grads, int n_rays, int n_samples, int n_other, uint32_t flags, cudaStream_t st);
 // fused evaluation (row X1): MLP forward with the compositing arithmetic in its head epilogue + the per-ray fold
 struct FusedComposite {
     const float *rays_o, *rays_d;     // camera rays (NDC depth conversion)

@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restri
                                                            float* __restrict__ vb, int n_rays,
                                                            int view_degree, int view_in, int col0, int venc,
                                                            const float* __restrict__ pts_d, const float* __restrict__ cam_o,
-                                                           const float* __restrict__ cam_d, float4* __restrict__ rayc) {
+                                                           const float* __restrict__ cam_d, float4* __restrict__ rayc,
+                                                           float* __restrict__ view_enc) {
     const int ray0 = blockIdx.x * kVbRays;
     // fused evaluation: the per-ray constants of the compositing arithmetic -- |d| (:436 / :441) and, for NDC depths, the two
     // factors of convert_depth_from_ndc (:498, :501), with composite.cu's expressions
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(128) tc_view_bias_kernel(const float* __restri
             }
         }
         ve[r][idx] = val;
+        if (view_enc != nullptr && ray < n_rays) view_enc[(size_t)ray * 32 + idx] = val;     // visibility head: PE(view_dir) per ray (vis_tc.cu)
     }
     __syncthreads();
     const int o = threadIdx.x;
@@ -217,6 +219,7 @@ struct FwdParams {
     int ndc;
     uint8_t* stash;                // null in eval
     uint8_t* bits;                 // (training) ReLU sign bits of the trunk activations, kBitsTileBytes per tile
+    uint8_t* vis_pre;              // (visibility head, SNERF_FLAG_VIS_HEAD) bf16 [n_points,128]: the view layer's accumulator without the per-ray bias; else null
     long long* trace;              // debug: clock64 timestamps of pair 0 (tools/trace_fwd.py), normally null
     int debug;                     // debug (timing experiments, results become garbage): bit0 no panel stores, bit1 no TMEM loads / epilogue math, bit2 no weight copies
     long long n_points;
@@ -530,6 +533,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     const uint32_t rx = (uint32_t)row & 7u;
                     tmem_ld_wait16(rr[0]);
                     tmem_ld_wait16(rr[1]);
+                    if (p.vis_pre != nullptr && valid) {
+                        // visibility head: the point part of the view layer (shared by every view, :691-695) leaves in bf16;
+                        // this thread holds columns 32 j .. 32 j + 31 of its row
+                        uint4* vp = reinterpret_cast<uint4*>(p.vis_pre + (size_t)pt * 256 + j * 64);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            vp[2 * k] = make_uint4(pack_bf16(__uint_as_float(rr[k][0]), __uint_as_float(rr[k][1])), pack_bf16(__uint_as_float(rr[k][2]), __uint_as_float(rr[k][3])),
+                                                   pack_bf16(__uint_as_float(rr[k][4]), __uint_as_float(rr[k][5])), pack_bf16(__uint_as_float(rr[k][6]), __uint_as_float(rr[k][7])));
+                            vp[2 * k + 1] = make_uint4(pack_bf16(__uint_as_float(rr[k][8]), __uint_as_float(rr[k][9])), pack_bf16(__uint_as_float(rr[k][10]), __uint_as_float(rr[k][11])),
+                                                       pack_bf16(__uint_as_float(rr[k][12]), __uint_as_float(rr[k][13])), pack_bf16(__uint_as_float(rr[k][14]), __uint_as_float(rr[k][15])));
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const int col0 = pan * 64 + (u0 + k) * 16;
@@ -852,7 +867,8 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
                                                     (const float*)((const uint8_t*)packed + align_up(pl.packed_bytes, 1024)) + 128 * 256,
                                                     (float*)(wsb + w.view_bias), n_rays, d.view_degree, m.view_in, m.width + m.enc_hi, m.venc,
                                                     rays_d, fused ? fused->cam_o : nullptr, fused ? fused->cam_d : nullptr,
-                                                    fused ? (float4*)(wsb + w.view_bias + (size_t)n_rays * 128 * sizeof(float)) : nullptr);
+                                                    fused ? (float4*)(wsb + w.view_bias + (size_t)n_rays * 128 * sizeof(float)) : nullptr,
+                                                    (flags & SNERF_FLAG_VIS_HEAD) ? (float*)(wsb + w.view_enc) : nullptr);
         SNERF_LAUNCH_OK("tc_view_bias_kernel");
     }
     FwdParams p{};
@@ -870,6 +886,7 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     }
     p.stash = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.act : nullptr;
     p.bits = (flags & SNERF_FLAG_SAVE_FOR_BWD) ? wsb + w.bits : nullptr;
+    p.vis_pre = ((flags & SNERF_FLAG_VIS_HEAD) && m.has_view) ? wsb + w.vis_pre : nullptr;
     if (fused) {
         p.seg = fused->seg; p.alpha_out = fused->alpha; p.wloc = fused->wloc; p.ndc = fused->cam_o != nullptr ? 1 : 0;
         p.rayc = (const float4*)(wsb + w.view_bias + (size_t)n_rays * 128 * sizeof(float));

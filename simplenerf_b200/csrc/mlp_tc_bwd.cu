@@ -47,6 +47,7 @@ struct BwdParams {
     const uint8_t* bits;          // ReLU sign bits written by the forward kernel (kBitsTileBytes per tile)
     RingCtl ring;                 // destination of the gradient panels
     const float *sigma, *rgb, *d_sigma, *d_rgb, *w_rgb;
+    const float* vis_extra;        // (SNERF_FLAG_VIS_GRAD) fp32 [n_points,128]: the visibility head's share of dY_v, masks applied (vis_tc.cu); else null
     long long n_points;
     int n_tiles, n_steps, has_view;
     int n_pairs;                  // CTA pairs running the chain
@@ -69,6 +70,8 @@ struct BwdBars {
     uint32_t tmem_base;
 };
 
+// kVis: the prologue adds the visibility head's share of dY_v (a template parameter: the plain kernel keeps its registers)
+template <bool kVis>
 __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, const int pair_index) {
     BwdBars* bars = (BwdBars*)(smem + kBOffBars);
     float* s_wrgb = (float*)(smem + kBOffConst);
@@ -310,6 +313,11 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
                             const uint32_t bits = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFFu);
                             dv[e] = bits != 0u ? d : 0.f;
                         }
+                        if (kVis && pt < p.n_points) {      // fourth row of the view head, own and other views (:646-649, :710-713)
+                            const float4* ex = reinterpret_cast<const float4*>(p.vis_extra + (size_t)pt * 128 + 8 * i);
+                            const float4 a = __ldg(ex), b = __ldg(ex + 1);
+                            dv[0] += a.x; dv[1] += a.y; dv[2] += a.z; dv[3] += a.w; dv[4] += b.x; dv[5] += b.y; dv[6] += b.z; dv[7] += b.w;
+                        }
                         *reinterpret_cast<uint4*>(pb + (i >> 3) * kPanelBytes + swz_offset(row, i & 7)) =
                             make_uint4(pack_bf16(dv[0], dv[1]), pack_bf16(dv[2], dv[3]), pack_bf16(dv[4], dv[5]), pack_bf16(dv[6], dv[7]));
                     }
@@ -420,9 +428,10 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
 }
 
 // the chain alone (two-kernel form)
+template <bool kVis>
 __global__ void __launch_bounds__(kBwdThreads, 1) tc_dgrad_kernel(const __grid_constant__ BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    dgrad_role(p, smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u), (int)blockIdx.x / 2);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
+    dgrad_role<kVis>(p, smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u), (int)blockIdx.x / 2);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
 }
 
 // =================================================================================================
@@ -826,7 +835,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_backward_kernel(const __gri
     const bool chain = wp.spread ? (int)((long long)(c + 1) * bp.n_pairs / nc) > before : c < bp.n_pairs;
     if (chain) {
         if (wp.debug & 16) return;                        // debug bit 4: weight-gradient jobs alone (timing experiments)
-        dgrad_role(bp, smem, before);
+        dgrad_role<false>(bp, smem, before);
     } else {
         if (wp.debug & 8) return;                         // debug bit 3: chain alone
         wgrad_role(wp, smem, 2 * (c - before) + ((int)blockIdx.x & 1));
@@ -956,13 +965,19 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
     bp.packed = (const uint8_t*)packed; bp.act = wsb + w.act; bp.bits = wsb + w.bits;
     bp.sigma = sigma; bp.rgb = rgb; bp.d_sigma = d_sigma; bp.d_rgb = d_rgb;
     bp.w_rgb = m.has_view ? prm[SNERF_P_RGB_W] : nullptr;
+    if (flags & SNERF_FLAG_VIS_GRAD) {
+        SNERF_REQUIRE((flags & SNERF_FLAG_VIS_HEAD) && m.has_view, "mlp_backward: SNERF_FLAG_VIS_GRAD on the tensor path needs the forward's SNERF_FLAG_VIS_HEAD");
+        SNERF_REQUIRE(!fused, "mlp_backward: SNERF_FLAG_VIS_GRAD is not built for the one-launch form (unset SNERF_BWD_RING)");
+        bp.vis_extra = (const float*)(wsb + w.vis_extra);
+    }
     bp.n_points = P; bp.n_tiles = w.n_tiles; bp.n_steps = pl.n_bwd; bp.has_view = m.has_view ? 1 : 0;
     bp.n_pairs = n_pairs;
     bp.tile_stash_bytes = pl.tile_stash_bytes;
     for (int s = 0; s < pl.n_bwd; ++s) bp.steps[s] = pl.bwd[s];
     static bool attr = false;
     if (!attr) {
-        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+        SNERF_CUDA_OK(cudaFuncSetAttribute(tc_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
         SNERF_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
         SNERF_CUDA_OK(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
         attr = true;
@@ -1105,7 +1120,8 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
         SNERF_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_backward_kernel, bp, wp));
         return unmerge();
     }
-    SNERF_CUDA_OK(launch_clustered(tc_dgrad_kernel, 2 * n_pairs, kBwdThreads, kBwdSmem, st, bp));
+    if (bp.vis_extra) SNERF_CUDA_OK(launch_clustered(tc_dgrad_kernel<true>, 2 * n_pairs, kBwdThreads, kBwdSmem, st, bp));
+    else SNERF_CUDA_OK(launch_clustered(tc_dgrad_kernel<false>, 2 * n_pairs, kBwdThreads, kBwdSmem, st, bp));
     if (g_split_event) cudaEventRecord(g_split_event, st);
     tc_wgrad_kernel<<<num_sms(), kWgThreads, kWgSmem, st>>>(wp);
     SNERF_LAUNCH_OK("tc_wgrad_kernel");

@@ -193,6 +193,7 @@ constexpr uint32_t kBitsTileBytes = 8 * kBitsSlotBytes;   // trunk layers 0..7
 
 struct TcWorkspace {
     size_t view_bias, act, dy, bits, flags, merged_grad, total;
+    size_t vis_pre, view_enc, vis_extra;   // SNERF_FLAG_VIS_HEAD only (vis_tc.cu)
     int n_tiles;
     uint32_t ring_cap;
 };
@@ -291,6 +292,19 @@ static inline TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n
         off += align_up((size_t)(1 + kRingConsumers) * kDySlots * w.ring_cap * sizeof(uint32_t), 1024);
         w.merged_grad = off;          // fp32 [128 x view_in] + [128]: dY_v^T [h | encodings] and the column sums of dY_v
         off += align_up(m.has_view ? (size_t)(128 * m.view_in + 128) * sizeof(float) : 0, 1024);
+    }
+    if (flags & SNERF_FLAG_VIS_HEAD) {
+        // visibility head on the tensor path: the view layer's point part per point (bf16 [P,128], written by the forward
+        // kernel's view-step epilogue), PE(view_dir) per ray (fp32 [n_rays,32], written by tc_view_bias_kernel) and, for the
+        // backward pass, the head's contribution to dY_v (fp32 [P,128], written by tc_vis_kernel, added by the dgrad prologue)
+        w.vis_pre = off;
+        off += align_up((size_t)P * 128 * 2, 1024);
+        w.view_enc = off;
+        off += align_up((size_t)n_rays * 32 * sizeof(float), 1024);
+        if (flags & SNERF_FLAG_SAVE_FOR_BWD) {
+            w.vis_extra = off;
+            off += align_up((size_t)P * 128 * sizeof(float), 1024);
+        }
     }
     w.total = off + 1024;
     return w;

@@ -26,7 +26,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .. import ops
-from .._lib import (FLAG_NDC, FLAG_PRECISE, FLAG_SAVE_FOR_BWD, FLAG_VIS_GRAD, FLAG_WHITE_BKGD, MlpDesc, P_COUNT, P_FEAT_B, P_FEAT_W,
+from .._lib import (FLAG_NDC, FLAG_PRECISE, FLAG_SAVE_FOR_BWD, FLAG_VIS_GRAD, FLAG_VIS_HEAD, FLAG_WHITE_BKGD, MlpDesc, P_COUNT, P_FEAT_B, P_FEAT_W,
                     P_HEAD_B, P_HEAD_W, P_RGB_B, P_RGB_W, P_VIEW_B, P_VIEW_W)
 
 _SLOTS = (   # attribute (reference :22-41), path in configs['model'], output-key prefix, level
@@ -190,6 +190,8 @@ class _RenderStream(torch.autograd.Function):
         ndc, white = opts['ndc'], opts['white_bkgd']
         need_grad = opts['need_grad']
         flags = (FLAG_PRECISE if opts['precise'] else 0) | (FLAG_SAVE_FOR_BWD if need_grad else 0)
+        if block.predict_visibility and not opts['precise']:
+            flags |= FLAG_VIS_HEAD            # tensor path: the forward kernel also leaves what the visibility head reads (vis_tc.cu)
         n, s = z.shape
         table: List[Optional[torch.Tensor]] = [None] * P_COUNT
         it = iter(params)
@@ -299,9 +301,6 @@ class FusedSimpleNeRF(torch.nn.Module):
         self.precision = mc.get('precision', 'bf16')
         if self.precision not in ('bf16', 'fp32'):
             raise ValueError(f"configs['model']['precision'] must be 'bf16' or 'fp32', got {self.precision!r}")
-        if self.predict_visibility and self.precision != 'fp32':
-            raise NotImplementedError("predict_visibility=True (secondary-view visibility head, SURVEY row a14 / N4) is built on the "
-                                      "fp32 path only: set configs['model']['precision'] = 'fp32' (every shipped config has it False)")
         self.launch_rays = int(mc.get('launch_rays', 65536))
         self.fused_composite = bool(mc.get('fused_composite', True))   # evaluation: MLP + compositing in one pass (row X1)
         rng = mc.get('rng', 'device')

@@ -272,15 +272,18 @@ def mlp_backward(desc: MlpDesc, params, packed, rays_o, rays_d, view_dirs, z, si
 
 
 def visibility_forward(desc: MlpDesc, params, mlp_workspace, rays_o, rays_d, z, rays_o2, flags: int):
-    """Secondary-view visibility head on the workspace of a precise-path `mlp_forward` (row a14 / N4; reference
-    :317-325, :640-649, :687-715).  rays_o2 [N, nf-1, 3] or None.  -> visibility [N,S], visibility2 [N,S,nf-1] or None, workspace."""
+    """Secondary-view visibility head on the workspace of the same MLP's `mlp_forward` (row a14 / N4; reference :317-325,
+    :640-649, :687-715): precise path, or tensor path with FLAG_VIS_HEAD in the forward's flags -- pass those flags (+ FLAG_NDC).
+    rays_o2 [N, nf-1, 3] or None.  -> visibility [N,S], visibility2 [N,S,nf-1] or None, workspace."""
     n, s = z.shape
     n_other = 0 if rays_o2 is None else rays_o2.shape[1]
     rays_o2 = None if rays_o2 is None else _f32(rays_o2)
     vis = torch.empty((n, s), device=z.device)
     vis2 = torch.empty((n, s, n_other), device=z.device) if n_other else None
-    ws = torch.empty(_lib.load().snerf_visibility_workspace_bytes(C.byref(desc), n, s, n_other), dtype=torch.uint8, device=z.device)
-    LAUNCHES['count'] += 3 + 3 * n_other
+    # the tensor path keeps everything in the MLP workspace; the precise path has buffers of its own
+    nbytes = _lib.load().snerf_visibility_workspace_bytes(C.byref(desc), n, s, n_other) if flags & FLAG_PRECISE else 256
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+    LAUNCHES['count'] += (3 + 3 * n_other) if flags & FLAG_PRECISE else 1
     _lib.check(_lib.load().snerf_visibility_forward(
         C.byref(desc), pointer_table(params), _ptr(mlp_workspace, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(z), _ptr(rays_o2),
         _ptr(vis), _ptr(vis2), _ptr(ws, torch.uint8), ws.numel(), n, s, n_other, flags, _stream()), 'snerf_visibility_forward')
@@ -294,7 +297,7 @@ def visibility_backward(desc: MlpDesc, params, mlp_workspace, rays_o, rays_d, z,
     n, s = z.shape
     n_other = 0 if rays_o2 is None else rays_o2.shape[1]
     rays_o2 = None if rays_o2 is None else _f32(rays_o2)
-    LAUNCHES['count'] += 4 + 7 * n_other
+    LAUNCHES['count'] += (4 + 7 * n_other) if flags & FLAG_PRECISE else 1
     _lib.check(_lib.load().snerf_visibility_backward(
         C.byref(desc), pointer_table(params), _ptr(mlp_workspace, torch.uint8), _ptr(rays_o), _ptr(rays_d), _ptr(z), _ptr(rays_o2),
         _ptr(vis), _ptr(vis2), _ptr(None if d_vis is None else _f32(d_vis)), _ptr(None if d_vis2 is None else _f32(d_vis2)),

@@ -74,9 +74,13 @@ def test_cpu_batch_is_refused_loudly():
 
 def test_unbuilt_features_raise():
     cfg = synthetic.make_configs('vanilla')
-    cfg['model']['coarse_mlp']['predict_visibility'] = True
+    cfg['model']['coarse_mlp']['views_net_depth'] = 2
     with pytest.raises(NotImplementedError):
         get_model(cfg, None)
+    cfg = synthetic.make_configs('vanilla')
+    cfg['model']['coarse_mlp']['predict_visibility'] = True          # row a14 / N4: built on both paths
+    model = get_model(cfg, None)
+    assert tuple(model.coarse_model.views_output_linear.weight.shape) == (4, 128) and model.predict_visibility
 
 
 def test_synthetic_rays_match_reference_geometry():
