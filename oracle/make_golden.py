@@ -30,7 +30,11 @@ from simplenerf_b200 import synthetic                             # noqa: E402
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 GRAD_KEYS = ('rgb_coarse', 'rgb_fine', 'depth_coarse', 'depth_fine',
              'points_augmentation_rgb_coarse', 'points_augmentation_depth_coarse',
-             'views_augmentation_rgb_coarse', 'views_augmentation_depth_coarse')
+             'views_augmentation_rgb_coarse', 'views_augmentation_depth_coarse',
+             # fine-level augmentation models (:234-263): present only in the 'simplenerf_fineaug' fixture; appended, so the
+             # cotangents of the older fixtures are drawn exactly as before
+             'points_augmentation_rgb_fine', 'points_augmentation_depth_fine',
+             'views_augmentation_rgb_fine', 'views_augmentation_depth_fine')
 
 
 def full_state(configs, seed, dense=False):
@@ -219,3 +223,4 @@ if __name__ == '__main__':
     golden_render('render_llff_simplenerf_dense.npz', 'simplenerf', True, 'llff', 12, True, 1022)
     golden_render('render_re10k_vanilla_dense.npz', 'vanilla', True, 're10k', 12, True, 21)
     golden_render('render_nondc_vanilla_dense.npz', 'vanilla', False, 'llff', 12, True, 33)
+    golden_render('render_llff_fineaug_dense.npz', 'simplenerf_fineaug', True, 'llff', 12, True, 1023)

@@ -15,6 +15,11 @@ from . import _lib
 from ._lib import FLAG_LINDISP, FLAG_NDC, FLAG_PRECISE, FLAG_SAVE_FOR_BWD, FLAG_VIS_GRAD, FLAG_WHITE_BKGD, MlpDesc, P_COUNT  # noqa: F401
 
 
+# torch.cuda.current_device() without its lazy-init checks (the tensors checked below are CUDA tensors, so CUDA is up): _ptr runs
+# ~650 times per training step
+_current_device = getattr(torch._C, '_cuda_getDevice', torch.cuda.current_device)
+
+
 def _ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
     if t is None:
         return None
@@ -22,7 +27,7 @@ def _ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
         raise RuntimeError('simplenerf_b200 kernels need CUDA tensors (no CPU fallback exists)')
     if t.dtype != dtype or not t.is_contiguous():
         raise RuntimeError(f'expected a contiguous {dtype} tensor, got {t.dtype}, contiguous={t.is_contiguous()}')
-    if t.device.index != torch.cuda.current_device():
+    if t.device.index != _current_device():
         # the launch goes to the CURRENT device's stream (_stream): a tensor of another device would hand the kernel a
         # foreign pointer.  The drop-in's forward / backward select the batch's device; direct callers must do the same.
         raise RuntimeError(f'tensor lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}: '

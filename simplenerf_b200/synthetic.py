@@ -31,12 +31,13 @@ def _main_mlp(num_samples: int) -> dict:
 
 
 def make_configs(kind: str = 'simplenerf', ndc: bool = True, device=None) -> dict:
-    """``kind``: 'simplenerf' (4 MLPs, the shipped train1021 model block) or 'vanilla'
-    (coarse + fine only: the same block with the two augmentation keys removed)."""
+    """``kind``: 'simplenerf' (4 MLPs, the shipped train1021 model block), 'vanilla' (coarse + fine only: the same
+    block with the two augmentation keys removed) or 'simplenerf_fineaug' (6 MLPs: the augmentation models also at
+    the fine level, src/models/SimpleNeRF01.py:234-263 -- no shipped config enables them)."""
     model = dict(name='FusedSimpleNeRF01', coarse_mlp=_main_mlp(64), fine_mlp=_main_mlp(128),
                  chunk=4096, lindisp=False, netchunk=16384, perturb=True, raw_noise_std=1.0,
                  white_bkgd=False)
-    if kind == 'simplenerf':
+    if kind in ('simplenerf', 'simplenerf_fineaug'):
         pa = _main_mlp(64)
         del pa['num_samples']
         pa['points_sigma_positional_encoding_degree'] = 3
@@ -46,6 +47,9 @@ def make_configs(kind: str = 'simplenerf', ndc: bool = True, device=None) -> dic
         va['view_dependent_rgb'] = False
         model['points_augmentation'] = dict(coarse_mlp=pa)
         model['views_augmentation'] = dict(coarse_mlp=va)
+        if kind == 'simplenerf_fineaug':
+            model['points_augmentation']['fine_mlp'] = dict(pa)
+            model['views_augmentation']['fine_mlp'] = dict(va)
     elif kind != 'vanilla':
         raise ValueError(kind)
     return dict(data_loader=dict(ndc=ndc), model=model, device=[0] if device is None else device)

@@ -13,6 +13,7 @@ RENDER_CASES = {
     'render_llff_simplenerf_dense.npz': ('simplenerf', True, 'llff'),
     'render_re10k_vanilla_dense.npz': ('vanilla', True, 're10k'),
     'render_nondc_vanilla_dense.npz': ('vanilla', False, 'llff'),
+    'render_llff_fineaug_dense.npz': ('simplenerf_fineaug', True, 'llff'),       # fine-level augmentation MLPs (row N4)
 }
 
 
