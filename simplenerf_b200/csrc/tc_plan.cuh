@@ -296,7 +296,7 @@ static inline TcWorkspace tc_ws_layout(const MlpDims& m, const TcPlan& pl, int n
     if (flags & SNERF_FLAG_VIS_HEAD) {
         // visibility head on the tensor path: the view layer's point part per point (bf16 [P,128], written by the forward
         // kernel's view-step epilogue), PE(view_dir) per ray (fp32 [n_rays,32], written by tc_view_bias_kernel) and, for the
-        // backward pass, the head's contribution to dY_v (fp32 [P,128], written by tc_vis_kernel, added by the dgrad prologue)
+        // backward pass, the head's contribution to dY_v (fp32 [P,128], written by tc_vis_bwd_kernel, added by the dgrad prologue)
         w.vis_pre = off;
         off += align_up((size_t)P * 128 * 2, 1024);
         w.view_enc = off;
