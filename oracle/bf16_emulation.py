@@ -2,8 +2,9 @@
 
 Same algorithm as ``oracle.nerf_oracle.mlp_forward`` (reference src/models/SimpleNeRF01.py:626-715) with
 bf16 rounding applied exactly where the tcgen05 kernels round: the encoded points and every hidden activation
-that feed a tensor-core GEMM, and the weights of those GEMMs.  Heads (sigma, rgb) and the view-direction part of
-the view layer stay fp32, as in the kernels.  feature_linear has no activation (:691-697), and the kernels multiply the
+that feed a tensor-core GEMM, and the weights of those GEMMs.  The rgb head and the view-direction part of the view layer stay
+fp32, as in the kernels; the sigma head of an MLP with a view branch is one more row of the view step's tensor-core product
+(bf16 row, bf16 activation), that of an MLP without one is an fp32 dot product on the un-rounded activation.  feature_linear has no activation (:691-697), and the kernels multiply the
 last trunk activation by the merged matrix  W_view[:, :256] @ W_feat  (formed in fp32, rounded to bf16 once; the feature
 bias reaches the view layer in fp32): the feature vector itself is never formed, so it is not rounded here either.  Rounding is straight-through in the
 backward pass, so autograd yields the gradient the kernels are expected to produce (it
@@ -34,16 +35,21 @@ def mlp_forward_bf16(spec, params, pts, view_dirs, sigma_noise=None, view_dirs2=
     h32 = None
     for i in range(spec.depth):
         acc = F.linear(x, bf(params[f'pts_linears.{i}.weight']))
-        if i < spec.depth - 1:
-            # hidden layers: packed epilogue, HFMA2.BF16.RELU(bf16(acc), 1, bf16(bias)) = one rounding of the sum
+        if i < spec.depth - 1 or spec.view_dep_rgb:
+            # hidden layers (and the last trunk layer of an MLP with a view branch): packed epilogue,
+            # HFMA2.BF16.RELU(bf16(acc), 1, bf16(bias)) = one rounding of the sum
             h32 = F.relu(bf(bf(acc) + bf(params[f'pts_linears.{i}.bias'])))
         else:
-            # last trunk layer: fp32 epilogue (its un-rounded output feeds the fp32 sigma head)
+            # last trunk layer without a view branch: fp32 epilogue (its un-rounded output feeds the fp32 sigma + rgb head)
             h32 = F.relu(acc + params[f'pts_linears.{i}.bias'])
         x = bf(h32)
         if i in spec.skips:
             x = torch.cat([e_bf[:, :spec.trunk_in], x], -1)
-    head = F.linear(h32, params['pts_output_linear.weight'], params['pts_output_linear.bias'])
+    if spec.view_dep_rgb:
+        # the sigma row rides the view step of the tensor core: bf16 row times the bf16 activation, fp32 accumulation and bias
+        head = F.linear(x, bf(params['pts_output_linear.weight'])) + params['pts_output_linear.bias']
+    else:
+        head = F.linear(h32, params['pts_output_linear.weight'], params['pts_output_linear.bias'])
     sigma = head[..., 0:1]
     if sigma_noise is not None:
         sigma = sigma + sigma_noise

@@ -12,8 +12,10 @@
 //   warp 5      weight loader  this CTA's half of every packed bf16 weight chunk, L2 -> smem ring by bulk async copy
 //   warps 6-21  epilogue       TMEM -> regs -> bias/ReLU -> bf16 -> swizzled smem panel (the next layer's A operand);
 //                              four warps per SM sub-partition, one 64-column panel each; hidden layers use one packed
-//                              HFMA2.BF16.RELU per value pair, the sigma / rgb heads are fp32 dot products on the
-//                              un-rounded activations; in training also the ReLU sign bits for the backward pass
+//                              HFMA2.BF16.RELU per value pair; the rgb head (and the sigma + rgb head of an MLP without a
+//                              view branch) are fp32 dot products on the un-rounded activations, the sigma head of an MLP
+//                              with a view branch is accumulator column 128 of the view step (tc_plan.cuh); in training
+//                              also the ReLU sign bits for the backward pass
 //   warp 22     MMA issuer (leader CTA: converged warp, one elected lane) / weight relay (peer CTA)
 // Activations never leave the SM in eval mode.
 #include <type_traits>
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ Pa
     const int total = c.n_rows * 8;   // one thread per 16-byte chunk (8 bf16)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int n = i >> 3, ch = i & 7;
+        const bool has_src = n < c.src_rows;
         uint32_t w[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ Pa
             for (int e = 0; e < 2; ++e) {
                 const int kk = ch * 8 + h * 2 + e;
                 float v = 0.f;
-                if (kk >= c.k_lo && kk < c.k_hi) {
+                if (has_src && kk >= c.k_lo && kk < c.k_hi) {
                     v = c.transposed ? c.src[(size_t)(c.row0 + kk - c.k_lo) * c.ld + c.col0 + n]
                                      : c.src[(size_t)(c.row0 + n) * c.ld + c.col0 + (kk - c.k_lo)];
                 }
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ Pa
             }
             w[h] = pack_bf16(f[0], f[1]);
         }
-        *reinterpret_cast<uint4*>(packed + c.dst_off + swz_offset(n, ch)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(packed + c.dst_off + swz_offset(c.dst_row0 + n, ch)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -441,7 +444,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
         const uint32_t ready0 = cluster_addr(&bars->tile_ready[0], 0), ready1 = cluster_addr(&bars->tile_ready[1], 0);
         // chunk c of this thread's panel row lives at (panel + row_base) ^ (c << 4)  (128-byte swizzle)
         const uint32_t row_base = smem_u32(smem + kOffH) + (uint32_t)row * kRowBytes + (((uint32_t)row & 7u) << 4);
-        float sig_keep[2] = {0.f, 0.f};     // (fused evaluation) sigma of this thread's row, per slot, from the head step to the rgb step
         auto job = [&](const int x, const int g, const int s) {
             const TcStep& st = p.steps[s];
             const int kind = st.kind;
@@ -514,18 +516,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 return;
             }
             if (kind == EPI_VIEW) {
-                // ---- view layer (N = 128) + rgb head: fp32 on the un-rounded activations.  The 128 columns are split over all
+                // ---- view layer (128 columns; column 128 = sigma_pre) + rgb head: fp32 on the un-rounded activations.  The 128 columns are split over all
                 // 16 warps (32 each: half a panel), since only the rgb head and -- in training -- the stash consume them ----
                 const int tile = tile_of(2 * g + x);
                 const long long pt = (long long)tile * kTileRows + row;
                 const bool valid = pt < p.n_points;
                 const int pan = j >> 1, u0 = 2 * (j & 1);
                 float head[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t sig_raw = 0u;         // sigma_pre of this thread's row: accumulator column kSigmaCol (the head row rides this step)
                 if (!(dbg & 2)) {
                     const uint32_t vaddr = tmem + ((uint32_t)(q * 32) << 16) + x * 256 + pan * 64 + u0 * 16;
                     uint32_t rr[2][16];
                     tmem_ld16_issue(vaddr, rr[0]);
                     tmem_ld16_issue(vaddr + 16, rr[1]);
+                    if (j == 0) tmem_ld1_issue(tmem + ((uint32_t)(q * 32) << 16) + x * 256 + kSigmaCol, sig_raw);
                     if (save && jx > 0) mbar_wait(&bars->stash_done[x], (jx - 1) & 1);
                     const int ray = valid ? (int)((unsigned)pt / (unsigned)p.n_samples) : 0;   // host guarantees n_points < 2^31
                     const float* vbias = p.view_bias + (size_t)ray * 128 + pan * 64 + u0 * 16;
@@ -533,6 +537,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     const uint32_t rx = (uint32_t)row & 7u;
                     tmem_ld_wait16(rr[0]);
                     tmem_ld_wait16(rr[1]);
+                    if (j == 0) tmem_ld_wait1(sig_raw);
                     if (p.vis_pre != nullptr && valid) {
                         // visibility head: the point part of the view layer (shared by every view, :691-695) leaves in bf16;
                         // this thread holds columns 32 j .. 32 j + 31 of its row
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     for (int h = 0; h < 4; ++h) s_part[((j - 1) * 128 + row) * 4 + h] = head[h];
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
-                float col[3] = {0.f, 0.f, 0.f};
+                float col[3] = {0.f, 0.f, 0.f}, sg = 0.f;
                 if (j == 0 && valid) {
 #pragma unroll
                     for (int jj = 0; jj < 3; ++jj) {
@@ -602,12 +607,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
 #pragma unroll
                         for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = col[h];
                     }
+                    float nz = 0.f;
+                    if (p.noise) nz = p.noise[pt];
+                    else if (p.use_rng) nz = p.noise_std * rng_pick(rng_normal4(p.noise_rng, (unsigned long long)pt >> 2), (unsigned long long)pt);
+                    sg = fmaxf(__uint_as_float(sig_raw) + s_misc[0] + nz, 0.f);                                   // :665-672
+                    if (p.sigma) p.sigma[pt] = sg;
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // the partial sums may be overwritten by the next head step
                 if (p.seg != nullptr && j == 0) {
                     // ---- fused evaluation: volume_rendering :430-483 on this warp's 32 consecutive samples of one ray ----
                     // (same arithmetic as composite.cu: delta :435-441, alpha :446, transmittance :447, NDC depth :495-501)
-                    const float sg = valid ? sig_keep[x] : 0.f, zz = pf_z;
+                    const float zz = pf_z;
                     const float delta = (pf_zn - zz) * pf_rc.x;
                     float zm = zz;
                     if (p.ndc) {
@@ -655,7 +665,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 }
                 return;
             }
-            // ---- last trunk layer with the sigma head (1 row) or the sigma + rgb head (4 rows): fp32 on the un-rounded activations ----
+            // ---- last trunk layer of an MLP without a view branch, with its sigma + rgb head (4 rows): fp32 on the un-rounded
+            // activations.  (With a view branch the last trunk layer is a plain EPI_RELU step and sigma rides the view step.) ----
             const int tile = tile_of(2 * g + x);
             const long long pt = (long long)tile * kTileRows + row;
             const bool valid = pt < p.n_points;
@@ -705,10 +716,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 if (save && tile < p.n_tiles)
                     *reinterpret_cast<uint2*>(p.bits + (size_t)tile * kBitsTileBytes + (size_t)st.slot * kBitsSlotBytes + row * 32 + j * 8) = make_uint2(mw[0], mw[1]);
             };
-            if (own) {
-                if (kind == EPI_RELU_HEAD1) head_units(std::integral_constant<int, 1>{});
-                else head_units(std::integral_constant<int, 4>{});
-            }
+            if (own) head_units(std::integral_constant<int, 4>{});
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -735,11 +743,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     else if (p.use_rng) nz = p.noise_std * rng_pick(rng_normal4(p.noise_rng, (unsigned long long)pt >> 2), (unsigned long long)pt);
                     const float sg = fmaxf(head[0] + nz, 0.f);                                     // :668-672
                     if (p.sigma) p.sigma[pt] = sg;
-                    sig_keep[x] = sg;
-                    if (kind == EPI_RELU_HEAD4) {
 #pragma unroll
-                        for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
-                    }
+                    for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
                 }
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // the partial sums may be overwritten by the next head step

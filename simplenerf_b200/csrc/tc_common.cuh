@@ -263,6 +263,12 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
                  : "memory");
 }
 
+// one column (the sigma column of the view step); the wait covers every load of the thread that is still in flight
+__device__ __forceinline__ void tmem_ld1_issue(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait1(uint32_t& r) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r) : : "memory"); }
+
 // ---- UMMA descriptors --------------------------------------------------------------------------------
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = 128-byte swizzle)

@@ -20,7 +20,7 @@ constexpr int kMaxChunks = 5;
 constexpr int kPanelE = 4;   // panel id of the encoding buffer
 constexpr int kPanelP = 5;   // (backward) first panel of the prologue buffer
 
-enum EpiKind : uint8_t { EPI_RELU = 0, EPI_RELU_HEAD1, EPI_RELU_HEAD4, EPI_LINEAR, EPI_VIEW, BWD_LINEAR, BWD_MASK };
+enum EpiKind : uint8_t { EPI_RELU = 0, EPI_RELU_HEAD4, EPI_LINEAR, EPI_VIEW, BWD_LINEAR, BWD_MASK };
 
 struct TcStep {
     uint32_t w_off;               // byte offset of the first weight chunk in the packed image
@@ -39,6 +39,8 @@ struct PackChunk {
     const float* src;
     int32_t ld;
     int16_t n_rows, k_lo, k_hi, col0, row0, transposed;
+    int16_t src_rows;             // rows the source really has from row0 on (the rest of n_rows is zero-filled)
+    int16_t dst_row0;             // first row inside the destination chunk image (a multiple of 8: swizzle phase)
     uint32_t dst_off;
 };
 constexpr int kMaxPack = 96;
@@ -57,6 +59,7 @@ static inline void add_chunk(TcPlan& pl, TcStep& st, int panel, int ksteps, cons
     PackChunk& c = pl.pack[pl.n_pack++];
     c.src = src; c.ld = ld; c.n_rows = (int16_t)n_rows; c.k_lo = (int16_t)k_lo; c.k_hi = (int16_t)k_hi;
     c.col0 = (int16_t)col0; c.row0 = (int16_t)row0; c.transposed = transposed ? 1 : 0;
+    c.src_rows = (int16_t)n_rows; c.dst_row0 = 0;
     c.dst_off = pl.packed_bytes;
     if (st.n_chunks == 0) st.w_off = pl.packed_bytes;
     st.panel[st.n_chunks] = (uint8_t)panel;
@@ -71,6 +74,15 @@ static inline void add_chunk(TcPlan& pl, TcStep& st, int panel, int ksteps, cons
 // time, rounded to bf16 once): the feature step, its dgrad step, its activation / gradient panels (1 KB of the 10.2 KB a
 // point moved through HBM) and its weight-gradient job are gone.  The gradients of the two original matrices follow from
 // G = dY_v^T h (accumulated by the view layer's weight-gradient job) by two small fp32 products (tc_unmerge_grads_kernel).
+// Sigma head on the tensor core (MLPs with a view branch).  sigma_pre = w_head . h8 + b_head reads the same operand as the view
+// step (the last trunk activation), so the head row rides that step as one more B row: N = 128 view columns + 16 (row 128 =
+// pts_output_linear.weight[0] in bf16, rows 129..143 zero; N % 16 == 0 for M = 256), and sigma_pre appears as accumulator
+// column 128.  An M256 pair MMA is paced by its A-operand fetch, so N = 144 costs what N = 128 did, while the last trunk
+// layer's epilogue becomes the plain packed one (it was the slowest step of the chain: fp32 bias / ReLU / dot product per
+// value, ~3 900 cycles against ~2 000).  The backward pass always treated the head that way (d h8 += d sigma_pre w_head as a
+// bf16 chunk of the first dgrad step, dW_head from the bf16 stash).
+constexpr int kViewN = 144;                                  // B rows of the view step
+constexpr int kSigmaCol = 128;                               // accumulator column of sigma_pre
 constexpr int kSlotHv = 8;                                   // activation-stash slot of the view layer's output
 constexpr int kDySlotView = 9;                               // gradient-ring slot of dY_v (2 panels)
 constexpr size_t kMergedWeightBytes = (128 * 256 + 128) * sizeof(float);   // W_vf and W_view[:, :256] b_feat, fp32, appended to the packed image
@@ -99,14 +111,26 @@ static inline TcPlan build_plan(const snerf_mlp_desc& d, const float* const* prm
             for (int j = 0; j < 4; ++j) add_chunk(pl, st, j, 4, P(2 * l), fan_in, 256, 0, 64, col + 64 * j, 0, false);
         }
     }
-    pl.fwd[m.depth - 1].kind = m.has_view ? EPI_RELU_HEAD1 : EPI_RELU_HEAD4;
+    pl.fwd[m.depth - 1].kind = m.has_view ? EPI_RELU : EPI_RELU_HEAD4;      // with a view branch the sigma head rides the view step
     pl.fwd[m.skip_layer + 1].last_e_use = 1;
     if (m.has_view) {
         TcStep& vw = pl.fwd[pl.n_fwd++];       // hv_pre = W_vf h + [per-ray bias] (+ W_view[:, enc part] E)
-        vw.n_rows = 128; vw.kind = EPI_VIEW; vw.slot = kSlotHv;
-        for (int j = 0; j < 4; ++j) add_chunk(pl, vw, j, 4, wvf, m.width, 128, 0, 64, 64 * j, 0, false);
-        if (m.enc_hi > 0) {   // points-augmentation: encoding bands trunk_degree.. feed the view layer (:633)
-            add_chunk(pl, vw, kPanelE, 4, P(SNERF_P_VIEW_W), m.view_in, 128, m.trunk_in, m.enc, m.width, 0, false);
+        vw.n_rows = kViewN; vw.kind = EPI_VIEW; vw.slot = kSlotHv;
+        // a chunk image of kViewN rows: rows 0..127 from `src`, rows 128..143 by a second entry (the sigma row or zeros)
+        auto add_view_chunk = [&](int panel, const float* src, int ld, int k_lo, int k_hi, int col0, const float* row128, int col128) {
+            add_chunk(pl, vw, panel, 4, src, ld, kViewN, k_lo, k_hi, col0, 0, false);
+            pl.pack[pl.n_pack - 1].n_rows = 128;
+            pl.pack[pl.n_pack - 1].src_rows = 128;
+            PackChunk& ex = pl.pack[pl.n_pack];
+            ex = pl.pack[pl.n_pack - 1];
+            ex.src = row128; ex.ld = m.width; ex.col0 = (int16_t)col128; ex.row0 = 0; ex.k_lo = 0; ex.k_hi = 64;
+            ex.n_rows = kViewN - 128; ex.src_rows = row128 ? 1 : 0; ex.dst_row0 = kSigmaCol;
+            ++pl.n_pack;
+        };
+        // row 128 = pts_output_linear.weight[0, 64 j .. 64 j + 63]  (layout-only plans pass a null table: nothing is read)
+        for (int j = 0; j < 4; ++j) add_view_chunk(j, wvf, m.width, 0, 64, 64 * j, prm ? P(SNERF_P_HEAD_W) : (const float*)nullptr, 64 * j);
+        if (m.enc_hi > 0) {   // points-augmentation: encoding bands trunk_degree.. feed the view layer (:633); no share in sigma
+            add_view_chunk(kPanelE, P(SNERF_P_VIEW_W), m.view_in, m.trunk_in, m.enc, m.width, nullptr, 0);
             pl.fwd[m.skip_layer + 1].last_e_use = 0;
             vw.last_e_use = 1;
         }

@@ -3,7 +3,7 @@
 # a stash of the working tree) against the working tree's build, alternating, short bench runs.  Usage (under gpurun): tools/ab.sh [tag]
 TAG=${1:-ab}
 B="python bench.py --steps 20 --warmup 5 --no-cpu --no-c5 --no-trainer --no-render"
-for i in 1 2; do
+for i in 1 2 3; do
   SNERF_B200_LIB_AB=$PWD/tools/ab/base.so $B > gpurun_out/${TAG}_base$i.json 2> gpurun_out/${TAG}_base$i.err
   $B > gpurun_out/${TAG}_new$i.json 2> gpurun_out/${TAG}_new$i.err
 done
