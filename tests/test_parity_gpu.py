@@ -776,6 +776,64 @@ def test_visibility_head_vs_oracle(ndc, precision):
     assert float(grads0[22][3].abs().max()) == 0.0          # fourth row of views_output_linear: untouched
 
 
+@pytest.mark.parametrize('nv', [0, 1, 5, 8])
+def test_visibility_head_view_counts(nv):
+    """Tensor path, other-view counts the two-views-per-pass forward kernel and the per-round shared-memory tables of the backward
+    kernel treat differently: none, one (a lone last view), an odd count, the maximum of eight; a ragged point count."""
+    from simplenerf_b200._lib import FLAG_SAVE_FOR_BWD, FLAG_VIS_GRAD, FLAG_VIS_HEAD
+    from simplenerf_b200.models.FusedSimpleNeRF01 import MlpBlock
+    mlp_cfg = dict(synthetic.make_configs('vanilla')['model']['coarse_mlp'], predict_visibility=True)
+    spec = orc.MlpSpec(mlp_cfg)
+    state = orc.deterministic_state(spec.param_shapes(), 31 + nv)
+    state['views_linears.0.weight'][:, spec.width:] *= 6
+    state['views_linears.0.weight'][:, :spec.width] *= 3
+    state['views_output_linear.weight'] *= 8
+    block = MlpBlock(mlp_cfg)
+    block.load_state_dict(state)
+    block.to(DEV)
+    gen = torch.Generator().manual_seed(40 + nv)
+    n, s = 67, 7                                                    # 469 points: not a multiple of 32, 128 or 256
+    rays_o = torch.rand((n, 3), generator=gen) - .5
+    rays_d = torch.nn.functional.normalize(torch.randn((n, 3), generator=gen), dim=-1)
+    z = torch.sort(torch.rand((n, s), generator=gen) * 3.0, -1)[0]
+    vd = torch.nn.functional.normalize(torch.randn((n, 3), generator=gen), dim=-1)
+    rays_o2 = torch.rand((n, nv, 3), generator=gen) - .5 if nv else None
+    pts = (rays_o[:, None] + rays_d[:, None] * z[..., None]).reshape(-1, 3)
+    dirs2 = orc.other_view_dirs(z, rays_o, rays_d, rays_o2, False).reshape(-1, nv, 3) if nv else None
+    params = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    out = mlp_forward_bf16(spec, params, pts, vd[:, None].expand(n, s, 3).reshape(-1, 3), None, dirs2)
+    keys = ('sigma', 'rgb', 'visibility') + (('visibility2',) if nv else ())
+    c = {k: torch.randn(out[k].shape, generator=gen) for k in keys}
+    sum((out[k] * c[k]).sum() for k in c).backward()
+
+    flags = FLAG_VIS_HEAD | FLAG_SAVE_FOR_BWD
+    table = [None if p is None else p.detach() for p in block.param_table()]
+    packed = block.packed(table)
+    ws = torch.empty(ops.mlp_workspace_bytes(block.desc, n, s, flags), dtype=torch.uint8, device=DEV)
+    sigma, rgb = ops.mlp_forward(block.desc, table, packed, cuda(rays_o), cuda(rays_d), cuda(vd), cuda(z), None, ws, flags)
+    vis, vis2, vws = ops.visibility_forward(block.desc, table, ws, cuda(rays_o), cuda(rays_d), cuda(z), None if rays_o2 is None else cuda(rays_o2), flags)
+    torch.testing.assert_close(vis.cpu().reshape(-1, 1), out['visibility'].detach(), rtol=0, atol=6e-3)
+    if nv:
+        torch.testing.assert_close(vis2.cpu().reshape(-1, nv, 1), out['visibility2'].detach(), rtol=0, atol=6e-3)
+    else:
+        assert vis2 is None
+    grads = [None if p is None else torch.zeros_like(p) for p in table]
+    ops.visibility_backward(block.desc, table, ws, cuda(rays_o), cuda(rays_d), cuda(z), None if rays_o2 is None else cuda(rays_o2), vis, vis2,
+                            cuda(c['visibility'].reshape(n, s)), cuda(c['visibility2'].reshape(n, s, nv)) if nv else None, grads, vws, flags)
+    ops.mlp_backward(block.desc, table, packed, cuda(rays_o), cuda(rays_d), cuda(vd), cuda(z), sigma, rgb, cuda(c['sigma'].reshape(n, s)),
+                     cuda(c['rgb'].reshape(n, s, 3)), grads, ws, flags | FLAG_VIS_GRAD)
+    by_ptr = {p.data_ptr(): k for k, p in block.named_parameters()}
+    for p, g in zip(table, grads):
+        if p is None:
+            continue
+        k = by_ptr[p.data_ptr()]
+        want = params[k].grad
+        rel = float((g.cpu() - want).norm() / (want.norm() + 1e-12))
+        assert rel <= 5e-2, (nv, k, rel)
+    gw, want = grads[20].cpu()[:, spec.width:], params['views_linears.0.weight'].grad[:, spec.width:]
+    assert float((gw - want).norm() / want.norm()) <= 2e-2, (nv, float((gw - want).norm() / want.norm()))
+
+
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 @pytest.mark.parametrize('tag', ['a', 'b'])
 def test_dropin_visibility_head_vs_reference_golden(tag, precision):
