@@ -222,6 +222,7 @@ struct FwdParams {
     int ndc;
     uint8_t* stash;                // null in eval
     uint8_t* bits;                 // (training) ReLU sign bits of the trunk activations, kBitsTileBytes per tile
+    int stash_pieces;              // 4 (default): the stash leaves one panel per bulk-copy request, paced; 1: one request per job (SNERF_STASH_PIECES)
     uint8_t* vis_pre;              // (visibility head, SNERF_FLAG_VIS_HEAD) bf16 [n_points,128]: the view layer's accumulator without the per-ray bias; else null
     long long* trace;              // debug: clock64 timestamps of pair 0 (tools/trace_fwd.py), normally null
     int debug;                     // debug (timing experiments, results become garbage): bit0 no panel stores, bit1 no TMEM loads / epilogue math, bit2 no weight copies
@@ -823,7 +824,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                         const uint32_t jx = (uint32_t)(g * p.n_steps + s);
                         const int tile = tile_of(2 * g + x);
                         mbar_wait_sleep(&bars->stash_ready[x], jx & 1, 64);
-                        if (tile < p.n_tiles) {
+                        if (tile < p.n_tiles && p.stash_pieces > 1) {
+                            // Paced: one 16 KB panel per request and at most two requests queued.  The weight chunks come through the same
+                            // bulk-copy unit of the SM: behind two 64 KB stores a chunk arrived up to ~2 000 cycles late (clock64 trace of the
+                            // issuer's waits, profiles/r2_weight_loader.md); behind 32 KB it does not.  Forward -6.5 %, dgrad -6.6 %.
+                            const uint32_t total = (uint32_t)(st.n_rows / 64) * kPanelBytes, piece = 65536u / (uint32_t)p.stash_pieces;
+                            for (uint32_t off = 0; off < total; off += piece) {
+                                bulk_s2g(p.stash + (size_t)tile * p.tile_stash_bytes + (size_t)st.slot * 65536 + off, smem + kOffH + x * 65536 + off, piece);
+                                bulk_commit();
+                                bulk_wait_read<1>();
+                                if (off == 0 && pending >= 0) { mbar_arrive(&bars->stash_done[pending]); pending = -1; }
+                            }
+                            if (two) pending = x;
+                            else { bulk_wait_read<0>(); mbar_arrive(&bars->stash_done[x]); }
+                        } else if (tile < p.n_tiles) {
                             bulk_s2g(p.stash + (size_t)tile * p.tile_stash_bytes + (size_t)st.slot * 65536, smem + kOffH + x * 65536,
                                      (uint32_t)(st.n_rows / 64) * kPanelBytes);
                             bulk_commit();
@@ -895,6 +909,11 @@ int tc_forward(const snerf_mlp_desc& d, const float* const* prm, const void* pac
     if (fused) {
         p.seg = fused->seg; p.alpha_out = fused->alpha; p.wloc = fused->wloc; p.ndc = fused->cam_o != nullptr ? 1 : 0;
         p.rayc = (const float4*)(wsb + w.view_bias + (size_t)n_rays * 128 * sizeof(float));
+    }
+    {
+        static int pieces = -1;
+        if (pieces < 0) { const char* e = getenv("SNERF_STASH_PIECES"); pieces = e ? atoi(e) : 4; }
+        p.stash_pieces = (pieces == 2 || pieces == 4 || pieces == 8 || pieces == 16) ? pieces : 1;
     }
     p.trace = g_trace; p.debug = g_fwd_debug;
     p.n_points = (long long)n_rays * n_samples;

@@ -47,6 +47,7 @@ struct BwdParams {
     const uint8_t* bits;          // ReLU sign bits written by the forward kernel (kBitsTileBytes per tile)
     RingCtl ring;                 // destination of the gradient panels
     const float *sigma, *rgb, *d_sigma, *d_rgb, *w_rgb;
+    int stash_pieces;              // 4: the gradient panels leave one per bulk-copy request (paced); 1: one request per job
     const float* vis_extra;        // (SNERF_FLAG_VIS_GRAD) fp32 [n_points,128]: the visibility head's share of dY_v, masks applied (vis_tc.cu); else null
     long long n_points;
     int n_tiles, n_steps, has_view;
@@ -390,7 +391,25 @@ __device__ __forceinline__ void dgrad_role(const BwdParams& p, uint8_t* smem, co
                 pending_free = false;
             };
             auto event = [&](const int x, const int tile, const int slot, const uint32_t bytes, const bool last_of_tile) {
-                if (tile < p.n_tiles) {
+                if (tile < p.n_tiles && !ring.use_flags && p.stash_pieces > 1) {
+                    // paced (see the forward kernel's stash writer): one panel per request, at most two requests queued in the SM's
+                    // bulk-copy unit, so that a weight chunk requested meanwhile is not held up behind 128 KB of stores
+                    const uint8_t* src = smem + kBOffH + x * 65536;
+                    uint8_t* dst = ring.base + ring_slot_off(slot, ring.cap) + (size_t)((uint32_t)tile % ring.cap) * ring_entry_bytes(slot);
+                    const uint32_t piece = 65536u / (uint32_t)p.stash_pieces;
+                    for (uint32_t off = 0; off < bytes; off += piece) {
+                        bulk_s2g(dst + off, src + off, piece);
+                        bulk_commit();
+                        bulk_wait_read<1>();
+                        if (off == 0 && pending >= 0) {        // every earlier request has been read: the previous slot's panels are free
+                            mbar_arrive(&bars->stash_done[pending]);
+                            if (pending_free) mbar_arrive(&bars->slot_free[pending]);
+                            pending = -1;
+                        }
+                    }
+                    pending = x;
+                    pending_free = last_of_tile;
+                } else if (tile < p.n_tiles) {
                     emit(tile, slot, smem + kBOffH + x * 65536, bytes);
                     release(true);
                     pending = x;
@@ -965,6 +984,11 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
     bp.packed = (const uint8_t*)packed; bp.act = wsb + w.act; bp.bits = wsb + w.bits;
     bp.sigma = sigma; bp.rgb = rgb; bp.d_sigma = d_sigma; bp.d_rgb = d_rgb;
     bp.w_rgb = m.has_view ? prm[SNERF_P_RGB_W] : nullptr;
+    {
+        static int pieces = -1;
+        if (pieces < 0) { const char* e = getenv("SNERF_STASH_PIECES"); pieces = e ? atoi(e) : 4; }
+        bp.stash_pieces = (pieces == 2 || pieces == 4 || pieces == 8 || pieces == 16) ? pieces : 1;
+    }
     if (flags & SNERF_FLAG_VIS_GRAD) {
         SNERF_REQUIRE((flags & SNERF_FLAG_VIS_HEAD) && m.has_view, "mlp_backward: SNERF_FLAG_VIS_GRAD on the tensor path needs the forward's SNERF_FLAG_VIS_HEAD");
         SNERF_REQUIRE(!fused, "mlp_backward: SNERF_FLAG_VIS_GRAD is not built for the one-launch form (unset SNERF_BWD_RING)");
