@@ -461,6 +461,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                     pf_rc = __ldg(p.rayc + ray);
                 }
             }
+            // training: the sigma noise of this row (Philox + Box-Muller, ~200 instructions) is drawn while the warp would otherwise
+            // wait for the accumulator, not on the critical path behind it
+            float pf_noise = 0.f;
+            if (j == 0 && (kind == EPI_VIEW || kind == EPI_RELU_HEAD4) && (p.noise != nullptr || p.use_rng)) {
+                const long long pt0 = (long long)tile_of(2 * g + x) * kTileRows + row;
+                if (pt0 < p.n_points)
+                    pf_noise = p.noise ? __ldg(p.noise + pt0)
+                                       : p.noise_std * rng_pick(rng_normal4(p.noise_rng, (unsigned long long)pt0 >> 2), (unsigned long long)pt0);
+            }
             mbar_wait(&bars->acc_full[x], jx & 1);
             tc_fence_after();
             const bool tr = kTrace && p.trace && blockIdx.x == 0 && g == 1 && warp == kWarpEpi0 && lane == 0;
@@ -608,10 +617,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
 #pragma unroll
                         for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = col[h];
                     }
-                    float nz = 0.f;
-                    if (p.noise) nz = p.noise[pt];
-                    else if (p.use_rng) nz = p.noise_std * rng_pick(rng_normal4(p.noise_rng, (unsigned long long)pt >> 2), (unsigned long long)pt);
-                    sg = fmaxf(__uint_as_float(sig_raw) + s_misc[0] + nz, 0.f);                                   // :665-672
+                    sg = fmaxf(__uint_as_float(sig_raw) + s_misc[0] + pf_noise, 0.f);                            // :665-672
                     if (p.sigma) p.sigma[pt] = sg;
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // the partial sums may be overwritten by the next head step
@@ -739,10 +745,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tc_forward_kernel(const __grid
                 }
                 head[0] += s_misc[0]; head[1] += s_misc[1]; head[2] += s_misc[2]; head[3] += s_misc[3];
                 {
-                    float nz = 0.f;
-                    if (p.noise) nz = p.noise[pt];
-                    else if (p.use_rng) nz = p.noise_std * rng_pick(rng_normal4(p.noise_rng, (unsigned long long)pt >> 2), (unsigned long long)pt);
-                    const float sg = fmaxf(head[0] + nz, 0.f);                                     // :668-672
+                    const float sg = fmaxf(head[0] + pf_noise, 0.f);                               // :668-672
                     if (p.sigma) p.sigma[pt] = sg;
 #pragma unroll
                     for (int h = 0; h < 3; ++h) p.rgb[pt * 3 + h] = sigmoid_acc(head[1 + h]);     // :676-680
