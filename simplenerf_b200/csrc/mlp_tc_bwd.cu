@@ -1090,12 +1090,16 @@ int tc_backward(const snerf_mlp_desc& d, const float* const* prm, const void* pa
             const WgJob& jb = wp.jobs[j];
             // measured with tools/wgrad_balance.py (cycles of work per tile, relative): streaming dominates, the
             // recomputed encodings and the CUDA-core head matrices add their own latency
+            // (re-measured at the end of round 2, work per job = sum of its CTAs' cycles, streaming job = 100: layer 0 147-150, skip layer's
+            // hidden part 103-109, its encoding part 135-140, view job + head 184 / 275 with the point encodings, head matrix alone 160,
+            // rgb matrix 116-118)
             cost[j] = (jb.a_panels + jb.b_panels) * 12.5;                             // streaming job: 100 for 4 + 4 panels
-            if (jb.kind == 0 && jb.b_panels == 0) cost[j] = 142.0;                    // dY x encoding only (encoder-bound)
-            if (jb.kind == 0 && jb.a_panels == 2) cost[j] = jb.b_enc ? 195.0 : 128.0; // view job: recomputed view-dir (+ point) encoding
-            if (jb.with_head) cost[j] += 73.0;
-            if (jb.kind == 1) cost[j] = 149.0;
-            if (jb.kind == 2) cost[j] = 112.0;
+            if (jb.kind == 0 && jb.b_panels == 4 && jb.seg[0].dst_col > 0) cost[j] = 105.0;   // skip layer, hidden part (offset columns)
+            if (jb.kind == 0 && jb.b_panels == 0) cost[j] = jb.db != nullptr ? 147.0 : 137.0; // dY x encoding only (encoder-bound): layer 0 / skip layer
+            if (jb.kind == 0 && jb.a_panels == 2) cost[j] = jb.b_enc ? 219.0 : 128.0; // view job: recomputed view-dir (+ point) encoding
+            if (jb.with_head) cost[j] += 56.0;
+            if (jb.kind == 1) cost[j] = 160.0;
+            if (jb.kind == 2) cost[j] = 117.0;
             total += cost[j];
         }
         int n[kMaxJobs], used = 0;
