@@ -47,3 +47,5 @@ for name, key, s in (('fine', 'fine_mlp', 192), ('views-aug', None, 64), ('pts-a
         jobs.setdefault(int(t[cta, 0]), []).append(int(t[cta, 1]))
     for j, v in sorted(jobs.items()):
         print(f'  job {j:2d}: {len(v):3d} CTAs, cycles min {min(v)} max {max(v)}  -> work {sum(v) / 1e6:.2f} Mcyc')
+        if max(v) > 1.1 * min(v):      # uneven inside one job: every CTA (in CTA order), kilo-cycles
+            print('           per CTA:', [c // 1000 for c in v])
