@@ -29,6 +29,13 @@ def test_header_symbols_are_exported(lib):
     assert lib.snerf_abi_version() == 1
 
 
+def test_flag_values_match_the_header():
+    header = open(os.path.join(ROOT, 'include', 'simplenerf_b200.h')).read()
+    declared = {name: int(val) for name, val in re.findall(r'#define\s+SNERF_(FLAG_[A-Z_]+)\s+(\d+)u', header)}
+    assert declared and all(getattr(_lib, name) == val for name, val in declared.items()), declared
+    assert len(set(declared.values())) == len(declared) and all(v & (v - 1) == 0 for v in declared.values())     # distinct single bits
+
+
 def test_argument_validation_without_gpu(lib):
     assert lib.snerf_sample_coarse(None, None, None, None, None, 4, 64, 0, None) == 1
     assert b'null' in lib.snerf_last_error()
